@@ -1,0 +1,307 @@
+// K1-K4: flat-arena kernels of the Neumann / CG / finite-difference K-loops.
+//
+// All vectors (v, p, x, r, hv) are fp32 arenas with the lower problem's parameters laid out back to
+// back, every tensor's offset rounded up to 4 floats, padding zero -- so each kernel is a pure
+// 128-bit streaming pass and the dot products need no masking.  CG's alpha/beta and the finite
+// difference eps never leave the device (the reference does a host sync per call, darts.py:35).
+//
+//   K1  bb_neumann_update   v <- v - alpha*hv ; p <- p + v              (reference neumann.py:63-64)
+//   K2  bb_cg_dots          rr = r.r (first iter), php=(cg_alpha*hp).p ; alpha = rr/php   (cg.py:42-47)
+//   K3  bb_cg_update_xr     x += alpha p ; r -= alpha hp ; rr' = r.r ; beta = rr'/rr      (cg.py:49-52)
+//       bb_cg_update_p      p <- r + beta p                                                (cg.py:53)
+//   K4  bb_mt_sumsq / bb_fd_eps / bb_mt_axpby / bb_mt_fd_combine                            (darts.py:30-67)
+#include "bb_common.cuh"
+#include "../../include/betty_b200.h"
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kBlocksPerSM = 4;
+constexpr int kMaxGrid = BB_SM_COUNT * kBlocksPerSM;  // 592 persistent-ish blocks, grid-stride
+
+inline int grid_for(int64_t n4) {
+  int64_t want = (n4 + kThreads - 1) / kThreads;
+  if (want < 1) want = 1;
+  if (want > kMaxGrid) want = kMaxGrid;
+  return (int)want;
+}
+
+// ---- K1 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) neumann_update_kernel(float* __restrict__ v, float* __restrict__ p,
+                                                                  const float* __restrict__ hv, float alpha,
+                                                                  float shift, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = bb::ld4(v + 4 * i);
+    const float4 h = bb::ld4_stream(hv + 4 * i);
+    float4 q = bb::ld4(p + 4 * i);
+    // v - alpha*(hv + shift*v): `shift` folds a declared c*I curvature term into the update
+    a.x = a.x - alpha * (h.x + shift * a.x);
+    a.y = a.y - alpha * (h.y + shift * a.y);
+    a.z = a.z - alpha * (h.z + shift * a.z);
+    a.w = a.w - alpha * (h.w + shift * a.w);
+    q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+    bb::st4(v + 4 * i, a);
+    bb::st4(p + 4 * i, q);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) scale_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                         float c, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = bb::ld4(in + 4 * i);
+    a.x *= c; a.y *= c; a.z *= c; a.w *= c;
+    bb::st4(out + 4 * i, a);
+  }
+}
+
+// ---- K2 -------------------------------------------------------------------------------------
+struct Ws {
+  bb_kloop_scalars* s;
+  unsigned int* ticket;
+  double* partials;  // 2 * kMaxGrid (overwritten by every reduction)
+  double* slots;     // kMaxGrid accumulation slots, kept zero between launches
+};
+
+__device__ __forceinline__ Ws ws_view(void* ws) {
+  Ws w;
+  char* b = reinterpret_cast<char*>(ws);
+  w.s = reinterpret_cast<bb_kloop_scalars*>(b);
+  w.ticket = reinterpret_cast<unsigned int*>(b + 256);
+  w.partials = reinterpret_cast<double*>(b + 512);
+  w.slots = w.partials + 2 * kMaxGrid;
+  return w;
+}
+
+__global__ void __launch_bounds__(kThreads) cg_dots_kernel(const float* __restrict__ r, const float* __restrict__ hp,
+                                                           const float* __restrict__ p, float cg_alpha,
+                                                           int first, int64_t n4, void* wsraw) {
+  __shared__ double red[32];
+  Ws w = ws_view(wsraw);
+  float acc_php = 0.f, acc_rr = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 h = bb::ld4(hp + 4 * i);
+    const float4 q = bb::ld4(p + 4 * i);
+    acc_php += (cg_alpha * h.x) * q.x + (cg_alpha * h.y) * q.y + (cg_alpha * h.z) * q.z + (cg_alpha * h.w) * q.w;
+    if (first) {
+      const float4 a = bb::ld4(r + 4 * i);
+      acc_rr += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+  }
+  double b_php = bb::block_sum<double>((double)acc_php, red);
+  double b_rr = first ? bb::block_sum<double>((double)acc_rr, red) : 0.0;
+  // two partial arrays; one ticket covers both
+  if (threadIdx.x == 0 && first) w.partials[kMaxGrid + blockIdx.x] = b_rr;
+  double php;
+  if (bb::grid_sum_finish(b_php, w.partials, w.ticket, &php, red)) {
+    if (first) {
+      double rr = 0.0;
+      for (unsigned int i = 0; i < gridDim.x; ++i) rr += w.partials[kMaxGrid + i];
+      w.s->rr = rr;
+    }
+    w.s->php = php;
+    w.s->alpha = w.s->rr / php;
+  }
+}
+
+// ---- K3 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) cg_update_xr_kernel(float* __restrict__ x, float* __restrict__ r,
+                                                                const float* __restrict__ p,
+                                                                const float* __restrict__ hp, int64_t n4,
+                                                                void* wsraw) {
+  __shared__ double red[32];
+  Ws w = ws_view(wsraw);
+  const float alpha = (float)w.s->alpha;
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 xx = bb::ld4(x + 4 * i);
+    float4 rr = bb::ld4(r + 4 * i);
+    const float4 q = bb::ld4(p + 4 * i);
+    const float4 h = bb::ld4_stream(hp + 4 * i);
+    xx.x += alpha * q.x; xx.y += alpha * q.y; xx.z += alpha * q.z; xx.w += alpha * q.w;
+    rr.x -= alpha * h.x; rr.y -= alpha * h.y; rr.z -= alpha * h.z; rr.w -= alpha * h.w;
+    acc += rr.x * rr.x + rr.y * rr.y + rr.z * rr.z + rr.w * rr.w;
+    bb::st4(x + 4 * i, xx);
+    bb::st4(r + 4 * i, rr);
+  }
+  double b = bb::block_sum<double>((double)acc, red);
+  double rr_new;
+  if (bb::grid_sum_finish(b, w.partials, w.ticket, &rr_new, red)) {
+    w.s->rr_new = rr_new;
+    w.s->beta = rr_new / w.s->rr;
+    w.s->rr = rr_new;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) cg_update_p_kernel(float* __restrict__ p, const float* __restrict__ r,
+                                                               int64_t n4, const void* wsraw) {
+  const float beta = (float)reinterpret_cast<const bb_kloop_scalars*>(wsraw)->beta;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 rr = bb::ld4(r + 4 * i);
+    float4 q = bb::ld4(p + 4 * i);
+    q.x = rr.x + beta * q.x; q.y = rr.y + beta * q.y; q.z = rr.z + beta * q.z; q.w = rr.w + beta * q.w;
+    bb::st4(p + 4 * i, q);
+  }
+}
+
+// ---- K4 + arena packing: multi-tensor kernels driven by a chunk table -----------------------
+// table[c] = {a, b, n}: chunk c covers n (<= BB_MT_CHUNK) floats at a / b.
+constexpr int kMtThreads = 256;
+
+__global__ void __launch_bounds__(kMtThreads) mt_copy_kernel(const bb_mt_chunk* __restrict__ tab, int dir) {
+  const bb_mt_chunk c = tab[blockIdx.x];
+  const float* src = reinterpret_cast<const float*>(dir == 0 ? c.a : c.b);
+  float* dst = reinterpret_cast<float*>(dir == 0 ? c.b : c.a);
+  for (int i = threadIdx.x; i < c.n; i += kMtThreads) dst[i] = src[i];
+}
+
+// b <- coef_a * scale_dev * a + coef_b * b   (scale_dev may be null => 1; a may alias b)
+__global__ void __launch_bounds__(kMtThreads) mt_axpby_kernel(const bb_mt_chunk* __restrict__ tab, float coef_a,
+                                                              const double* __restrict__ scale_dev, float coef_b) {
+  const bb_mt_chunk c = tab[blockIdx.x];
+  const float s = coef_a * (scale_dev ? (float)(*scale_dev) : 1.f);
+  const float* a = reinterpret_cast<const float*>(c.a);
+  float* b = reinterpret_cast<float*>(c.b);
+  if (coef_b == 0.f) {
+    for (int i = threadIdx.x; i < c.n; i += kMtThreads) b[i] = s * a[i];
+  } else {
+    for (int i = threadIdx.x; i < c.n; i += kMtThreads) b[i] = s * a[i] + coef_b * b[i];
+  }
+}
+
+__global__ void __launch_bounds__(kMtThreads) mt_sumsq_kernel(const bb_mt_chunk* __restrict__ tab, void* wsraw) {
+  __shared__ double red[32];
+  Ws w = ws_view(wsraw);
+  const bb_mt_chunk c = tab[blockIdx.x];
+  const float* a = reinterpret_cast<const float*>(c.a);
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < c.n; i += kMtThreads) acc += a[i] * a[i];
+  double b = bb::block_sum<double>((double)acc, red);
+  // chunk count can exceed kMaxGrid: accumulate with a fixed-order scheme per slot
+  if (threadIdx.x == 0) atomicAdd(&w.slots[blockIdx.x % kMaxGrid], b);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(w.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (int i = 0; i < kMaxGrid; ++i) {
+      s += w.slots[i];
+      w.slots[i] = 0.0;
+    }
+    w.s->sumsq = s;
+    *w.ticket = 0u;
+  }
+}
+
+__global__ void fd_eps_kernel(void* wsraw, double darts_alpha) {
+  bb_kloop_scalars* s = reinterpret_cast<bb_kloop_scalars*>(wsraw);
+  // reference darts.py:30-35: eps = R / (||v|| + 1e-15); fp32 norm in the reference
+  const float nrm = sqrtf((float)s->sumsq);
+  s->eps = darts_alpha / ((double)nrm + 1e-15);
+  s->inv_2eps = 1.0 / (2.0 * s->eps);
+}
+
+// out(a) = (a - b) * inv_2eps   (a = g_minus, b = g_plus, in place on a)
+__global__ void __launch_bounds__(kMtThreads) mt_fd_combine_kernel(const bb_mt_chunk* __restrict__ tab,
+                                                                   const void* wsraw) {
+  const float s = (float)reinterpret_cast<const bb_kloop_scalars*>(wsraw)->inv_2eps;
+  const bb_mt_chunk c = tab[blockIdx.x];
+  float* a = reinterpret_cast<float*>(c.a);
+  const float* b = reinterpret_cast<const float*>(c.b);
+  for (int i = threadIdx.x; i < c.n; i += kMtThreads) a[i] = (a[i] - b[i]) * s;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int bb_kloop_ws_bytes(void) { return 512 + 3 * kMaxGrid * (int)sizeof(double); }
+
+int bb_neumann_update(float* v, float* p, const float* hv, float alpha, float shift, int64_t n, void* stream) {
+  if ((n & 3) != 0) return BB_ERR_ARG;
+  if (n == 0) return BB_OK;
+  const int64_t n4 = n >> 2;
+  neumann_update_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(v, p, hv, alpha, shift, n4);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_scale(float* out, const float* in, float c, int64_t n, void* stream) {
+  if ((n & 3) != 0) return BB_ERR_ARG;
+  if (n == 0) return BB_OK;
+  const int64_t n4 = n >> 2;
+  scale_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(out, in, c, n4);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, int first, int64_t n, void* ws,
+               void* stream) {
+  if ((n & 3) != 0) return BB_ERR_ARG;
+  const int64_t n4 = n >> 2;
+  cg_dots_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(r, hp, p, cg_alpha, first, n4, ws);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_cg_update_xr(float* x, float* r, const float* p, const float* hp, int64_t n, void* ws, void* stream) {
+  if ((n & 3) != 0) return BB_ERR_ARG;
+  const int64_t n4 = n >> 2;
+  cg_update_xr_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(x, r, p, hp, n4, ws);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_cg_update_p(float* p, const float* r, int64_t n, const void* ws, void* stream) {
+  if ((n & 3) != 0) return BB_ERR_ARG;
+  const int64_t n4 = n >> 2;
+  cg_update_p_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(p, r, n4, ws);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_mt_copy(const bb_mt_chunk* table_dev, int nchunks, int dir, void* stream) {
+  if (nchunks <= 0) return BB_OK;
+  mt_copy_kernel<<<nchunks, kMtThreads, 0, (cudaStream_t)stream>>>(table_dev, dir);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_mt_axpby(const bb_mt_chunk* table_dev, int nchunks, float coef_a, const double* scale_dev, float coef_b,
+                void* stream) {
+  if (nchunks <= 0) return BB_OK;
+  mt_axpby_kernel<<<nchunks, kMtThreads, 0, (cudaStream_t)stream>>>(table_dev, coef_a, scale_dev, coef_b);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_mt_sumsq(const bb_mt_chunk* table_dev, int nchunks, void* ws, void* stream) {
+  if (nchunks <= 0) return BB_ERR_ARG;
+  mt_sumsq_kernel<<<nchunks, kMtThreads, 0, (cudaStream_t)stream>>>(table_dev, ws);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_fd_eps(void* ws, double darts_alpha, void* stream) {
+  fd_eps_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ws, darts_alpha);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_mt_fd_combine(const bb_mt_chunk* table_dev, int nchunks, const void* ws, void* stream) {
+  if (nchunks <= 0) return BB_OK;
+  mt_fd_combine_kernel<<<nchunks, kMtThreads, 0, (cudaStream_t)stream>>>(table_dev, ws);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+}  // extern "C"

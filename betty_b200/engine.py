@@ -1,0 +1,207 @@
+"""Call-level orchestration shared by the neumann / cg plugins.
+
+One hypergradient call =
+  prologue   lower forward on ``curr.cur_batch`` (recorded as an op tape when the native HVP is on)
+             and ``g = grad_w L_in`` with a graph           (reference neumann.py:31-36, cg.py:27-32)
+  K-loop     K Hessian-vector products + vector updates      (reference neumann.py:59-66, cg.py:34-56)
+             -> CUDA: flat-arena kernels K1-K3 (csrc/kloop.cu) around either
+                  * the native second-order tape (csrc/plan.cu, K5-K9), or
+                  * (development mode ``hvp="autograd"``) torch's double backward
+  epilogue   ``-(d^2 L_in/d lambda d w)^T x`` through autograd (reference neumann.py:44-54, cg.py:58-68)
+
+There is no CPU path: everything here raises without a CUDA device.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _native as N
+from .arena import ArenaLayout, pack, stream_ptr
+
+
+@dataclass
+class Settings:
+    # "native": hand-written second-order tape; "autograd" (development only): torch double backward
+    hvp: str = os.environ.get("BB200_HVP", "native")
+    cuda_graph: bool = True   # capture one K-loop iteration and replay it
+    record_events: bool = True
+
+
+settings = Settings()
+
+
+@dataclass
+class CallStats:
+    """Filled by every call; bench.py reads the CUDA events after a synchronize."""
+    method: str = ""
+    iterations: int = 0
+    n_params: int = 0
+    ev_start: Optional[torch.cuda.Event] = None
+    ev_end: Optional[torch.cuda.Event] = None
+    plan_launches_per_iter: int = 0
+    extra: dict = field(default_factory=dict)
+
+    def kloop_ms(self) -> float:
+        self.ev_end.synchronize()
+        return self.ev_start.elapsed_time(self.ev_end)
+
+
+last_stats = CallStats()
+
+
+class Workspace:
+    """Zero-initialised device block for the K-loop scalars / reduction slots (bb_kloop_scalars)."""
+
+    _cache = {}
+
+    def __init__(self, device):
+        nbytes = N.lib().bb_kloop_ws_bytes()
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.scalars = self.buf[:64].view(torch.float64)  # rr, php, rr_new, alpha, beta, sumsq, eps, inv_2eps
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def scalar_ptr(self, idx: int) -> int:
+        return self.buf.data_ptr() + 8 * idx
+
+    @classmethod
+    def get(cls, device) -> "Workspace":
+        key = (device.type, device.index)
+        ws = cls._cache.get(key)
+        if ws is None:
+            ws = cls._cache[key] = cls(device)
+        return ws
+
+
+def lower_gradient(curr, want_tape: bool):
+    """Prologue.  Returns (in_grad, tape-or-None)."""
+    params = curr.trainable_parameters()
+    tape = None
+    if want_tape:
+        from .trace import record_tape
+
+        in_loss, tape = record_tape(lambda: curr.training_step_exec(curr.cur_batch), params)
+    else:
+        in_loss = curr.training_step_exec(curr.cur_batch)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        in_grad = torch.autograd.grad(in_loss, params, create_graph=True)
+    return in_loss, in_grad, tape
+
+
+class AutogradHvp:
+    """Development mode: H.d by torch double backward, result packed into the hv arena."""
+
+    def __init__(self, in_grad, params, layout: ArenaLayout, d_arena: torch.Tensor, hv_arena: torch.Tensor):
+        self.in_grad, self.params, self.layout = in_grad, params, layout
+        self.d_views = layout.views(d_arena)
+        self.hv_arena = hv_arena
+        self.launches_per_iter = 1
+
+    def __call__(self):
+        hv = torch.autograd.grad(self.in_grad, self.params, grad_outputs=self.d_views, retain_graph=True)
+        pack(self.layout, hv, self.hv_arena)
+
+
+def _events():
+    if not settings.record_events:
+        return None, None
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _make_hvp(curr, in_grad, tape, layout, d_arena, hv_arena):
+    if settings.hvp == "autograd":
+        return AutogradHvp(in_grad, curr.trainable_parameters(), layout, d_arena, hv_arena)
+    from .plan import HvpPlan
+
+    return HvpPlan(tape, curr.trainable_parameters(), layout, d_arena, hv_arena)
+
+
+class HypergradientCall:
+    """One ``fn(vector, curr, prev, sync)`` invocation split into its three phases so that
+    ``bench.py`` can time the K-loop alone: ``__init__`` = prologue (+ arenas, + native plan),
+    ``solve`` = K-loop, ``finish`` = epilogue."""
+
+    def __init__(self, curr, method: str):
+        N.require_cuda()
+        self.curr, self.method = curr, method
+        cfg = curr.config
+        if method == "neumann":
+            self.K, self.alpha = int(cfg.neumann_iterations), float(cfg.neumann_alpha)
+        elif method == "cg":
+            self.K, self.alpha = int(cfg.cg_iterations), float(cfg.cg_alpha)
+        else:
+            raise ValueError(method)
+        self.in_loss, self.in_grad, self.tape = lower_gradient(curr, want_tape=(settings.hvp == "native"))
+        params = curr.trainable_parameters()
+        self.dev = params[0].device
+        lay = self.layout = ArenaLayout.like(params)
+        # d = direction the HVP is taken along (v for Neumann, p for CG); hd = H.d
+        self.d, self.hd, self.acc, self.out = lay.new(self.dev), lay.new(self.dev), lay.new(self.dev), lay.new(self.dev)
+        self.r = lay.new(self.dev) if method == "cg" else None
+        self.ws = Workspace.get(self.dev)
+        self.hvp = _make_hvp(curr, self.in_grad, self.tape, lay, self.d, self.hd)
+
+    def solve(self, vector: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        global last_stats
+        lay, s, n = self.layout, stream_ptr(), self.layout.total
+        K, alpha, hvp = self.K, self.alpha, self.hvp
+        d, hd, acc = self.d, self.hd, self.acc
+        pack(lay, vector, d)
+        e0, e1 = _events()
+        if self.method == "neumann":
+            # reference neumann.py:59-66:  v <- v - alpha H v ; p <- p + v ; return alpha p
+            acc.copy_(d)
+            if e0 is not None:
+                e0.record()
+            if hasattr(hvp, "neumann_loop"):
+                hvp.neumann_loop(K, alpha, d, acc, hd)
+            else:
+                for _ in range(K):
+                    hvp()
+                    N.call("bb_neumann_update", d.data_ptr(), acc.data_ptr(), hd.data_ptr(), alpha, 0.0, n, s)
+            if e1 is not None:
+                e1.record()
+            N.call("bb_scale", self.out.data_ptr(), acc.data_ptr(), alpha, n, s)
+        else:
+            # reference cg.py:34-56 with x = acc, p = d
+            r, ws = self.r, self.ws
+            r.copy_(d)
+            acc.zero_()
+            if e0 is not None:
+                e0.record()
+            if hasattr(hvp, "cg_loop"):
+                hvp.cg_loop(K, alpha, acc, r, d, hd, ws)
+            else:
+                for k in range(K):
+                    hvp()
+                    N.call("bb_cg_dots", r.data_ptr(), hd.data_ptr(), d.data_ptr(), alpha, int(k == 0), n, ws.ptr, s)
+                    N.call("bb_cg_update_xr", acc.data_ptr(), r.data_ptr(), d.data_ptr(), hd.data_ptr(), n, ws.ptr, s)
+                    N.call("bb_cg_update_p", d.data_ptr(), r.data_ptr(), n, ws.ptr, s)
+            if e1 is not None:
+                e1.record()
+            N.call("bb_scale", self.out.data_ptr(), acc.data_ptr(), alpha, n, s)
+        last_stats = CallStats(self.method, K, lay.n_logical, e0, e1, getattr(hvp, "launches_per_iter", 0))
+        return lay.views(self.out)
+
+    def finish(self, prev, x, sync):
+        return mixed_product(self.in_grad, prev, x, sync)
+
+
+def mixed_product(in_grad, prev, x: Sequence[torch.Tensor], sync: bool):
+    """Epilogue: -(d^2 L_in / d lambda d w)^T x.  ``sync`` accumulates into ``.grad`` through
+    ``torch.autograd.backward`` so the upper module's DDP reducer averages it across ranks
+    (reference neumann.py:44-54, cg.py:58-68)."""
+    lam = prev.trainable_parameters()
+    if sync:
+        torch.autograd.backward(in_grad, inputs=lam, grad_tensors=[-xi for xi in x])
+        return None
+    out = torch.autograd.grad(in_grad, lam, grad_outputs=list(x))
+    return [-g for g in out]

@@ -1,0 +1,37 @@
+"""Drop-in replacements for ``betty.hypergradient.{neumann, cg, darts}`` (+ the ``finite_diff`` alias
+named by BASELINE.json; the reference calls the same algorithm ``darts``).
+
+``install()`` rebinds the reference's plugin table in place, so ``Engine`` / ``ImplicitProblem`` and
+the ``Config(type=...)`` selector are used unchanged (reference betty/hypergradient/__init__.py:13-19).
+"""
+from .cg import cg
+from .darts import darts
+from .neumann import neumann
+
+finite_diff = darts
+
+jvp_fn_mapping = {"darts": darts, "finite_diff": darts, "neumann": neumann, "cg": cg}
+
+
+def get_grads(loss, path, retain_graph, do_sync):
+    """Mirror of reference ``betty/hypergradient/__init__.py:22-39`` over this package's table (used
+    when the reference is not importable, e.g. on the GPU box)."""
+    import torch
+
+    lower = path[1].meta_trainable_parameters()
+    jvp = torch.autograd.grad(loss, lower, retain_graph=retain_graph, allow_unused=True)
+    jvp = tuple(torch.zeros_like(p) if g is None else g for g, p in zip(jvp, lower))
+    for i in range(1, len(path) - 1):
+        kind = path[i].config.type
+        assert kind in jvp_fn_mapping
+        sync = bool(do_sync and i == len(path) - 2)
+        jvp = jvp_fn_mapping[kind](jvp, path[i], path[i + 1], sync)
+    return jvp
+
+
+def install(reference_module=None):
+    """Rebind ``betty.hypergradient.jvp_fn_mapping`` entries to the B200 engine.  Returns the table."""
+    if reference_module is None:
+        import betty.hypergradient as reference_module  # the user's installed reference
+    reference_module.jvp_fn_mapping.update(jvp_fn_mapping)
+    return reference_module.jvp_fn_mapping

@@ -1,0 +1,96 @@
+/* betty_b200 -- C ABI of the B200-native hypergradient engine.
+ *
+ * The reference (leopard-ai/betty) has NO native layer and no FFI: its extension point for this path
+ * is the Python plugin table `jvp_fn_mapping[Config.type](vector, curr, prev, sync)`
+ * (reference betty/hypergradient/__init__.py:13-19,33-37).  This header is therefore the engine's own
+ * boundary: plain pointers, sizes and a `cudaStream_t` passed as `void*`; no torch types.  The Python
+ * plugins in betty_b200/hypergradient bind it through ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).  Every entry point returns 0 on success, a negative BB_ERR_* code
+ * for argument errors, or a positive cudaError_t.  Nothing here allocates inside the K-loop.
+ *
+ * Each group cites the reference computation it replaces.
+ */
+#ifndef BETTY_B200_H
+#define BETTY_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- workspace shared by the K-loop kernels (device memory, zero-initialised by the caller) ---- */
+typedef struct {
+  double rr;       /* r.r                        reference cg.py:45   */
+  double php;      /* (cg_alpha*Hp).p            reference cg.py:46   */
+  double rr_new;   /* r'.r'                      reference cg.py:52   */
+  double alpha;    /* rr / php                   reference cg.py:47   */
+  double beta;     /* rr_new / rr                reference cg.py:52   */
+  double sumsq;    /* ||v||^2                    reference darts.py:30 */
+  double eps;      /* darts_alpha/(||v||+1e-15)  reference darts.py:35 */
+  double inv_2eps; /* 1/(2 eps)                  reference darts.py:45,53,67 */
+} bb_kloop_scalars;
+
+int bb_kloop_ws_bytes(void); /* scalars at offset 0, tickets at 256, reduction slots from 512 */
+
+/* ---- K1: Neumann accumulate.  Replaces reference neumann.py:63-64 (two list comprehensions, three
+ *      elementwise launches + two allocations per parameter tensor).  n % 4 == 0.
+ *      v <- v - alpha*(hv + shift*v);  p <- p + v                                              */
+int bb_neumann_update(float* v, float* p, const float* hv, float alpha, float shift, int64_t n, void* stream);
+/* out <- c * in   (final alpha*p, reference neumann.py:66; cg_alpha*x, reference cg.py:56) */
+int bb_scale(float* out, const float* in, float c, int64_t n, void* stream);
+
+/* ---- K2/K3: conjugate-gradient inner products and updates.  Replaces reference cg.py:42-53
+ *      (three to_vec concatenations, three dots, three list-comprehension AXPYs per iteration).
+ *      alpha and beta stay in `ws`; `first` != 0 also computes rr = r.r.                        */
+int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, int first, int64_t n, void* ws,
+               void* stream);
+int bb_cg_update_xr(float* x, float* r, const float* p, const float* hp, int64_t n, void* ws, void* stream);
+int bb_cg_update_p(float* p, const float* r, int64_t n, const void* ws, void* stream);
+
+/* ---- K4 + packing: multi-tensor kernels over a chunk table.  Replaces reference darts.py:30-38,
+ *      49-50,61-67 (per-tensor add_/sub_ loops, to_vec().norm().item(), (x-y).div_(2 eps)).      */
+#define BB_MT_CHUNK 16384
+typedef struct {
+  void* a;
+  void* b;
+  int32_t n; /* <= BB_MT_CHUNK floats */
+  int32_t pad;
+} bb_mt_chunk;
+int bb_mt_copy(const bb_mt_chunk* table_dev, int nchunks, int dir /*0: a->b, 1: b->a*/, void* stream);
+/* b <- coef_a * (*scale_dev) * a + coef_b * b   (scale_dev may be NULL => 1) */
+int bb_mt_axpby(const bb_mt_chunk* table_dev, int nchunks, float coef_a, const double* scale_dev, float coef_b,
+                void* stream);
+int bb_mt_sumsq(const bb_mt_chunk* table_dev, int nchunks, void* ws, void* stream); /* -> ws.sumsq */
+int bb_fd_eps(void* ws, double darts_alpha, void* stream);                          /* -> ws.eps, inv_2eps */
+/* a <- (a - b) * ws.inv_2eps */
+int bb_mt_fd_combine(const bb_mt_chunk* table_dev, int nchunks, const void* ws, void* stream);
+
+/* ---- K5-K9: second-order tape ("HVP plan").  Replaces reference neumann.py:62 / cg.py:39-41
+ *      (torch.autograd.grad(in_grad, params, grad_outputs=v, retain_graph=True): reverse-over-reverse
+ *      through the retained autograd graph) with forward-over-reverse over a recorded op list.
+ *      See betty_b200/csrc/plan.h for the node descriptor.                                        */
+struct bb_node;
+typedef struct bb_plan bb_plan;
+#define BB_PASS_BASE_BWD 0 /* delta from the loss seed, once per call                */
+#define BB_PASS_TAN_FWD 1  /* tangents along the direction arena                     */
+#define BB_PASS_TAN_BWD 2  /* adjoint-tangents -> Hv slices of the hv arena          */
+int bb_node_bytes(void);
+int bb_plan_create(const struct bb_node* nodes, int n_nodes, bb_plan** out);
+int bb_plan_destroy(bb_plan* plan);
+int bb_plan_set_zero_regions(bb_plan* plan, int pass, void* const* ptrs, const int64_t* bytes, int n);
+int bb_plan_run(bb_plan* plan, int pass, void* stream);
+int bb_plan_launch_count(const bb_plan* plan, int pass);
+/* one H.d product: zero regions, tangent forward, tangent backward */
+int bb_plan_hvp(bb_plan* plan, void* stream);
+/* whole K-loops, captured once into a CUDA graph and replayed (direction arena `d`, result `hv`) */
+int bb_plan_neumann_loop(bb_plan* plan, int iterations, float alpha, float* v /*direction*/, float* p,
+                         const float* hv, int64_t n, int use_graph, void* stream);
+int bb_plan_cg_loop(bb_plan* plan, int iterations, float cg_alpha, float* x, float* r, float* p /*direction*/,
+                    const float* hp, int64_t n, void* ws, int use_graph, void* stream);
+
+const char* bb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

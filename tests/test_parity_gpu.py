@@ -1,0 +1,75 @@
+"""GPU parity: engine plugins vs (i) the oracle port run on the same device and (ii) the golden vectors
+the real reference produced on CPU (tests/golden, made by oracle/make_golden.py).
+Tolerance: rtol 1e-4 fp32 (BASELINE.json north_star), protocol of SURVEY.md §8(c)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from betty_b200 import engine as E
+from betty_b200 import hypergradient as H
+from betty_b200 import workloads as W
+from oracle import ref_port
+from tests.helpers import GOLDEN, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+@pytest.fixture(params=["autograd", "native"])
+def hvp_mode(request):
+    old = E.settings.hvp
+    E.settings.hvp = request.param
+    yield request.param
+    E.settings.hvp = old
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_engine_matches_reference_golden(case, hvp_mode):
+    rec = load_golden(case)
+    wl = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
+    got = H.jvp_fn_mapping[rec["method"]](wl.vector, wl.lower, wl.upper, False)
+    assert_close(got, rec["hypergrad"], 1e-4, f"{case}[{hvp_mode}]")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_engine_matches_oracle_same_device(case, hvp_mode):
+    rec = load_golden(case)
+    wl = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
+    want = ref_port.METHODS[rec["method"]](wl.vector, wl.lower, wl.upper, False)
+    w_before = [p.detach().clone() for p in wl.lower.parameters()]
+    got = H.jvp_fn_mapping[rec["method"]](wl.vector, wl.lower, wl.upper, False)
+    assert_close(got, want, 1e-4, f"{case}[{hvp_mode}]")
+    # inputs are borrowed: parameters restored / untouched (SURVEY §8b ownership)
+    for a, b in zip(wl.lower.parameters(), w_before):
+        assert torch.allclose(a, b, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("method", ["neumann", "cg", "darts"])
+def test_sync_accumulates_into_upper_grads(method, hvp_mode):
+    wl = W.logistic_hpo(device="cuda", method=method, K=4)
+    want = H.jvp_fn_mapping[method](wl.vector, wl.lower, wl.upper, False)
+    for p in wl.upper.trainable_parameters():
+        p.grad = torch.ones_like(p)  # pre-existing grads must be accumulated into, not replaced
+    assert H.jvp_fn_mapping[method](wl.vector, wl.lower, wl.upper, True) is None
+    got = [p.grad - 1 for p in wl.upper.trainable_parameters()]
+    assert_close(got, want, 1e-5, f"sync {method}")
+
+
+def test_get_grads_walks_the_path(hvp_mode):
+    wl = W.logistic_hpo(device="cuda", method="cg", K=6)
+    x, y = wl.lower.cur_batch
+    upper_loss = torch.nn.functional.binary_cross_entropy_with_logits(wl.lower.module(x)[0], y)
+    path = [wl.upper, wl.lower, wl.upper]
+    got = H.get_grads(upper_loss, path, True, False)
+    v = torch.autograd.grad(upper_loss, wl.lower.trainable_parameters())
+    want = ref_port.cg(v, wl.lower, wl.upper, False)
+    assert_close(got, want, 1e-4, "get_grads")
