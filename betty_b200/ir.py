@@ -1,0 +1,483 @@
+"""Second-order tape IR: the recorded aten ops lowered to a small set of nodes, each with three rules
+
+    TF  tangent forward        t_y   = J_x(x) t_x                       (R-forward of SURVEY.md App. B)
+    BB  base backward          a_x  += J_x(x)^T a_y                     (delta, once per call)
+    TB  tangent backward       at_x += J^T at_y + (dJ^T/dx . t_x) a_y   (R-backward -> H.v slices)
+
+Every lower-active value carries four same-shaped tensors: ``base`` (recorded by the forward, fp32 or
+bf16 under autocast), ``t`` (tangent), ``a`` (adjoint, delta) and ``at`` (adjoint tangent); the
+last three are fp32.  A parameter's ``t`` is its slice of the direction arena and its ``at`` is its
+slice of the H.d arena, so the K-loop kernels read/write them with no gather/scatter.
+
+View ops (view/transpose/select/...) create *aliases*: their buffers are the same view applied to the
+parent's buffers, so they cost nothing in any pass.  Because adjoints reach a buffer through aliases
+from several consumers, adjoint writes either overwrite (``beta=0``: the buffer has exactly one writer
+and it covers the whole buffer) or accumulate into a buffer zeroed at the start of the pass.
+
+The node rules are implemented twice: in CUDA (``csrc/*.cu``, the product) and in torch
+(``oracle/plan_interp.py``, test infrastructure that checks this file's lowering and the rule maths on
+CPU against autograd's double backward).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+
+class UnsupportedGraph(NotImplementedError):
+    """Raised when the lower forward contains an op the engine has no second-order rule for.
+    There is deliberately no fallback (BASELINE.json north_star)."""
+
+
+class Val:
+    """A lower-active tensor value."""
+
+    __slots__ = ("vid", "base", "param_index", "parent", "viewfn", "full_cover", "name", "t", "a", "at",
+                 "writers", "needed", "zero_init")
+
+    def __init__(self, vid, base, param_index=None, parent=None, viewfn=None, full_cover=True, name=""):
+        self.vid = vid
+        self.base = base
+        self.param_index = param_index      # index into the lower parameter list, or None
+        self.parent: Optional["Val"] = parent
+        self.viewfn: Optional[Callable] = viewfn
+        self.full_cover = full_cover        # does this alias cover every element of its parent exactly once?
+        self.name = name
+        self.t = self.a = self.at = None    # root buffers, filled by the executor
+        self.writers = 0                    # adjoint writers reaching this root (through aliases)
+        self.needed = False
+        self.zero_init = False              # root adjoint buffers must be zeroed before BB / TB
+
+    @property
+    def root(self) -> "Val":
+        v = self
+        while v.parent is not None:
+            v = v.parent
+        return v
+
+    @property
+    def is_param(self) -> bool:
+        return self.root.param_index is not None and self.parent is None
+
+    def chain_full_cover(self) -> bool:
+        v, ok = self, True
+        while v.parent is not None:
+            ok = ok and v.full_cover
+            v = v.parent
+        return ok
+
+    @property
+    def shape(self):
+        return tuple(self.base.shape)
+
+    def __repr__(self):
+        return f"Val#{self.vid}{tuple(self.base.shape)}{'P' if self.param_index is not None else ''}"
+
+
+@dataclass
+class Node:
+    op: str
+    ins: List[Optional[Val]]            # active inputs; None where that operand is a constant
+    out: Optional[Val]
+    attrs: Dict[str, Any] = field(default_factory=dict)
+    beta: List[int] = field(default_factory=list)   # per input: 0 overwrite / 1 accumulate (adjoint writes)
+    src: str = ""                                    # aten op it came from
+
+    def __repr__(self):
+        return f"Node({self.op}, ins={self.ins}, out={self.out})"
+
+
+@dataclass
+class Graph:
+    nodes: List[Node]
+    values: List[Val]
+    params: List[Val]
+    loss: Val
+    stats: Dict[str, int] = field(default_factory=dict)
+
+
+# --------------------------------------------------------------------------------------------------
+# lowering
+# --------------------------------------------------------------------------------------------------
+_VIEW_OPS = {
+    # name -> full_cover
+    "aten.view.default": True, "aten._unsafe_view.default": True, "aten.reshape.default": True,
+    "aten.t.default": True, "aten.transpose.int": True, "aten.permute.default": True,
+    "aten.unsqueeze.default": True, "aten.squeeze.dim": True, "aten.squeeze.default": True,
+    "aten.alias.default": True, "aten.select.int": False, "aten.slice.Tensor": False,
+    "aten.expand.default": True, "aten.flatten.using_ints": True,
+}
+_UNARY = {"aten.relu.default": "relu", "aten.gelu.default": "gelu", "aten.tanh.default": "tanh",
+          "aten.sigmoid.default": "sigmoid", "aten.neg.default": "neg"}
+_BN_OPS = ("aten.native_batch_norm.default", "aten._native_batch_norm_legit.default",
+           "aten._native_batch_norm_legit_no_stats.default", "aten.cudnn_batch_norm.default",
+           "aten._native_batch_norm_legit.no_stats", "aten._batch_norm_with_update.default",
+           "aten.miopen_batch_norm.default")
+
+
+def _is_dense(t: torch.Tensor) -> bool:
+    """non-overlapping and dense: some permutation of the dims is contiguous"""
+    if t.numel() <= 1:
+        return True
+    dims = sorted([(st, sz) for sz, st in zip(t.shape, t.stride()) if sz != 1])
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+class _Lowering:
+    def __init__(self, tape):
+        self.tape = tape
+        self.vals: Dict[int, Val] = {}
+        self.all_vals: List[Val] = []
+        self.nodes: List[Node] = []
+        self.params: List[Val] = []
+        for i, p in enumerate(tape.params):
+            v = self._new(p, param_index=i, name=f"param{i}")
+            self.params.append(v)
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _new(self, base, **kw) -> Val:
+        v = Val(len(self.all_vals), base, **kw)
+        self.all_vals.append(v)
+        self.vals[id(base)] = v
+        return v
+
+    def act(self, x) -> Optional[Val]:
+        return self.vals.get(id(x)) if isinstance(x, torch.Tensor) else None
+
+    def emit(self, op, ins, out_tensor, src, **attrs) -> Node:
+        out = self._new(out_tensor) if out_tensor is not None else None
+        n = Node(op, list(ins), out, attrs, src=src)
+        self.nodes.append(n)
+        return n
+
+    def alias(self, parent: Val, out_tensor, viewfn, full_cover=True):
+        return self._new(out_tensor, parent=parent, viewfn=viewfn, full_cover=full_cover)
+
+    @staticmethod
+    def need_contig(v: Val, what: str):
+        if not v.base.is_contiguous():
+            raise UnsupportedGraph(f"{what}: needs a contiguous operand, got strides {v.base.stride()} for {v.shape}")
+
+    # -- main loop ---------------------------------------------------------------------------
+    def run(self) -> Graph:
+        for op in self.tape.ops:
+            tensors = [a for a in op.args if isinstance(a, torch.Tensor)]
+            for a in op.args:
+                if isinstance(a, (list, tuple)):
+                    tensors += [x for x in a if isinstance(x, torch.Tensor)]
+            if not any(id(t) in self.vals for t in tensors):
+                continue  # constant w.r.t. the lower parameters (data prep, upper module forward, ...)
+            self.lower_op(op)
+        loss = self.vals.get(id(self.tape.loss))
+        if loss is None:
+            raise UnsupportedGraph("the lower loss does not depend on the lower parameters (or was produced "
+                                   "outside the recorded forward)")
+        if loss.base.numel() != 1:
+            raise UnsupportedGraph("the lower loss must be a scalar")
+        g = Graph(self.nodes, self.all_vals, self.params, loss)
+        _analyse(g)
+        return g
+
+    # -- per-op rules ------------------------------------------------------------------------
+    def lower_op(self, op):
+        name, a, kw = op.name, op.args, op.kwargs
+        A = self.act
+        if name in ("aten.detach.default", "aten.detach_.default", "aten.lift_fresh.default"):
+            return  # output is a constant
+        opname = name.split(".")[1]
+        if opname.endswith("_") and not opname.startswith("_"):
+            raise UnsupportedGraph(f"in-place op {name} on a parameter-dependent tensor")
+        if name in _VIEW_OPS:
+            x = A(a[0])
+            if name == "aten.expand.default" and tuple(op.out.shape) != tuple(a[0].shape):
+                raise UnsupportedGraph("broadcasting expand of a parameter-dependent tensor")
+            func, rest = op.func, tuple(a[1:])
+            self.alias(x, op.out, lambda t, func=func, rest=rest, kw=dict(kw): func(t, *rest, **kw),
+                       full_cover=_VIEW_OPS[name])
+            return
+        if name == "aten._to_copy.default":
+            x = A(a[0])
+            okw = {k: v for k, v in kw.items() if k not in ("dtype", "layout", "device", "pin_memory", "non_blocking")
+                   and v is not None}
+            if okw or not op.out.is_floating_point() or op.out.stride() != a[0].stride():
+                raise UnsupportedGraph(f"_to_copy with {kw}")
+            self.alias(x, op.out, lambda t: t)  # a dtype cast is the identity on fp32 tangents/adjoints
+            return
+        if name == "aten.clone.default":
+            x = A(a[0])
+            self.emit("copy", [x], op.out, name)  # strided gather into the (usually contiguous) clone
+            return
+        if name in _UNARY:
+            self.emit("unary", [A(a[0])], op.out, name, kind=_UNARY[name],
+                      approximate=kw.get("approximate", "none"))
+            return
+        if name == "aten.pow.Tensor_Scalar":
+            self.emit("unary", [A(a[0])], op.out, name, kind="pow", scalar=float(a[1]))
+            return
+        if name in ("aten.mul.Tensor", "aten.mul.Scalar", "aten.div.Tensor", "aten.div.Scalar"):
+            return self._mul_div(op)
+        if name in ("aten.add.Tensor", "aten.sub.Tensor", "aten.add.Scalar", "aten.sub.Scalar", "aten.rsub.Scalar"):
+            return self._add_sub(op)
+        if name in ("aten.sum.default", "aten.mean.default"):
+            x = A(a[0])
+            scale = 1.0 if name.startswith("aten.sum") else 1.0 / max(1, a[0].numel())
+            self.emit("sumall", [x], op.out, name, scale=scale)
+            return
+        if name in ("aten.sum.dim_IntList", "aten.mean.dim"):
+            x = A(a[0])
+            dims = a[1] if len(a) > 1 else None
+            nd = a[0].dim()
+            if dims is None or sorted(d % nd for d in dims) == list(range(nd)):
+                scale = 1.0 if name.startswith("aten.sum") else 1.0 / max(1, a[0].numel())
+                self.emit("sumall", [x], op.out, name, scale=scale)
+                return
+            raise UnsupportedGraph(f"partial reduction {name} over dims {dims}")
+        if name in ("aten.mm.default", "aten.addmm.default", "aten.bmm.default", "aten.mv.default"):
+            return self._gemm(op)
+        if name == "aten.convolution.default":
+            return self._conv(op)
+        if name == "aten.max_pool2d_with_indices.default":
+            x = A(a[0])
+            self.need_contig(x, "max_pool2d")
+            out, idx = op.out
+            if not out.is_contiguous():
+                raise UnsupportedGraph("max_pool2d: non-contiguous output")
+            self.emit("maxpool2d", [x], out, name, indices=idx)
+            return
+        if name in _BN_OPS:
+            return self._batchnorm(op)
+        if name == "aten.native_layer_norm.default":
+            return self._layernorm(op)
+        if name in ("aten._softmax.default", "aten._log_softmax.default"):
+            x = A(a[0])
+            dim = a[1] % a[0].dim()
+            if dim != a[0].dim() - 1:
+                raise UnsupportedGraph("softmax over a non-last dim")
+            self.need_contig(x, name)
+            self.emit("softmax" if name == "aten._softmax.default" else "logsoftmax", [x], op.out, name)
+            return
+        if name == "aten.nll_loss_forward.default":
+            x = A(a[0])
+            target, weight, reduction, ignore_index = a[1], a[2], a[3], a[4]
+            if weight is not None:
+                raise UnsupportedGraph("nll_loss with class weights")
+            if a[0].dim() != 2:
+                raise UnsupportedGraph("nll_loss on non-2D input")
+            self.need_contig(x, name)
+            if bool((target == ignore_index).any()):
+                raise UnsupportedGraph("nll_loss with ignored targets")
+            out = op.out[0]
+            scale = {0: 1.0, 1: 1.0 / a[0].shape[0], 2: 1.0}[reduction]
+            self.emit("nll", [x], out, name, target=target, reduction=reduction, scale=scale)
+            return
+        if name == "aten.binary_cross_entropy_with_logits.default":
+            x = A(a[0])
+            if A(a[1]) is not None:
+                raise UnsupportedGraph("BCE with parameter-dependent targets")
+            weight = a[2] if len(a) > 2 else None
+            pos_weight = a[3] if len(a) > 3 else None
+            reduction = a[4] if len(a) > 4 else 1
+            if weight is not None or pos_weight is not None or reduction != 1:
+                raise UnsupportedGraph("BCE-with-logits variant")
+            self.need_contig(x, name)
+            self.emit("bce_logits", [x], op.out, name, target=a[1])
+            return
+        if name == "aten.embedding.default":
+            w = A(a[0])
+            if w is None or w.parent is not None or w.param_index is None:
+                raise UnsupportedGraph("embedding of a non-parameter table")
+            padding_idx = a[2] if len(a) > 2 else -1
+            self.emit("embedding", [w], op.out, name, indices=a[1], padding_idx=padding_idx)
+            return
+        if name == "aten.native_dropout.default":
+            x = A(a[0])
+            out, mask = op.out
+            p = float(a[1])
+            self.emit("mulc", [x], out, name, const=mask.to(a[0].dtype if a[0].dtype == torch.float64 else torch.float32) * (1.0 / (1.0 - p)), scalar=None)
+            return
+        raise UnsupportedGraph(f"no second-order rule for {name}")
+
+    def _mul_div(self, op):
+        name, a = op.name, op.args
+        x, y = self.act(a[0]), self.act(a[1])
+        is_div = ".div" in name
+        if x is not None and y is not None:
+            if is_div:
+                raise UnsupportedGraph("division of two parameter-dependent tensors")
+            if tuple(a[0].shape) != tuple(a[1].shape) or a[0].stride() != a[1].stride():
+                raise UnsupportedGraph("product of parameter-dependent tensors with different shapes/layout")
+            self.emit("mul2", [x, y], op.out, name)
+            return
+        if x is None:
+            if is_div:
+                raise UnsupportedGraph("constant / parameter-dependent tensor")
+            x, c = y, a[0]
+        else:
+            c = a[1]
+        if isinstance(c, torch.Tensor):
+            cc = c.detach()
+            cc = cc if cc.dtype == torch.float64 else cc.to(torch.float32)  # fp64 only in the CPU rule tests
+            if is_div:
+                cc = 1.0 / cc
+            if tuple(cc.shape) != tuple(op.out.shape):
+                cc = cc.expand(op.out.shape)
+            if tuple(x.base.shape) != tuple(op.out.shape):
+                raise UnsupportedGraph("broadcast of the parameter-dependent factor")
+            self.emit("mulc", [x], op.out, name, const=cc.contiguous(),
+                      scalar=None)
+        else:
+            s = float(c)
+            self.emit("unary", [x], op.out, name, kind="scale", scalar=(1.0 / s if is_div else s))
+
+    def _add_sub(self, op):
+        name, a, kw = op.name, op.args, op.kwargs
+        alpha = float(kw.get("alpha", 1))
+        sub = ".sub" in name
+        rsub = "rsub" in name
+        x, y = self.act(a[0]), self.act(a[1])
+        sx, sy = 1.0, (-alpha if sub else alpha)
+        if rsub:
+            sx, sy = -1.0, alpha
+        if x is not None and y is not None:
+            if tuple(a[0].shape) != tuple(a[1].shape):
+                raise UnsupportedGraph(f"broadcasting add of parameter-dependent tensors {a[0].shape} + {a[1].shape}")
+            self.emit("add2", [x, y], op.out, name, sa=sx, sb=sy)
+            return
+        v, s = (x, sx) if x is not None else (y, sy)
+        if tuple(v.base.shape) != tuple(op.out.shape):
+            raise UnsupportedGraph("broadcast of the parameter-dependent addend")
+        if s == 1.0 and op.out.stride() == v.base.stride():
+            # y = x + const: identity on tangents and adjoints.  The output is a fresh tensor in the
+            # forward but aliases x's second-order buffers.
+            self.alias(v, op.out, lambda t: t)
+        else:
+            self.emit("unary", [v], op.out, name, kind="scale", scalar=s)
+
+    def _gemm(self, op):
+        name, a, kw = op.name, op.args, op.kwargs
+        if name == "aten.addmm.default":
+            bias_t, A_t, B_t = a
+            beta, alpha = float(kw.get("beta", 1)), float(kw.get("alpha", 1))
+            if beta != 1 or alpha != 1:
+                raise UnsupportedGraph("addmm with alpha/beta != 1")
+        else:
+            bias_t, (A_t, B_t) = None, a[:2]
+        bias = self.act(bias_t) if bias_t is not None else None
+        if bias is not None and (bias.base.dim() != 1 or bias.base.shape[0] != op.out.shape[-1]):
+            raise UnsupportedGraph("addmm bias that is not a length-N vector")
+        self.emit("gemm", [self.act(A_t), self.act(B_t), bias], op.out, name, A=A_t, B=B_t,
+                  mv=(name == "aten.mv.default"))
+
+    def _conv(self, op):
+        a = op.args
+        x_t, w_t, b_t, stride, padding, dilation, transposed, output_padding, groups = a
+        if transposed:
+            raise UnsupportedGraph("transposed convolution")
+        if x_t.dim() != 4:
+            raise UnsupportedGraph("only 2-D convolutions")
+        x, w, b = self.act(x_t), self.act(w_t), self.act(b_t) if b_t is not None else None
+        for v, what in ((x, "conv input"), (w, "conv weight")):
+            if v is not None:
+                self.need_contig(v, what)
+        if not op.out.is_contiguous():
+            raise UnsupportedGraph("conv output is not NCHW-contiguous (channels_last?)")
+        self.emit("conv2d", [x, w, b], op.out, op.name, X=x_t, W=w_t, stride=tuple(stride), padding=tuple(padding),
+                  dilation=tuple(dilation), groups=int(groups))
+
+    def _batchnorm(self, op):
+        name, a = op.name, op.args
+        x_t, g_t, b_t = a[0], a[1], a[2]
+        if name in ("aten.native_batch_norm.default", "aten._native_batch_norm_legit.default"):
+            training, eps = a[5], a[7]
+        elif name in ("aten._native_batch_norm_legit_no_stats.default", "aten._native_batch_norm_legit.no_stats"):
+            training, eps = a[3], a[5]
+        elif name in ("aten.cudnn_batch_norm.default", "aten.miopen_batch_norm.default"):
+            training, eps = a[5], a[7]
+        elif name == "aten._batch_norm_with_update.default":
+            training, eps = True, a[6]
+        else:  # pragma: no cover
+            raise UnsupportedGraph(name)
+        if not training:
+            raise UnsupportedGraph("batch_norm in eval mode (running statistics)")
+        x = self.act(x_t)
+        if x is None:
+            raise UnsupportedGraph("batch_norm of a constant input with parameter-dependent affine")
+        self.need_contig(x, "batch_norm")
+        out = op.out[0]
+        if x_t.dim() != 4 or not out.is_contiguous():
+            raise UnsupportedGraph("batch_norm: only contiguous NCHW")
+        self.emit("batchnorm", [x, self.act(g_t) if g_t is not None else None,
+                                self.act(b_t) if b_t is not None else None], out, name, X=x_t, gamma=g_t,
+                  eps=float(eps))
+
+    def _layernorm(self, op):
+        a = op.args
+        x_t, nshape, g_t, b_t, eps = a
+        x = self.act(x_t)
+        if x is None:
+            raise UnsupportedGraph("layer_norm of a constant input")
+        if len(nshape) != 1:
+            raise UnsupportedGraph("layer_norm over more than the last dim")
+        self.need_contig(x, "layer_norm")
+        out = op.out[0]
+        self.emit("layernorm", [x, self.act(g_t) if g_t is not None else None,
+                                self.act(b_t) if b_t is not None else None], out, op.name, X=x_t, gamma=g_t,
+                  eps=float(eps))
+
+
+def _analyse(g: Graph):
+    """Dead-code elimination from the loss, then adjoint-writer counting (beta / zero-init)."""
+    loss = g.loss
+    needed_roots = {id(loss.root)}
+    loss.root.needed = True
+    live: List[Node] = []
+    for n in reversed(g.nodes):
+        if n.out is None or id(n.out.root) not in needed_roots:
+            continue
+        live.append(n)
+        for v in n.ins:
+            if v is not None:
+                needed_roots.add(id(v.root))
+                v.root.needed = True
+    live.reverse()
+    g.nodes = live
+    # count adjoint writers per root (parameters: writers of the H.d slice)
+    for v in g.values:
+        v.writers = 0
+    for n in g.nodes:
+        for v in n.ins:
+            if v is not None:
+                v.root.writers += 1
+    for n in g.nodes:
+        n.beta = []
+        for v in n.ins:
+            if v is None:
+                n.beta.append(0)
+                continue
+            r = v.root
+            single = (r.writers == 1 and v.chain_full_cover() and n.op not in ("embedding",)
+                      and not (n.op == "conv2d" and v is n.ins[1]))
+            # embedding scatter-adds rows and the conv weight-gradient kernel is split-K with atomics:
+            # both accumulate into a zeroed slice
+            if single:
+                n.beta.append(0)
+            else:
+                n.beta.append(1)
+                r.zero_init = True
+    for p in g.params:
+        if p.writers == 0:
+            p.zero_init = True  # unused parameter: H.d slice must read as zero
+    g.stats = {"nodes": len(g.nodes), "values": sum(1 for v in g.values if v.parent is None and v.needed),
+               "aliases": sum(1 for v in g.values if v.parent is not None)}
+
+
+def lower_tape(tape) -> Graph:
+    return _Lowering(tape).run()
