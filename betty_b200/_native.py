@@ -35,6 +35,7 @@ _SIGS = {
     "bb_neumann_update": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p], 1),
     "bb_scale": ([C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p], 1),
     "bb_cg_dots": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_void_p, C.c_void_p], 1),
+    "bb_cg_init": ([C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p], 1),
     "bb_cg_update_xr": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p], 1),
     "bb_cg_update_p": ([C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p], 1),
     "bb_mt_copy": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p], 1),
@@ -48,6 +49,7 @@ _SIGS = {
     "bb_plan_set_zero_regions": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int], 0),
     "bb_plan_run": ([C.c_void_p, C.c_int, C.c_void_p], None),
     "bb_plan_launch_count": ([C.c_void_p, C.c_int], 0),
+    "bb_plan_profile": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
     "bb_plan_hvp": ([C.c_void_p, C.c_void_p], None),
     "bb_plan_neumann_loop": ([C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_int, C.c_void_p], None),

@@ -1,0 +1,161 @@
+// K5: second-order rules of C = A.B (+ bias) -- Linear layers (addmm with a transposed-view weight),
+// attention score/context products (bmm), and any mm/mv in user loss code.  Exact-fp32 SIMT path.
+//
+//   TF  t_C  = t_A.B + A.t_B (+ t_bias)                       one dual-product launch
+//   BB  a_A  = a_C.B^T            a_B  = A^T.a_C
+//   TB  at_A = at_C.B^T + a_C.t_B^T      at_B = A^T.at_C + t_A^T.a_C      at_bias = colsum(at_C)
+//
+// (SURVEY.md Appendix B "Linear": 6 GEMMs per iteration; here 3 dual launches.)  Spec:
+// oracle/plan_interp.py tf_gemm/bb_gemm/tb_gemm.
+#include "../../include/betty_b200.h"
+#include "plan.h"
+#include "tile_gemm.cuh"
+
+namespace {
+
+using bb::StridedLoad;
+using bb::StridedStore;
+
+struct Mat {  // a (possibly transposed) strided matrix view
+  const void* p;
+  int dt;
+  int64_t rs, cs, bs;
+};
+
+inline Mat T(const Mat& m) { return Mat{m.p, m.dt, m.cs, m.rs, m.bs}; }
+
+inline bool dense_block(int64_t M, int64_t N, int64_t batch, int64_t rs, int64_t cs, int64_t bs) {
+  const bool rowmajor = (cs == 1 && rs == N), colmajor = (rs == 1 && cs == M);
+  return (rowmajor || colmajor || M == 1 || N == 1) && (batch == 1 || bs == M * N) &&
+         ((M == 1 || N == 1) ? (rs == 1 || cs == 1 || M * N == 1 || (M == 1 ? cs == 1 : rs == 1)) : true);
+}
+
+// out (M x N) (beta)= sum_p L_p (M x K) . R_p (K x N)  [+ bias]
+int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const Mat* L, const Mat* R, float* out,
+             int64_t ors, int64_t ocs, int64_t obs, int beta, const float* bias, int64_t bias_stride,
+             cudaStream_t s) {
+  if (M <= 0 || N <= 0 || batch <= 0) return BB_OK;
+  StridedLoad la{}, lb{};
+  for (int p = 0; p < npairs; ++p) {
+    la.p[p] = L[p].p; la.dt[p] = L[p].dt; la.rs[p] = L[p].rs; la.cs[p] = L[p].cs; la.bs[p] = L[p].bs;
+    lb.p[p] = R[p].p; lb.dt[p] = R[p].dt; lb.rs[p] = R[p].rs; lb.cs[p] = R[p].cs; lb.bs[p] = R[p].bs;
+  }
+  la.k_fast = (npairs > 0 && L[0].cs == 1) ? 1 : 0;
+  lb.k_fast = (npairs > 0 && R[0].rs == 1) ? 1 : 0;
+  StridedStore sc{out, ors, ocs, obs, beta, bias, bias_stride};
+
+  const bool small_m = M <= 16, small_n = N <= 16 && !small_m;
+  const int BM = small_m ? 16 : 64, BN = small_n ? 16 : 64;
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
+  int ksplit = 1;
+  if (npairs > 0 && tiles < BB_SM_COUNT && K >= 1024 && dense_block(M, N, batch, ors, ocs, obs)) {
+    int64_t want = (2 * BB_SM_COUNT + tiles - 1) / tiles;
+    int64_t maxs = K / 256;
+    ksplit = (int)(want < maxs ? want : maxs);
+    if (ksplit > 64) ksplit = 64;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit > 1 && !beta) {
+    BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * M * N * batch, s));
+    bb_launch_tally += 1;
+  }
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)(batch * ksplit));
+  if (small_m)
+    bb::tile_gemm_kernel<16, 64, 16, 1, 4, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
+  else if (small_n)
+    bb::tile_gemm_kernel<64, 16, 16, 4, 1, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
+  else
+    bb::tile_gemm_kernel<64, 64, 16, 4, 4, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+// out[n] += sum_{b,m} g[b*bs + m*rs + n*cs]   (out must hold the value to accumulate onto)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, float* out, int64_t rows_per_b,
+                                                     int64_t batch, int64_t N, int64_t rs, int64_t cs, int64_t bs,
+                                                     int64_t out_stride) {
+  __shared__ float sm[8][33];
+  const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int64_t total = rows_per_b * batch;
+  float acc = 0.f;
+  if (n < N) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < total; r += (int64_t)gridDim.y * 8) {
+      const int64_t b = r / rows_per_b, m = r - b * rows_per_b;
+      acc += g[b * bs + m * rs + n * cs];
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    atomicAdd(out + n * out_stride, t);
+  }
+}
+
+int run_colsum(const float* g, float* out, int64_t M, int64_t batch, int64_t N, int64_t rs, int64_t cs, int64_t bs,
+               int64_t out_stride, int beta, cudaStream_t s) {
+  if (!beta) {
+    if (out_stride != 1) return BB_ERR_UNSUPPORTED;
+    BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
+    bb_launch_tally += 1;
+  }
+  const int64_t rows = M * batch;
+  int gy = (int)((rows + 63) / 64);
+  if (gy < 1) gy = 1;
+  if (gy > 64) gy = 64;
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)gy);
+  colsum_kernel<<<grid, dim3(32, 8), 0, s>>>(g, out, M, batch, N, rs, cs, bs, out_stride);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+}  // namespace
+
+int bb_launch_gemm(const bb_node& nd, int pass, cudaStream_t s) {
+  const int64_t M = nd.dims[0], N = nd.dims[1], K = nd.dims[2], batch = nd.dims[3];
+  const bool actA = nd.active & 1, actB = nd.active & 2, actBias = nd.active & 4;
+  const int64_t* sa = nd.stride[0];  // A: m, k, b
+  const int64_t* sb = nd.stride[1];  // B: k, n, b
+  const int64_t* sc = nd.stride[3];  // C: m, n, b
+  const Mat A{nd.base[0], nd.dt[0], sa[0], sa[1], sa[2]};
+  const Mat B{nd.base[1], nd.dt[1], sb[0], sb[1], sb[2]};
+  const Mat tA{nd.t[0], BB_F32, sa[0], sa[1], sa[2]};
+  const Mat tB{nd.t[1], BB_F32, sb[0], sb[1], sb[2]};
+  int rc;
+  if (pass == BB_PASS_TAN_FWD) {
+    Mat L[2], R[2];
+    int np = 0;
+    if (actA) { L[np] = tA; R[np] = B; ++np; }
+    if (actB) { L[np] = A; R[np] = tB; ++np; }
+    return run_gemm(M, N, K, batch, np, L, R, reinterpret_cast<float*>(nd.t[3]), sc[0], sc[1], sc[2], 0,
+                    actBias ? reinterpret_cast<const float*>(nd.t[2]) : nullptr, nd.stride[2][0], s);
+  }
+  const bool base = pass == BB_PASS_BASE_BWD;
+  const Mat gC{base ? nd.a[3] : nd.at[3], BB_F32, sc[0], sc[1], sc[2]};   // adjoint being propagated
+  const Mat aC{nd.a[3], BB_F32, sc[0], sc[1], sc[2]};                      // base adjoint (curvature terms)
+  const int need = base ? nd.pad0 : nd.active;                              // pad0 = need_a mask
+  if (need & 1) {  // (M x K) = gC (M x N) . B^T (N x K)  [+ aC . tB^T]
+    Mat L[2] = {gC, aC}, R[2] = {T(B), T(tB)};
+    const int np = (!base && actB) ? 2 : 1;
+    rc = run_gemm(M, K, N, batch, np, L, R, reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]), sa[0], sa[1], sa[2],
+                  nd.beta[0], nullptr, 0, s);
+    if (rc) return rc;
+  }
+  if (need & 2) {  // (K x N) = A^T (K x M) . gC (M x N)  [+ tA^T . aC]
+    Mat L[2] = {T(A), T(tA)}, R[2] = {gC, aC};
+    const int np = (!base && actA) ? 2 : 1;
+    rc = run_gemm(K, N, M, batch, np, L, R, reinterpret_cast<float*>(base ? nd.a[1] : nd.at[1]), sb[0], sb[1], sb[2],
+                  nd.beta[1], nullptr, 0, s);
+    if (rc) return rc;
+  }
+  if (need & 4) {
+    rc = run_colsum(reinterpret_cast<const float*>(gC.p), reinterpret_cast<float*>(base ? nd.a[2] : nd.at[2]), M, batch,
+                    N, sc[0], sc[1], sc[2], nd.stride[2][0], nd.beta[2], s);
+    if (rc) return rc;
+  }
+  return BB_OK;
+}

@@ -106,6 +106,21 @@ __global__ void __launch_bounds__(kThreads) cg_dots_kernel(const float* __restri
   }
 }
 
+// rr = r.r before the first iteration (so that the captured iteration body is identical for all k)
+__global__ void __launch_bounds__(kThreads) cg_init_kernel(const float* __restrict__ r, int64_t n4, void* wsraw) {
+  __shared__ double red[32];
+  Ws w = ws_view(wsraw);
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = bb::ld4(r + 4 * i);
+    acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  double b = bb::block_sum<double>((double)acc, red);
+  double rr;
+  if (bb::grid_sum_finish(b, w.partials, w.ticket, &rr, red)) w.s->rr = rr;
+}
+
 // ---- K3 -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) cg_update_xr_kernel(float* __restrict__ x, float* __restrict__ r,
                                                                 const float* __restrict__ p,
@@ -249,6 +264,14 @@ int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, 
   if ((n & 3) != 0) return BB_ERR_ARG;
   const int64_t n4 = n >> 2;
   cg_dots_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(r, hp, p, cg_alpha, first, n4, ws);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_cg_init(const float* r, int64_t n, void* ws, void* stream) {
+  if ((n & 3) != 0) return BB_ERR_ARG;
+  const int64_t n4 = n >> 2;
+  cg_init_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(r, n4, ws);
   BB_LAUNCH_CHECK();
   return BB_OK;
 }

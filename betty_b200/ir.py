@@ -463,18 +463,19 @@ def _analyse(g: Graph):
                 n.beta.append(0)
                 continue
             r = v.root
-            single = (r.writers == 1 and v.chain_full_cover() and n.op not in ("embedding",)
-                      and not (n.op == "conv2d" and v is n.ins[1]))
-            # embedding scatter-adds rows and the conv weight-gradient kernel is split-K with atomics:
-            # both accumulate into a zeroed slice
+            # Overwrite only when this is the buffer's single writer and covers it entirely.  Parameter
+            # slices (H.d arena) always accumulate into the arena zeroed at the start of the pass -- several
+            # of their kernels are split-K / scatter kernels with atomics -- and so do max-pool / embedding
+            # scatters.
+            single = (r.writers == 1 and v.chain_full_cover() and r.param_index is None
+                      and n.op not in ("embedding", "maxpool2d"))
             if single:
                 n.beta.append(0)
             else:
                 n.beta.append(1)
                 r.zero_init = True
     for p in g.params:
-        if p.writers == 0:
-            p.zero_init = True  # unused parameter: H.d slice must read as zero
+        p.zero_init = True
     g.stats = {"nodes": len(g.nodes), "values": sum(1 for v in g.values if v.parent is None and v.needed),
                "aliases": sum(1 for v in g.values if v.parent is not None)}
 

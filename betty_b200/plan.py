@@ -1,0 +1,424 @@
+"""Native second-order plan: lowers a recorded tape (ir.py), lays every tangent / adjoint buffer out in
+a handful of device arenas, serialises the node list into ``bb_node`` descriptors (csrc/plan.h) and
+drives the C executor (csrc/plan.cu).  After construction the K-loop makes no Python-level launches:
+``neumann_loop`` / ``cg_loop`` are one C call each (CUDA-graph replay of one iteration).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .arena import ArenaLayout
+from .ir import Graph, Node, UnsupportedGraph, Val, _is_dense, lower_tape
+
+BB_MAX_DIMS = 6
+OPS = {"unary": 1, "copy": 2, "add2": 3, "mulc": 4, "mul2": 5, "sumall": 6, "gemm": 7, "conv2d": 8,
+       "maxpool2d": 9, "batchnorm": 10, "layernorm": 11, "softmax": 12, "logsoftmax": 13, "nll": 14,
+       "bce_logits": 15, "embedding": 16}
+UNARY = {"relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4, "pow": 5, "scale": 6, "neg": 6}
+PASS_BB, PASS_TF, PASS_TB = 0, 1, 2
+
+NODE_DTYPE = np.dtype([
+    ("op", np.int32), ("kind", np.int32), ("active", np.int32), ("linear", np.int32),
+    ("beta", np.int32, (4,)), ("dt", np.int32, (4,)), ("ndim", np.int32), ("pad0", np.int32),
+    ("n", np.int64), ("dims", np.int64, (16,)), ("f", np.float64, (4,)),
+    ("base", np.uint64, (4,)), ("t", np.uint64, (4,)), ("a", np.uint64, (4,)), ("at", np.uint64, (4,)),
+    ("aux", np.uint64, (4,)), ("sizes", np.int64, (BB_MAX_DIMS,)), ("stride", np.int64, (4, BB_MAX_DIMS)),
+], align=True)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise UnsupportedGraph(f"activation dtype {t.dtype} (only fp32 / bf16 autocast are supported)")
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+class HvpPlan:
+    def __init__(self, tape, params: Sequence[torch.Tensor], layout: ArenaLayout, d_arena: torch.Tensor,
+                 hv_arena: torch.Tensor, cuda_graph: Optional[bool] = None, dry_run: bool = False):
+        """``dry_run`` (CPU unit tests only) builds buffers and descriptors but launches nothing."""
+        from .engine import settings
+
+        if not dry_run:
+            N.require_cuda()
+        assert N.lib().bb_node_bytes() == NODE_DTYPE.itemsize, (N.lib().bb_node_bytes(), NODE_DTYPE.itemsize)
+        self.dev = d_arena.device
+        self.layout, self.d_arena, self.hv_arena = layout, d_arena, hv_arena
+        self.use_graph = settings.cuda_graph if cuda_graph is None else cuda_graph
+        self.tape = tape                      # keeps the base activations alive
+        self.g: Graph = lower_tape(tape)
+        self._keep: List[torch.Tensor] = []   # constants / scratch referenced by raw pointer
+        self._alloc_buffers()
+        self._build_nodes()
+        self.launches_per_iter = 0
+        if dry_run:
+            return
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.run_pass(PASS_BB)                # delta, once per call (reference: part of in_grad's backward)
+
+    # ------------------------------------------------------------------------------------------
+    def _alloc_buffers(self):
+        g = self.g
+        roots = [v for v in g.values if v.parent is None and v.needed and v.param_index is None]
+        for v in roots:
+            if not _is_dense(v.base):
+                raise UnsupportedGraph(f"activation {v} is not dense (strides {v.base.stride()})")
+        sizes = {"t": 0, "z": 0, "nz": 0}
+        place = {}
+        for v in roots:
+            n = _align(v.base.numel())
+            place[v.vid] = (sizes["t"], sizes["z" if v.zero_init else "nz"])
+            sizes["t"] += n
+            sizes["z" if v.zero_init else "nz"] += n
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.T = torch.zeros(max(sizes["t"], 1), **f32)
+        self.A = {"z": torch.zeros(max(sizes["z"], 1), **f32), "nz": torch.zeros(max(sizes["nz"], 1), **f32)}
+        self.AT = {"z": torch.zeros(max(sizes["z"], 1), **f32), "nz": torch.zeros(max(sizes["nz"], 1), **f32)}
+        self.zero_bytes = 4 * sizes["z"]
+        for v in roots:
+            ot, oa = place[v.vid]
+            k = "z" if v.zero_init else "nz"
+            shape, stride = tuple(v.base.shape), tuple(v.base.stride())
+            v.t = torch.as_strided(self.T, shape, stride, ot)
+            v.a = torch.as_strided(self.A[k], shape, stride, oa)
+            v.at = torch.as_strided(self.AT[k], shape, stride, oa)
+        dviews, hviews = self.layout.views(self.d_arena), self.layout.views(self.hv_arena)
+        for p in g.params:
+            if not p.base.is_contiguous() or p.base.dtype != torch.float32:
+                raise UnsupportedGraph("lower parameters must be contiguous fp32 tensors")
+            p.t, p.at, p.a = dviews[p.param_index], hviews[p.param_index], None
+        g.loss.root.a.fill_(1.0)   # seed dL/dL; its adjoint tangent stays 0
+        self.bytes_buffers = 4 * (self.T.numel() + 2 * (self.A["z"].numel() + self.A["nz"].numel()))
+
+    def buf(self, v: Optional[Val], kind: str) -> Optional[torch.Tensor]:
+        if v is None:
+            return None
+        if v.parent is None:
+            return getattr(v, kind)
+        b = self.buf(v.parent, kind)
+        return None if b is None else v.viewfn(b)
+
+    # ------------------------------------------------------------------------------------------
+    def _ptr(self, t: Optional[torch.Tensor]) -> int:
+        return 0 if t is None else t.data_ptr()
+
+    def _const(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
+        t = t.detach()
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        t = t.to(self.dev).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _scratch(self, nbytes: int) -> torch.Tensor:
+        t = torch.zeros(_align(nbytes, 8) // 8, dtype=torch.float64, device=self.dev)
+        self._keep.append(t)
+        return t
+
+    def _slot(self, rec, s: int, v: Optional[Val], base_t: Optional[torch.Tensor]):
+        """Fill operand slot ``s`` (pointers + dtype); returns the buffer used for stride checks."""
+        if base_t is not None:
+            rec["base"][s] = base_t.data_ptr()
+            rec["dt"][s] = _dt(base_t) if base_t.is_floating_point() else 0
+        if v is not None:
+            for kind in ("t", "a", "at"):
+                b = self.buf(v, kind)
+                rec[kind][s] = self._ptr(b)
+                if b is not None and base_t is not None and b.numel() > 1 and tuple(b.stride()) != tuple(base_t.stride()):
+                    raise UnsupportedGraph(f"buffer/base stride mismatch for {v}: {b.stride()} vs {base_t.stride()}")
+
+    def _build_nodes(self):
+        g = self.g
+        recs = np.zeros(len(g.nodes), dtype=NODE_DTYPE)
+        for i, n in enumerate(g.nodes):
+            r = recs[i]
+            r["op"] = OPS[n.op]
+            r["active"] = sum(1 << k for k, v in enumerate(n.ins) if v is not None)
+            r["pad0"] = sum(1 << k for k, v in enumerate(n.ins) if v is not None and v.root.param_index is None)
+            for k, b in enumerate(n.beta[:4]):
+                r["beta"][k] = b
+            getattr(self, "_n_" + n.op)(n, r)
+        self.recs = recs
+        handle = C.c_void_p()
+        N.call("bb_plan_create", recs.ctypes.data, len(recs), C.byref(handle))
+        self.handle = handle
+
+        def regions(ts):
+            ts = [t for t in ts if t is not None and t.numel() > 0]
+            ptrs = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+            nb = (C.c_int64 * len(ts))(*[t.numel() * t.element_size() for t in ts])
+            return ptrs, nb, len(ts)
+
+        zb = [self.A["z"]] if self.zero_bytes else []
+        zt = ([self.AT["z"]] if self.zero_bytes else []) + [self.hv_arena]
+        for pas, ts in ((PASS_BB, zb), (PASS_TF, []), (PASS_TB, zt)):
+            ptrs, nb, cnt = regions(ts)
+            N.call("bb_plan_set_zero_regions", self.handle, pas, ptrs, nb, cnt)
+
+    # ---- per-op descriptor builders -----------------------------------------------------------
+    def _ew_layout(self, r, out: Val, operands: List[Optional[torch.Tensor]]):
+        """operands: buffers (or const tensors) for slots 0,1,2; slot 3 is the output buffer."""
+        ob = self.buf(out, "t")
+        shape = tuple(ob.shape)
+        if len(shape) > BB_MAX_DIMS:
+            raise UnsupportedGraph(f"element-wise op on a {len(shape)}-d tensor")
+        tens = list(operands) + [ob]
+        linear = _is_dense(ob)
+        for t in tens:
+            if t is None:
+                continue
+            if tuple(t.shape) != shape:
+                raise UnsupportedGraph(f"element-wise operand shape {tuple(t.shape)} != {shape}")
+            if ob.numel() > 1 and tuple(t.stride()) != tuple(ob.stride()):
+                linear = False
+        r["linear"] = int(linear)
+        r["ndim"] = max(len(shape), 1)
+        r["n"] = ob.numel()
+        for d, sz in enumerate(shape):
+            r["sizes"][d] = sz
+        if not shape:
+            r["sizes"][0] = 1
+        for s, t in enumerate(tens):
+            if t is None:
+                continue
+            for d, st in enumerate(t.stride()):
+                r["stride"][s][d] = st
+
+    def _n_unary(self, n: Node, r):
+        x = n.ins[0]
+        r["kind"] = UNARY[n.attrs["kind"]]
+        if n.attrs["kind"] == "gelu" and n.attrs.get("approximate", "none") != "none":
+            raise UnsupportedGraph("tanh-approximated GELU")
+        r["f"][0] = -1.0 if n.attrs["kind"] == "neg" else float(n.attrs.get("scalar") or 0.0)
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+        self._ew_layout(r, n.out, [self.buf(x, "t"), None, None])
+
+    def _n_copy(self, n: Node, r):
+        x = n.ins[0]
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+        self._ew_layout(r, n.out, [self.buf(x, "t"), None, None])
+
+    def _n_add2(self, n: Node, r):
+        a, b = n.ins
+        r["f"][1], r["f"][2] = n.attrs["sa"], n.attrs["sb"]
+        self._slot(r, 0, a, a.base)
+        self._slot(r, 1, b, b.base)
+        self._slot(r, 3, n.out, None)
+        self._ew_layout(r, n.out, [self.buf(a, "t"), self.buf(b, "t"), None])
+
+    def _n_mulc(self, n: Node, r):
+        x = n.ins[0]
+        c = self._const(n.attrs["const"], torch.float32)
+        r["aux"][0] = c.data_ptr()
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+        self._ew_layout(r, n.out, [self.buf(x, "t"), None, c])
+
+    def _n_mul2(self, n: Node, r):
+        a, b = n.ins
+        self._slot(r, 0, a, a.base)
+        self._slot(r, 1, b, b.base)
+        self._slot(r, 3, n.out, None)
+        self._ew_layout(r, n.out, [self.buf(a, "t"), self.buf(b, "t"), None])
+
+    def _n_sumall(self, n: Node, r):
+        x = n.ins[0]
+        xb = self.buf(x, "t")
+        if not _is_dense(xb):
+            raise UnsupportedGraph("full reduction of a non-dense tensor")
+        r["n"] = xb.numel()
+        r["f"][0] = n.attrs["scale"]
+        r["aux"][0] = self._scratch(8 * (2 * 148 + 2)).data_ptr()
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+
+    def _n_gemm(self, n: Node, r):
+        A_t, B_t = n.attrs["A"], n.attrs["B"]
+        a, b, bias = n.ins
+        out = n.out.base
+        if n.attrs["mv"]:
+            M, K = A_t.shape
+            Nn, batch = 1, 1
+            sa = (A_t.stride(0), A_t.stride(1), 0)
+            sb = (B_t.stride(0), 0, 0)
+            sc = (out.stride(0), 0, 0)
+        elif A_t.dim() == 2:
+            M, K = A_t.shape
+            Nn, batch = B_t.shape[1], 1
+            sa = (A_t.stride(0), A_t.stride(1), 0)
+            sb = (B_t.stride(0), B_t.stride(1), 0)
+            sc = (out.stride(0), out.stride(1), 0)
+        else:
+            batch, M, K = A_t.shape
+            Nn = B_t.shape[2]
+            sa = (A_t.stride(1), A_t.stride(2), A_t.stride(0))
+            sb = (B_t.stride(1), B_t.stride(2), B_t.stride(0))
+            sc = (out.stride(1), out.stride(2), out.stride(0))
+        r["dims"][0:4] = (M, Nn, K, batch)
+        for d in range(3):
+            r["stride"][0][d], r["stride"][1][d], r["stride"][3][d] = sa[d], sb[d], sc[d]
+        self._slot(r, 0, a, A_t)
+        self._slot(r, 1, b, B_t)
+        self._slot(r, 3, n.out, None)
+        if bias is not None:
+            bb = self.buf(bias, "t")
+            r["stride"][2][0] = bb.stride(0)
+            self._slot(r, 2, bias, None)
+
+    def _n_conv2d(self, n: Node, r):
+        x, w, b = n.ins
+        X, W = n.attrs["X"], n.attrs["W"]
+        if n.attrs["groups"] != 1:
+            raise UnsupportedGraph("grouped / depthwise convolution")
+        if not X.is_contiguous() or not W.is_contiguous():
+            raise UnsupportedGraph("conv operands must be NCHW-contiguous")
+        Nn, Cc, H, Wd = X.shape
+        O, _, KH, KW = W.shape
+        _, _, HO, WO = n.out.base.shape
+        (sh, sw), (ph, pw), (dh, dw) = n.attrs["stride"], n.attrs["padding"], n.attrs["dilation"]
+        r["dims"][0:15] = (Nn, Cc, H, Wd, O, KH, KW, HO, WO, sh, sw, ph, pw, dh, dw)
+        self._slot(r, 0, x, X)
+        self._slot(r, 1, w, W)
+        self._slot(r, 2, b, None)
+        self._slot(r, 3, n.out, None)
+
+    def _n_maxpool2d(self, n: Node, r):
+        x = n.ins[0]
+        idx = n.attrs["indices"]
+        Nn, Cc, H, W = x.base.shape
+        _, _, HO, WO = n.out.base.shape
+        r["dims"][0:3] = (Nn * Cc, H * W, HO * WO)
+        r["aux"][0] = self._const(idx, torch.int64).data_ptr()
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+
+    def _n_batchnorm(self, n: Node, r):
+        x, gv, bv = n.ins
+        X = n.attrs["X"]
+        Nn, Cc, H, W = X.shape
+        r["dims"][0:3] = (Nn, Cc, H * W)
+        r["f"][0] = n.attrs["eps"]
+        r["aux"][0] = self._scratch(8 * 16 * Cc).data_ptr()
+        self._slot(r, 0, x, X)
+        gam = n.attrs["gamma"]
+        if gam is not None:
+            self._slot(r, 1, gv, self._const(gam, torch.float32) if gam.dtype != torch.float32 else gam)
+        self._slot(r, 2, bv, None)
+        self._slot(r, 3, n.out, None)
+
+    def _n_layernorm(self, n: Node, r):
+        x, gv, bv = n.ins
+        X = n.attrs["X"]
+        D = X.shape[-1]
+        r["dims"][0:2] = (X.numel() // D, D)
+        r["f"][0] = n.attrs["eps"]
+        self._slot(r, 0, x, X)
+        gam = n.attrs["gamma"]
+        if gam is not None:
+            self._slot(r, 1, gv, self._const(gam, torch.float32) if gam.dtype != torch.float32 else gam)
+        self._slot(r, 2, bv, None)
+        self._slot(r, 3, n.out, None)
+
+    def _n_softmax(self, n: Node, r):
+        x = n.ins[0]
+        D = x.base.shape[-1]
+        r["dims"][0:2] = (x.base.numel() // D, D)
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+
+    _n_logsoftmax = _n_softmax
+
+    def _n_nll(self, n: Node, r):
+        x = n.ins[0]
+        B, Cc = x.base.shape
+        r["dims"][0:2] = (B, Cc)
+        r["kind"] = n.attrs["reduction"]
+        r["f"][0] = n.attrs["scale"]
+        r["aux"][0] = self._const(n.attrs["target"], torch.int64).data_ptr()
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+
+    def _n_bce_logits(self, n: Node, r):
+        x = n.ins[0]
+        r["n"] = x.base.numel()
+        r["aux"][0] = self._const(n.attrs["target"], torch.float32).data_ptr()
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+
+    def _n_embedding(self, n: Node, r):
+        w = n.ins[0]
+        idx = n.attrs["indices"]
+        V, D = w.base.shape
+        pad = n.attrs["padding_idx"]
+        r["dims"][0:4] = (idx.numel(), D, V, -1 if pad is None else pad)
+        r["aux"][0] = self._const(idx, torch.int64).data_ptr()
+        if not n.out.base.is_contiguous():
+            raise UnsupportedGraph("embedding output must be contiguous")
+        self._slot(r, 0, w, w.base)
+        self._slot(r, 3, n.out, None)
+
+    # ------------------------------------------------------------------------------------------
+    def _on_side(self, fn):
+        """Run ``fn(stream_ptr)`` on the plan's side stream (stream capture is illegal on the legacy
+        default stream), ordered after / before the caller's current stream."""
+        cur = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            fn(self.side.cuda_stream)
+        cur.wait_stream(self.side)
+
+    def run_pass(self, pas: int):
+        self._on_side(lambda s: N.call("bb_plan_run", self.handle, pas, s))
+        cnt = N.lib().bb_plan_launch_count(self.handle, pas)
+        N.launch_counter += cnt
+        return cnt
+
+    def __call__(self):
+        """hv_arena <- H . d_arena"""
+        self._on_side(lambda s: N.call("bb_plan_hvp", self.handle, s))
+        self._count_iter(1, 0)
+
+    def _count_iter(self, iters: int, extra_per_iter: int):
+        per = N.lib().bb_plan_launch_count(self.handle, PASS_TF) + N.lib().bb_plan_launch_count(self.handle, PASS_TB)
+        self.launches_per_iter = per + extra_per_iter
+        N.launch_counter += iters * self.launches_per_iter
+
+    def neumann_loop(self, K: int, alpha: float, v: torch.Tensor, p: torch.Tensor, hv: torch.Tensor):
+        assert v.data_ptr() == self.d_arena.data_ptr() and hv.data_ptr() == self.hv_arena.data_ptr()
+        self._on_side(lambda s: N.call("bb_plan_neumann_loop", self.handle, K, alpha, v.data_ptr(), p.data_ptr(),
+                                       hv.data_ptr(), self.layout.total, int(self.use_graph), s))
+        self._count_iter(K, 1)
+
+    def cg_loop(self, K: int, cg_alpha: float, x: torch.Tensor, r: torch.Tensor, p: torch.Tensor, hp: torch.Tensor, ws):
+        assert p.data_ptr() == self.d_arena.data_ptr() and hp.data_ptr() == self.hv_arena.data_ptr()
+        self._on_side(lambda s: N.call("bb_plan_cg_loop", self.handle, K, cg_alpha, x.data_ptr(), r.data_ptr(),
+                                       p.data_ptr(), hp.data_ptr(), self.layout.total, ws.ptr, int(self.use_graph), s))
+        self._count_iter(K, 3)
+
+    def profile(self, pas: int) -> np.ndarray:
+        ms = np.zeros(len(self.recs), dtype=np.float32)
+        self._on_side(lambda s: N.call("bb_plan_profile", self.handle, pas, ms.ctypes.data, s))
+        return ms
+
+    def describe(self) -> List[str]:
+        return [f"{i:4d} {n.op:10s} {n.src:40s} out={tuple(n.out.base.shape)}" for i, n in enumerate(self.g.nodes)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                N.lib().bb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

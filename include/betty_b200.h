@@ -44,6 +44,7 @@ int bb_scale(float* out, const float* in, float c, int64_t n, void* stream);
  *      alpha and beta stay in `ws`; `first` != 0 also computes rr = r.r.                        */
 int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, int first, int64_t n, void* ws,
                void* stream);
+int bb_cg_init(const float* r, int64_t n, void* ws, void* stream); /* ws.rr = r.r */
 int bb_cg_update_xr(float* x, float* r, const float* p, const float* hp, int64_t n, void* ws, void* stream);
 int bb_cg_update_p(float* p, const float* r, int64_t n, const void* ws, void* stream);
 
@@ -80,6 +81,8 @@ int bb_plan_destroy(bb_plan* plan);
 int bb_plan_set_zero_regions(bb_plan* plan, int pass, void* const* ptrs, const int64_t* bytes, int n);
 int bb_plan_run(bb_plan* plan, int pass, void* stream);
 int bb_plan_launch_count(const bb_plan* plan, int pass);
+/* eager run of one pass with a CUDA event pair around every node: ms_per_node[n_nodes] */
+int bb_plan_profile(bb_plan* plan, int pass, float* ms_per_node, void* stream);
 /* one H.d product: zero regions, tangent forward, tangent backward */
 int bb_plan_hvp(bb_plan* plan, void* stream);
 /* whole K-loops, captured once into a CUDA graph and replayed (direction arena `d`, result `hv`) */

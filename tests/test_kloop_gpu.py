@@ -21,8 +21,9 @@ def test_neumann_update(n):
     v0, p0 = v.clone(), p.clone()
     N.call("bb_neumann_update", v.data_ptr(), p.data_ptr(), hv.data_ptr(), 0.3, 0.0, n, stream_ptr())
     want_v = v0 - 0.3 * hv
-    assert torch.equal(v, want_v) or torch.allclose(v, want_v, rtol=1e-6, atol=1e-7)
-    assert torch.allclose(p, p0 + want_v, rtol=1e-6, atol=1e-7)
+    # the kernel contracts v - alpha*hv into one FMA; torch rounds the product first
+    assert torch.allclose(v, want_v, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(p, p0 + want_v, rtol=1e-6, atol=2e-6)
     # with a declared c*I shift
     v2, p2 = v0.clone(), p0.clone()
     N.call("bb_neumann_update", v2.data_ptr(), p2.data_ptr(), hv.data_ptr(), 0.3, 2.0, n, stream_ptr())

@@ -1,0 +1,97 @@
+"""GPU tests of the native second-order plan (csrc/plan.cu + per-op kernels) against the torch
+interpreter of the same IR (oracle/plan_interp.py, float64) -- value by value, so a wrong kernel is
+named -- and against autograd's double backward."""
+import pytest
+import torch
+
+from betty_b200 import workloads as W
+from betty_b200.arena import ArenaLayout, pack
+from betty_b200.ir import lower_tape
+from betty_b200.plan import PASS_BB, HvpPlan
+from betty_b200.trace import record_tape
+from oracle.plan_interp import Interp
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "logistic": ("logistic_regression_hpo", dict(), 1e-5),
+    "mlp": ("mlp_reweight", dict(batch=48), 1e-5),
+    "lenet": ("learning_to_reweight", dict(batch=12), 1e-5),
+    "lenet_b300": ("learning_to_reweight", dict(batch=300), 1e-5),
+    "fourconv": ("implicit_maml", dict(n=10, hidden=16), 2e-5),
+    "fourconv_mini": ("implicit_maml", dict(n=3, hidden=8, image="miniimagenet"), 2e-5),
+    "roberta": ("bert_data_reweighting", dict(batch=3, seq=9, tiny=True), 2e-5),
+    "fourconv_bf16": ("implicit_maml", dict(n=10, hidden=16, precision="bf16"), 3e-2),
+    "roberta_bf16": ("bert_data_reweighting", dict(batch=3, seq=9, tiny=True, precision="bf16"), 3e-2),
+}
+
+
+def _build(fac, kw):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wl = W.FACTORIES[fac](device="cuda", **kw)
+    params = wl.lower.trainable_parameters()
+    loss, tape = record_tape(lambda: wl.lower.training_step_exec(wl.lower.cur_batch), params)
+    lay = ArenaLayout.like(params)
+    d, hv = lay.new(params[0].device), lay.new(params[0].device)
+    plan = HvpPlan(tape, params, lay, d, hv, cuda_graph=False)
+    interp = Interp(lower_tape(tape), torch.float64)
+    interp.base_backward()
+    return wl, params, loss, tape, lay, d, hv, plan, interp
+
+
+def _compare(plan, interp, kinds, tol, what):
+    bad = []
+    for vn, vi in zip(plan.g.values, interp.g.values):
+        if vn.parent is not None or not vn.needed or vn.param_index is not None:
+            continue
+        for k in kinds:
+            a, b = getattr(vn, k), getattr(vi, k)
+            err = float((a.double() - b).norm() / (b.norm() + 1e-30)) if float(b.norm()) > 0 else float(a.double().norm())
+            if not (err <= tol):
+                prod = [n for n in plan.g.nodes if n.out is vn]
+                cons = [n.op for n in plan.g.nodes if any(x is not None and x.root is vn for x in n.ins)]
+                bad.append(f"{what}: value #{vn.vid} {tuple(vn.base.shape)} kind={k} rel={err:.3e} "
+                           f"producer={prod[0].op if prod else None} consumers={cons}")
+    assert not bad, "\n".join(bad[:12])
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_plan_matches_interpreter_and_autograd(case):
+    fac, kw, tol = CASES[case]
+    wl, params, loss, tape, lay, d, hv, plan, interp = _build(fac, kw)
+    # base backward (delta): adjoints of every activation
+    _compare(plan, interp, ["a"], tol, "base-backward")
+    in_grad = torch.autograd.grad(loss, params, create_graph=True)
+    for trial in range(2):
+        vec = [torch.randn_like(p) for p in params] if trial else list(wl.vector)
+        pack(lay, vec, d)
+        plan()
+        want_i = interp.hvp(vec)
+        _compare(plan, interp, ["t"], tol, "tangent-forward")
+        _compare(plan, interp, ["at"], tol * 5, "tangent-backward")
+        got = lay.views(hv)
+        assert rel_l2(got, want_i) < tol * 5, f"{case}: H.v vs fp64 interpreter {rel_l2(got, want_i):.3e}"
+        want_a = torch.autograd.grad(in_grad, params, grad_outputs=vec, retain_graph=True)
+        e = rel_l2(got, want_a)
+        assert e < max(1e-4, tol * 5), f"{case}: H.v vs autograd double backward {e:.3e}"
+        for g_, w_ in zip(got, want_a):   # per-tensor, so a wrong small tensor is not hidden by a big one
+            if float(w_.norm()) > 0:
+                assert rel_l2([g_], [w_]) < max(3e-4, tol * 20), f"{case}: tensor {tuple(g_.shape)}"
+
+
+def test_graph_replay_equals_eager_loop():
+    from betty_b200 import engine as E
+
+    for method, kw in (("neumann", dict(K=6, alpha=0.1)), ("cg", dict(K=6))):
+        outs = []
+        for graph in (False, True):
+            E.settings.cuda_graph = graph
+            wl = W.lenet_reweight(device="cuda", method=method, batch=16, **kw)
+            call = E.HypergradientCall(wl.lower, method)
+            outs.append([t.clone() for t in call.solve(wl.vector)])
+            outs.append([t.clone() for t in call.solve(wl.vector)])   # plan + graph are reusable
+        E.settings.cuda_graph = True
+        for o in outs[1:]:
+            assert rel_l2(o, outs[0]) < 1e-5

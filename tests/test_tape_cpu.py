@@ -85,3 +85,32 @@ def test_dead_branches_and_unused_parameters():
     want = torch.autograd.grad([in_grad[i] for i in keep], [params[i] for i in keep],
                                grad_outputs=[vec[i] for i in keep])
     assert rel_l2([got[i] for i in keep], want) < 1e-9
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_native_descriptors_build_on_cpu(case):
+    """Dry run of betty_b200/plan.py: buffer arenas + bb_node descriptors for every workload family (no launch)."""
+    import numpy as np
+
+    from betty_b200.arena import ArenaLayout
+    from betty_b200.plan import NODE_DTYPE, OPS, HvpPlan
+
+    fac, kw = CASES[case]
+    wl = W.FACTORIES[fac](device="cpu", **kw)
+    loss, tape, params = trace(wl)
+    lay = ArenaLayout.like(params)
+    d, hv = lay.new("cpu"), lay.new("cpu")
+    plan = HvpPlan(tape, params, lay, d, hv, dry_run=True)
+    assert len(plan.recs) == len(plan.g.nodes) > 0
+    assert plan.recs.dtype.itemsize == NODE_DTYPE.itemsize
+    assert set(int(o) for o in plan.recs["op"]) <= set(OPS.values())
+    # every active input of every node has tangent and adjoint-tangent pointers; outputs too
+    for r, n in zip(plan.recs, plan.g.nodes):
+        for k, v in enumerate(n.ins):
+            if v is not None:
+                assert r["t"][k] != 0 and r["at"][k] != 0, (n, k)
+        assert r["t"][3] != 0 and r["at"][3] != 0 and r["a"][3] != 0
+    # parameter tangents alias the direction arena, adjoint tangents the H.d arena
+    lo, hi = d.data_ptr(), d.data_ptr() + 4 * d.numel()
+    for p in plan.g.params:
+        assert lo <= p.t.data_ptr() < hi and p.at.data_ptr() - hv.data_ptr() == p.t.data_ptr() - lo
