@@ -412,6 +412,73 @@ class HvpPlan:
         self._on_side(lambda s: N.call("bb_plan_profile", self.handle, pas, ms.ctypes.data, s))
         return ms
 
+    # ---- roofline bookkeeping -------------------------------------------------------------------
+    def node_bytes(self, i: int, pas: int) -> int:
+        """ALGORITHMIC bytes of node ``i`` in pass ``pas``: every operand the rule needs is read once and
+        every result written once (DESIGN.md "Algorithmic bytes").  Base tensors count at their own width
+        (2 B under bf16 autocast), tangents/adjoints at 4 B."""
+        n = self.g.nodes[i]
+        out_n = n.out.base.numel()
+        total = 0
+        uses_base = {"unary": (0,), "mul2": (0, 1), "gemm": (0, 1), "conv2d": (0, 1), "batchnorm": (0,),
+                     "layernorm": (0,), "softmax": (0,), "logsoftmax": (0,), "bce_logits": (0,)}.get(n.op, ())
+        base_of = {0: n.attrs.get("A", n.attrs.get("X")), 1: n.attrs.get("B", n.attrs.get("W"))}
+        for k, v in enumerate(n.ins):
+            bt = base_of.get(k) if n.op in ("gemm", "conv2d", "batchnorm", "layernorm") else (v.base if v is not None else None)
+            if k in uses_base and bt is not None and (pas != PASS_TF or n.op not in ("softmax", "logsoftmax") or True):
+                total += bt.numel() * bt.element_size()
+            if v is None:
+                continue
+            m = v.base.numel()
+            if pas == PASS_TF:
+                total += 4 * m                       # read t_x
+            elif pas == PASS_TB:
+                total += 4 * m                       # write at_x
+                if n.op in ("unary", "mul2", "gemm", "conv2d", "batchnorm", "layernorm", "softmax", "logsoftmax", "bce_logits"):
+                    total += 4 * m                   # read t_x (curvature term)
+            else:
+                total += 4 * m if v.root.param_index is None else 0
+        if pas == PASS_TF:
+            total += 4 * out_n
+        elif pas == PASS_TB:
+            total += 8 * out_n                       # read a_y and at_y
+        else:
+            total += 4 * out_n
+        if n.op == "mulc":
+            total += 4 * out_n
+        if n.op in ("maxpool2d", "embedding", "nll"):
+            idx = n.attrs.get("indices", n.attrs.get("target"))
+            total += idx.numel() * 8
+        return int(total)
+
+    def roofline(self, hbm_gbs: float, which: str = "measured", reps: int = 3) -> dict:
+        """Time every node of the two K-loop passes with CUDA events (eager, on the plan's stream) and
+        report the dominant one against the HBM roofline, plus the whole-iteration figure."""
+        names = {PASS_TF: "tangent-forward", PASS_TB: "tangent-backward"}
+        best = None
+        it_ms, it_bytes = 0.0, 0
+        rows = []
+        for pas in (PASS_TF, PASS_TB):
+            ms = np.min(np.stack([self.profile(pas) for _ in range(reps)]), axis=0)
+            for i, t in enumerate(ms):
+                b = self.node_bytes(i, pas)
+                it_ms += float(t)
+                it_bytes += b
+                rows.append((float(t), b, i, pas))
+        rows.sort(reverse=True)
+        t, b, i, pas = rows[0]
+        n = self.g.nodes[i]
+        ach = b / (t * 1e-3) / 1e9 if t > 0 else 0.0
+        top = [{"node": f"{self.g.nodes[j].op}{tuple(self.g.nodes[j].out.base.shape)}:{names[q]}", "ms": round(tt, 4),
+                "alg_MB": round(bb_ / 1e6, 3)} for tt, bb_, j, q in rows[:6]]
+        return {"bound": "hbm", "kernel": f"{n.op}{tuple(n.out.base.shape)} {names[pas]} ({n.src})",
+                "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": None,
+                "peak_source": which, "kernel_ms": t, "kernel_alg_bytes": b,
+                "iteration": {"alg_bytes": it_bytes, "sum_node_ms": it_ms,
+                              "achieved_GBps": it_bytes / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0,
+                              "frac": (it_bytes / (it_ms * 1e-3) / 1e9) / hbm_gbs if it_ms > 0 else 0.0},
+                "top_nodes": top}
+
     def describe(self) -> List[str]:
         return [f"{i:4d} {n.op:10s} {n.src:40s} out={tuple(n.out.base.shape)}" for i, n in enumerate(self.g.nodes)]
 
