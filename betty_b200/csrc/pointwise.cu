@@ -68,7 +68,10 @@ __device__ __forceinline__ void d12(int kind, float x, float s, float& d1, float
   }
 }
 
-__device__ __forceinline__ void put(float* p, int64_t o, float v, int beta) { p[o] = beta ? p[o] + v : v; }
+// a null destination means "this input's adjoint is not needed" (base adjoints of parameters)
+__device__ __forceinline__ void put(float* p, int64_t o, float v, int beta) {
+  if (p != nullptr) p[o] = beta ? p[o] + v : v;
+}
 
 constexpr int kEwThreads = 256;
 
@@ -195,9 +198,11 @@ int bb_launch_ew(const bb_node& nd, int pass, cudaStream_t s) {
   A.ty = reinterpret_cast<float*>(nd.t[3]);
   A.ay = reinterpret_cast<const float*>(nd.a[3]);
   if (pass == BB_PASS_BASE_BWD) {
+    // nd.pad0 = mask of inputs whose base adjoint is needed (activations, not parameters)
     A.gy = reinterpret_cast<const float*>(nd.a[3]);
-    A.g0 = reinterpret_cast<float*>(nd.a[0]);
-    A.g1 = reinterpret_cast<float*>(nd.a[1]);
+    A.g0 = (nd.pad0 & 1) ? reinterpret_cast<float*>(nd.a[0]) : nullptr;
+    A.g1 = (nd.pad0 & 2) ? reinterpret_cast<float*>(nd.a[1]) : nullptr;
+    if (A.g0 == nullptr && A.g1 == nullptr) return BB_OK;
   } else {
     A.gy = reinterpret_cast<const float*>(nd.at[3]);
     A.g0 = reinterpret_cast<float*>(nd.at[0]);
@@ -223,6 +228,7 @@ int bb_launch_sumall(const bb_node& nd, int pass, cudaStream_t s) {
         reinterpret_cast<double*>(nd.aux[0]));
   } else {
     const bool bb = pass == BB_PASS_BASE_BWD;
+    if (bb && !(nd.pad0 & 1)) return BB_OK;
     sum_bwd_kernel<<<grid_1d(nd.n, kEwThreads, BB_SM_COUNT * 8), kEwThreads, 0, s>>>(
         reinterpret_cast<float*>(bb ? nd.a[0] : nd.at[0]), reinterpret_cast<const float*>(bb ? nd.a[3] : nd.at[3]),
         scale, nd.n, nd.beta[0]);

@@ -173,6 +173,7 @@ inline unsigned blocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 }  // namespace
 
 int bb_launch_softmax(const bb_node& nd, int pass, cudaStream_t s) {
+  if (pass == BB_PASS_BASE_BWD && !(nd.pad0 & 1)) return BB_OK;
   const int64_t rows = nd.dims[0];
   const int D = (int)nd.dims[1];
   const int mode = nd.op == BB_OP_SOFTMAX ? 0 : 1;
@@ -188,6 +189,7 @@ int bb_launch_softmax(const bb_node& nd, int pass, cudaStream_t s) {
 }
 
 int bb_launch_nll(const bb_node& nd, int pass, cudaStream_t s) {
+  if (pass == BB_PASS_BASE_BWD && !(nd.pad0 & 1)) return BB_OK;
   const int B = (int)nd.dims[0], C = (int)nd.dims[1];
   const int64_t* target = reinterpret_cast<const int64_t*>(nd.aux[0]);
   const float scale = (float)nd.f[0];
@@ -210,6 +212,7 @@ int bb_launch_nll(const bb_node& nd, int pass, cudaStream_t s) {
 }
 
 int bb_launch_bce(const bb_node& nd, int pass, cudaStream_t s) {
+  if (pass == BB_PASS_BASE_BWD && !(nd.pad0 & 1)) return BB_OK;
   const int64_t n = nd.n;
   const float* y = reinterpret_cast<const float*>(nd.aux[0]);
   if (pass == BB_PASS_TAN_FWD) {
@@ -247,6 +250,7 @@ int bb_launch_embedding(const bb_node& nd, int pass, cudaStream_t s) {
 }
 
 int bb_launch_maxpool2d(const bb_node& nd, int pass, cudaStream_t s) {
+  if (pass == BB_PASS_BASE_BWD && !(nd.pad0 & 1)) return BB_OK;
   const int64_t planes = nd.dims[0];
   const int hw_in = (int)nd.dims[1], hw_out = (int)nd.dims[2];
   const int64_t nout = planes * hw_out;

@@ -207,9 +207,12 @@ class _Lowering:
             x = A(a[0])
             okw = {k: v for k, v in kw.items() if k not in ("dtype", "layout", "device", "pin_memory", "non_blocking")
                    and v is not None}
-            if okw or not op.out.is_floating_point() or op.out.stride() != a[0].stride():
+            if okw or not op.out.is_floating_point():
                 raise UnsupportedGraph(f"_to_copy with {kw}")
-            self.alias(x, op.out, lambda t: t)  # a dtype cast is the identity on fp32 tangents/adjoints
+            if op.out.stride() == a[0].stride():
+                self.alias(x, op.out, lambda t: t)  # a dtype cast is the identity on fp32 tangents/adjoints
+            else:
+                self.emit("copy", [x], op.out, name)  # cast that also re-lays-out (e.g. of a select view)
             return
         if name == "aten.clone.default":
             x = A(a[0])

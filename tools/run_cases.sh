@@ -7,7 +7,7 @@ out=gpurun_out/cases.log
 for c in logistic mlp lenet lenet_b300 fourconv fourconv_mini roberta fourconv_bf16 roberta_bf16; do
   echo "=== $c" >> $out
   CUDA_LAUNCH_BLOCKING=1 timeout 300 python -m pytest tests/test_plan_gpu.py -q --tb=short -p no:cacheprovider -k "test_plan_matches and [$c]" 2>&1 | grep -v "^$" | tail -25 >> $out
-  if grep -q "illegal memory\|AcceleratorError" <(tail -30 $out); then
+  if grep -q "illegal memory\|AcceleratorError\|status 7" <(tail -30 $out); then
     echo "--- sanitizer $c" >> $out
     timeout 600 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_plan_gpu.py -q --tb=no -p no:cacheprovider -k "test_plan_matches and [$c]" 2>&1 | grep -A22 "Invalid\|Error:" | head -60 >> $out
   fi
