@@ -7,7 +7,10 @@
 //       at_W = wgrad(at_y, x) + wgrad(a_y, t_x)   (split-K, atomics)      C[o][cij]   K = N*HO*WO
 //       at_b = sum_{n,y,x} at_y
 // (SURVEY.md Appendix B "Conv2d".)  Spec: oracle/plan_interp.py tf_conv2d/bb_conv2d/tb_conv2d.
+#include <stdlib.h>
+
 #include "../../include/betty_b200.h"
+#include "conv_small.h"
 #include "plan.h"
 #include "tile_gemm.cuh"
 
@@ -154,6 +157,20 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   const int64_t CKK = (int64_t)g.C * g.KH * g.KW, OKK = (int64_t)g.O * g.KH * g.KW;
   const int64_t P = (int64_t)g.N * g.HO * g.WO, PIN = (int64_t)g.N * g.H * g.W;
   int rc;
+  const bool unit = g.sh == 1 && g.sw == 1 && g.dh == 1 && g.dw == 1 && !getenv("BB200_CONV_IGEMM");
+  if (pass == BB_PASS_TAN_FWD && unit && bb_conv_small_corr_ok(g.C, g.O, g.KH, g.KW, (actX ? 1 : 0) + (actW ? 1 : 0))) {
+    SmallConvArgs A{};
+    int np = 0;
+    if (actX) { A.in[np] = nd.t[0]; A.dt_in[np] = BB_F32; A.w[np] = nd.base[1]; A.dt_w[np] = nd.dt[1]; ++np; }
+    if (actW) { A.in[np] = nd.base[0]; A.dt_in[np] = nd.dt[0]; A.w[np] = nd.t[1]; A.dt_w[np] = BB_F32; ++np; }
+    A.npairs = np; A.mode = 0;
+    A.out = reinterpret_cast<float*>(nd.t[3]);
+    A.bias = actB ? reinterpret_cast<const float*>(nd.t[2]) : nullptr;
+    A.beta = 0;
+    A.N = g.N; A.CI = g.C; A.H = g.H; A.W = g.W; A.CO = g.O; A.KH = g.KH; A.KW = g.KW; A.HO = g.HO; A.WO = g.WO;
+    A.ph = g.ph; A.pw = g.pw; A.C_orig = g.C;
+    return bb_conv_small_corr(A, s);
+  }
   if (pass == BB_PASS_TAN_FWD) {
     WLoad la{};
     ImLoad lb{};
@@ -169,10 +186,23 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   const bool base = pass == BB_PASS_BASE_BWD;
   const void* gy = base ? nd.a[3] : nd.at[3];
   const int need = base ? nd.pad0 : nd.active;
-  if (need & 1) {
+  if ((need & 1) && unit && bb_conv_small_corr_ok(g.O, g.C, g.KH, g.KW, (!base && actW) ? 2 : 1)) {
+    SmallConvArgs A{};
+    int np = 0;
+    A.in[np] = gy; A.dt_in[np] = BB_F32; A.w[np] = nd.base[1]; A.dt_w[np] = nd.dt[1]; ++np;
+    if (!base && actW) { A.in[np] = nd.a[3]; A.dt_in[np] = BB_F32; A.w[np] = nd.t[1]; A.dt_w[np] = BB_F32; ++np; }
+    A.npairs = np; A.mode = 1;
+    A.out = reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]);
+    A.bias = nullptr;
+    A.beta = nd.beta[0];
+    A.N = g.N; A.CI = g.O; A.H = g.HO; A.W = g.WO; A.CO = g.C; A.KH = g.KH; A.KW = g.KW; A.HO = g.H; A.WO = g.W;
+    A.ph = g.KH - 1 - g.ph; A.pw = g.KW - 1 - g.pw; A.C_orig = g.C;
+    rc = bb_conv_small_corr(A, s);
+    if (rc) return rc;
+  } else if (need & 1) {
     WLoadD la{};
     GLoadD lb{};
-    la.g = g; la.k_fast = 0;
+    la.g = g; la.k_fast = 1;
     lb.g = g; lb.k_fast = 0;
     int np = 0;
     la.p[np] = nd.base[1]; la.dt[np] = nd.dt[1]; lb.p[np] = gy; lb.dt[np] = BB_F32; ++np;
@@ -181,11 +211,27 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
     rc = launch(la, lb, sc, g.C, PIN, OKK, np, 1, s);
     if (rc) return rc;
   }
-  if (need & 2) {
+  if ((need & 2) && unit && bb_conv_small_wgrad_ok(g.O, g.C, g.H, g.W, g.HO, g.WO, g.KH, g.KW)) {
+    SmallConvArgs A{};
+    int np = 0;
+    A.g[np] = gy; A.dt_g[np] = BB_F32; A.in[np] = nd.base[0]; A.dt_in[np] = nd.dt[0]; ++np;
+    if (!base && actX) { A.g[np] = nd.a[3]; A.dt_g[np] = BB_F32; A.in[np] = nd.t[0]; A.dt_in[np] = BB_F32; ++np; }
+    A.npairs = np;
+    float* out = reinterpret_cast<float*>(base ? nd.a[1] : nd.at[1]);
+    if (!nd.beta[1]) {
+      BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * g.O * CKK, s));
+      bb_launch_tally += 1;
+    }
+    A.out = out;
+    A.N = g.N; A.CI = g.C; A.H = g.H; A.W = g.W; A.CO = g.O; A.KH = g.KH; A.KW = g.KW; A.HO = g.HO; A.WO = g.WO;
+    A.ph = g.ph; A.pw = g.pw; A.C_orig = g.C;
+    rc = bb_conv_small_wgrad(A, s);
+    if (rc) return rc;
+  } else if (need & 2) {
     GLoadW la{};
     ImLoadT lb{};
     la.g = g; la.k_fast = 1;
-    lb.im.g = g; lb.k_fast = 0;
+    lb.im.g = g; lb.k_fast = 1;
     int np = 0;
     la.p[np] = gy; la.dt[np] = BB_F32; lb.im.p[np] = nd.base[0]; lb.im.dt[np] = nd.dt[0]; ++np;
     if (!base && actX) { la.p[np] = nd.a[3]; la.dt[np] = BB_F32; lb.im.p[np] = nd.t[0]; lb.im.dt[np] = BB_F32; ++np; }

@@ -36,3 +36,12 @@ def checksum(wl):
         if torch.is_tensor(b):
             s += float(b.double().sum())
     return s
+
+
+def to_double(wl):
+    """fp64 copy of a workload in place (modules, floating inputs, direction)."""
+    wl.lower.module.double()
+    wl.upper.module.double()
+    wl.lower.cur_batch = tuple(b.double() if torch.is_tensor(b) and b.is_floating_point() else b for b in wl.lower.cur_batch)
+    wl.vector = tuple(v.double() for v in wl.vector)
+    return wl

@@ -8,7 +8,7 @@ from betty_b200 import workloads as W
 from betty_b200.ir import UnsupportedGraph, lower_tape
 from betty_b200.trace import record_tape
 from oracle.plan_interp import Interp
-from tests.helpers import rel_l2
+from tests.helpers import rel_l2, to_double
 
 CASES = {
     "logistic": ("logistic_regression_hpo", dict()),
@@ -18,14 +18,6 @@ CASES = {
     "fourconv_mini": ("implicit_maml", dict(n=2, hidden=4, image="miniimagenet")),
     "roberta": ("bert_data_reweighting", dict(batch=3, seq=7, tiny=True)),
 }
-
-
-def to_double(wl):
-    wl.lower.module.double()
-    wl.upper.module.double()
-    wl.lower.cur_batch = tuple(b.double() if torch.is_tensor(b) and b.is_floating_point() else b for b in wl.lower.cur_batch)
-    wl.vector = tuple(v.double() for v in wl.vector)
-    return wl
 
 
 def trace(wl):
