@@ -43,6 +43,8 @@ _SIGS = {
     "bb_mt_sumsq": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], 1),
     "bb_fd_eps": ([C.c_void_p, C.c_double, C.c_void_p], 1),
     "bb_mt_fd_combine": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], 1),
+    "bb_gemm_bf16_tc": ([C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
+                         C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p], 1),
     "bb_node_bytes": ([], 0),
     "bb_plan_create": ([C.c_void_p, C.c_int, C.POINTER(C.c_void_p)], 0),
     "bb_plan_destroy": ([C.c_void_p], 0),

@@ -7,7 +7,10 @@
 //
 // (SURVEY.md Appendix B "Linear": 6 GEMMs per iteration; here 3 dual launches.)  Spec:
 // oracle/plan_interp.py tf_gemm/bb_gemm/tb_gemm.
+#include <stdlib.h>
+
 #include "../../include/betty_b200.h"
+#include "gemm_tc.h"
 #include "plan.h"
 #include "tile_gemm.cuh"
 
@@ -24,17 +27,33 @@ struct Mat {  // a (possibly transposed) strided matrix view
 
 inline Mat T(const Mat& m) { return Mat{m.p, m.dt, m.cs, m.rs, m.bs}; }
 
+// does {m*rs + n*cs (+ b*bs)} cover exactly [0, M*N*batch)?  (needed before a memset + atomic split-K)
 inline bool dense_block(int64_t M, int64_t N, int64_t batch, int64_t rs, int64_t cs, int64_t bs) {
-  const bool rowmajor = (cs == 1 && rs == N), colmajor = (rs == 1 && cs == M);
-  return (rowmajor || colmajor || M == 1 || N == 1) && (batch == 1 || bs == M * N) &&
-         ((M == 1 || N == 1) ? (rs == 1 || cs == 1 || M * N == 1 || (M == 1 ? cs == 1 : rs == 1)) : true);
+  bool ok;
+  if (M == 1) ok = (cs == 1 || N == 1);
+  else if (N == 1) ok = (rs == 1);
+  else ok = (cs == 1 && rs == N) || (rs == 1 && cs == M);
+  return ok && (batch == 1 || bs == M * N);
 }
 
 // out (M x N) (beta)= sum_p L_p (M x K) . R_p (K x N)  [+ bias]
 int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const Mat* L, const Mat* R, float* out,
              int64_t ors, int64_t ocs, int64_t obs, int beta, const float* bias, int64_t bias_stride,
-             cudaStream_t s) {
+             cudaStream_t s, bool tensor_cores = false) {
   if (M <= 0 || N <= 0 || batch <= 0) return BB_OK;
+  if (tensor_cores && npairs > 0 && bb_gemm_tc_eligible(M, N, K, batch)) {
+    // bf16-autocast configuration: tcgen05 path (operands rounded to bf16, fp32 accumulation in TMEM)
+    TcGemmArgs G{};
+    G.M = M; G.N = N; G.K = K; G.npairs = npairs;
+    for (int p = 0; p < npairs; ++p) {
+      G.a[p] = L[p].p; G.dta[p] = L[p].dt; G.ars[p] = L[p].rs; G.acs[p] = L[p].cs; G.a_kfast[p] = L[p].cs == 1;
+      G.b[p] = R[p].p; G.dtb[p] = R[p].dt; G.brs[p] = R[p].rs; G.bcs[p] = R[p].cs; G.b_kfast[p] = R[p].rs == 1;
+    }
+    G.out = out; G.ors = ors; G.ocs = ocs; G.beta = beta; G.bias = bias; G.bias_stride = bias_stride;
+    G.allow_split = 1;
+    G.out_dense = dense_block(M, N, 1, ors, ocs, 0);
+    return bb_gemm_tc_run(G, s);
+  }
   StridedLoad la{}, lb{};
   for (int p = 0; p < npairs; ++p) {
     la.p[p] = L[p].p; la.dt[p] = L[p].dt; la.rs[p] = L[p].rs; la.cs[p] = L[p].cs; la.bs[p] = L[p].bs;
@@ -126,13 +145,14 @@ int bb_launch_gemm(const bb_node& nd, int pass, cudaStream_t s) {
   const Mat tA{nd.t[0], BB_F32, sa[0], sa[1], sa[2]};
   const Mat tB{nd.t[1], BB_F32, sb[0], sb[1], sb[2]};
   int rc;
+  const bool tc = (nd.kind & 1) && !getenv("BB200_NO_TC");   // set by plan.py for bf16-autocast graphs
   if (pass == BB_PASS_TAN_FWD) {
     Mat L[2], R[2];
     int np = 0;
     if (actA) { L[np] = tA; R[np] = B; ++np; }
     if (actB) { L[np] = A; R[np] = tB; ++np; }
     return run_gemm(M, N, K, batch, np, L, R, reinterpret_cast<float*>(nd.t[3]), sc[0], sc[1], sc[2], 0,
-                    actBias ? reinterpret_cast<const float*>(nd.t[2]) : nullptr, nd.stride[2][0], s);
+                    actBias ? reinterpret_cast<const float*>(nd.t[2]) : nullptr, nd.stride[2][0], s, tc);
   }
   const bool base = pass == BB_PASS_BASE_BWD;
   const Mat gC{base ? nd.a[3] : nd.at[3], BB_F32, sc[0], sc[1], sc[2]};   // adjoint being propagated
@@ -142,14 +162,14 @@ int bb_launch_gemm(const bb_node& nd, int pass, cudaStream_t s) {
     Mat L[2] = {gC, aC}, R[2] = {T(B), T(tB)};
     const int np = (!base && actB) ? 2 : 1;
     rc = run_gemm(M, K, N, batch, np, L, R, reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]), sa[0], sa[1], sa[2],
-                  nd.beta[0], nullptr, 0, s);
+                  nd.beta[0], nullptr, 0, s, tc);
     if (rc) return rc;
   }
   if (need & 2) {  // (K x N) = A^T (K x M) . gC (M x N)  [+ tA^T . aC]
     Mat L[2] = {T(A), T(tA)}, R[2] = {gC, aC};
     const int np = (!base && actA) ? 2 : 1;
     rc = run_gemm(K, N, M, batch, np, L, R, reinterpret_cast<float*>(base ? nd.a[1] : nd.at[1]), sb[0], sb[1], sb[2],
-                  nd.beta[1], nullptr, 0, s);
+                  nd.beta[1], nullptr, 0, s, tc);
     if (rc) return rc;
   }
   if (need & 4) {

@@ -1,0 +1,322 @@
+// K5 tensor-core path: dual-product GEMM on the 5th-generation tensor cores (tcgen05.mma, kind::f16 with
+// bf16 operands, fp32 accumulation in TMEM) for the bf16-autocast configurations.
+//
+//   D[m][n] (beta/atomic)= sum over up to two operand pairs p of  sum_k A_p[m][k] * B_p[k][n]   (+ bias[n])
+//
+// Operand staging is done by the four producer warps rather than by TMA because the second-order
+// operands are heterogeneous: base activations / weights are bf16 (autocast), tangents and adjoints are
+// fp32 slices of arenas, and half of them are consumed through transposed views.  The producers read
+// global memory with whatever strides the operand has, convert to bf16 and write the canonical K-major
+// SWIZZLE_128B layout the UMMA shared-memory descriptors expect (row pitch 128 B, 16-byte chunk index
+// XOR (row % 8), 8-row groups 1024 B apart), then publish the stage through an mbarrier after a
+// generic->async proxy fence.  One elected thread of the MMA warp issues 4 x tcgen05.mma (M=128, N=128,
+// K=16) per 64-wide k-block into a 128-column TMEM accumulator; tcgen05.commit releases the stage.  After
+// the last k-block the producer warps turn into the epilogue: tcgen05.ld (32 lanes x 32 columns per warp)
+// -> registers -> strided global store with beta / atomic split-K / bias handling.
+//
+// Roles (160 threads): warps 0-3 producers + epilogue (warp w owns TMEM lanes 32w..32w+31), warp 4 MMA
+// issue + TMEM alloc/dealloc.  3-stage ring, 32 KB per stage.
+#include <cuda_bf16.h>
+
+#include "../../include/betty_b200.h"
+#include "bb_common.cuh"
+#include "gemm_tc.h"
+#include "plan.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int NPROD = 128;                   // producer / epilogue threads
+constexpr int NTHREADS = NPROD + 32;
+constexpr int TILE_BYTES = BM * BK * 2;      // 16 KB per operand per stage
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;
+constexpr int TMEM_COLS = 128;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// start address >> 4 | LBO(=1, unused for swizzled K-major) << 16 | SBO (1024 B >> 4) << 32 | version 1 << 46 |
+// layout type SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format BF16 (1) @7/@10,
+// a/b major K (0), n_dim = N>>3 @17, m_dim = M>>4 @24
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Stage one (128 rows x 64 k) operand tile.  Element (row, k) of the tile = src[(row0+row)*rs + (k0+k)*cs].
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int dt, int64_t rs, int64_t cs, int64_t row0,
+                                           int64_t nrows, int64_t k0, int64_t kend, int k_fast, int tid) {
+  if (k_fast) {
+    // 8 threads per row, one 16-byte (8 x bf16) chunk each: coalesced along k
+    const int chunk = tid & 7;
+#pragma unroll 4
+    for (int it = 0; it < BM / (NPROD / 8); ++it) {
+      const int row = (tid >> 3) + it * (NPROD / 8);
+      const int64_t gr = row0 + row, gk = k0 + chunk * 8;
+      float v[8];
+      if (gr < nrows && gk + 8 <= kend && cs == 1) {
+        const int64_t off = gr * rs + gk;
+        if (dt == BB_F32) {
+          const float* p = reinterpret_cast<const float*>(src) + off;
+          if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = p[e];
+          }
+        } else {
+          const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(src) + off;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __bfloat162float(p[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int64_t kk = gk + e;
+          v[e] = (gr < nrows && kk < kend) ? bb::ldf(src, gr * rs + kk * cs, dt) : 0.f;
+        }
+      }
+      uint4 q;
+      q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+    }
+  } else {
+    // one row per thread (consecutive rows are adjacent in memory): coalesced along the row index
+    const int row = tid;
+    const int64_t gr = row0 + row;
+#pragma unroll 2
+    for (int chunk = 0; chunk < 8; ++chunk) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int64_t kk = k0 + chunk * 8 + e;
+        v[e] = (gr < nrows && kk < kend) ? bb::ldf(src, gr * rs + kk * cs, dt) : 0.f;
+      }
+      uint4 q;
+      q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms must start on a 1024-byte boundary of the *shared* address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[3], empty[3], accum, tmem slot
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int split = blockIdx.z;
+  // k range of this split, in whole k-blocks
+  const int64_t kblocks_total = (G.K + BK - 1) / BK;
+  const int64_t kb_per = (kblocks_total + G.ksplit - 1) / G.ksplit;
+  const int64_t kb_beg = (int64_t)split * kb_per;
+  int64_t kb_end = kb_beg + kb_per;
+  if (kb_end > kblocks_total) kb_end = kblocks_total;
+  const int nkb = (int)(kb_end > kb_beg ? kb_end - kb_beg : 0);
+  const int total_kb = nkb * G.npairs;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, NPROD);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- producers ----------------
+    for (int it = 0; it < total_kb; ++it) {
+      const int s = it % STAGES;
+      if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+      const int pair = it / nkb;
+      const int64_t k0 = (kb_beg + (it % nkb)) * BK;
+      int64_t kend = (kb_end * BK < G.K) ? kb_end * BK : G.K;
+      uint8_t* st = smem + s * STAGE_BYTES;
+      // A tile: rows = m, element(m,k) = A[m*ars + k*acs]; B tile: rows = n, element(n,k) = B[k*brs + n*bcs]
+      stage_tile(st, G.a[pair], G.dta[pair], G.ars[pair], G.acs[pair], m0, G.M, k0, kend, G.a_kfast[pair], tid);
+      stage_tile(st + TILE_BYTES, G.b[pair], G.dtb[pair], G.bcs[pair], G.brs[pair], n0, G.N, k0, kend, G.b_kfast[pair], tid);
+      fence_proxy_async();
+      mbar_arrive(full0 + 8 * s);
+    }
+    // ---------------- epilogue ----------------
+    if (total_kb > 0) {
+      mbar_wait(accum, 0);
+      tc_fence_after();
+    }
+    const int64_t row = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      if (total_kb > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row < G.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t col = n0 + c * 32 + j;
+          if (col < G.N) {
+            float v = __uint_as_float(r[j]);
+            if (G.bias != nullptr && split == 0) v += G.bias[col * G.bias_stride];
+            float* dst = G.out + row * G.ors + col * G.ocs;
+            if (G.ksplit > 1) atomicAdd(dst, v);
+            else *dst = G.beta ? *dst + v : v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---------------- MMA issuer (warp 4, one elected lane) ----------------
+    if (lane == 0) {
+      for (int it = 0; it < total_kb; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_bf16(tmem_base, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);   // stage free once these MMAs have read it
+      }
+      if (total_kb > 0) umma_commit(accum);
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
+}  // namespace
+
+bool bb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int64_t batch) {
+  return batch == 1 && M >= 64 && N >= 64 && K >= 64;
+}
+
+int bb_gemm_tc_run(const TcGemmArgs& G0, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    configured = true;
+  }
+  TcGemmArgs G = G0;
+  const int64_t tiles = ((G.M + BM - 1) / BM) * ((G.N + BN - 1) / BN);
+  const int64_t kblocks = (G.K + BK - 1) / BK;
+  int ksplit = 1;
+  if (G.allow_split && tiles < BB_SM_COUNT / 2 && kblocks >= 8) {
+    int64_t want = (BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 4;
+    ksplit = (int)(want < maxs ? want : maxs);
+    if (ksplit > 32) ksplit = 32;
+    if (ksplit < 1) ksplit = 1;
+  }
+  G.ksplit = ksplit;
+  if (ksplit > 1 && !G.beta) {
+    if (!G.out_dense) {
+      G.ksplit = ksplit = 1;
+    } else {
+      BB_CUDA_TRY(cudaMemsetAsync(G.out, 0, sizeof(float) * G.M * G.N, s));
+      bb_launch_tally += 1;
+    }
+  }
+  dim3 grid((unsigned)((G.N + BN - 1) / BN), (unsigned)((G.M + BM - 1) / BM), (unsigned)ksplit);
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(G);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+extern "C" int bb_gemm_bf16_tc(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs,
+                               const void* B, int dtB, int64_t brs, int64_t bcs, float* C, int64_t crs, int64_t ccs,
+                               int beta, void* stream) {
+  TcGemmArgs G{};
+  G.M = M; G.N = N; G.K = K; G.npairs = 1;
+  G.a[0] = A; G.dta[0] = dtA; G.ars[0] = ars; G.acs[0] = acs; G.a_kfast[0] = acs == 1;
+  G.b[0] = B; G.dtb[0] = dtB; G.brs[0] = brs; G.bcs[0] = bcs; G.b_kfast[0] = brs == 1;
+  G.out = C; G.ors = crs; G.ocs = ccs; G.beta = beta; G.bias = nullptr; G.bias_stride = 0;
+  G.allow_split = 1;
+  G.out_dense = (ccs == 1 && crs == N) || (crs == 1 && ccs == M);
+  return bb_gemm_tc_run(G, (cudaStream_t)stream);
+}

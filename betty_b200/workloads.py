@@ -214,14 +214,15 @@ def logistic_hpo(device="cpu", method="neumann", n=500, dim=20, K=5, alpha=1.0, 
 
 
 def mlp_reweight(device="cpu", method="cg", batch=64, din=32, hidden=64, classes=10, depth=2, K=5,
-                 alpha=1.0, l2=0.05, seed=0):
+                 alpha=1.0, l2=0.05, precision="fp32", seed=0):
     """Small Linear/ReLU/weighted-CE problem used for fast kernel-level parity tests."""
     torch.manual_seed(seed)
     x = torch.randn(batch, din)
     y = torch.randint(0, classes, (batch,))
     lower = MLPNet(din, hidden, classes, depth)
     upper = MetaWeightNet(16)
-    cfg = ShimConfig(type=method, neumann_iterations=K, neumann_alpha=alpha, cg_iterations=K, cg_alpha=alpha)
+    cfg = ShimConfig(type=method, precision=precision, neumann_iterations=K, neumann_alpha=alpha, cg_iterations=K,
+                     cg_alpha=alpha)
     return _pair("mlp_reweight", lower, _reweighted_ce_step(l2), upper, cfg, (x, y), device,
                  describe=dict(batch=batch, K=K, method=method))
 
@@ -261,15 +262,15 @@ def fourconv_imaml(device="cpu", method="neumann", n=25, ways=5, image="omniglot
 
 
 def roberta_reweight(device="cpu", method="cg", batch=16, seq=50, K=10, alpha=1.0, l2=5e-3, precision="fp32",
-                     tiny=False, seed=0):
+                     tiny=False, tiny_hidden=32, seed=0):
     """Config 5: HF RobertaForSequenceClassification (random init, eager attention, dropout 0) with
     MWN-weighted CE (reference examples/bert_data_reweighting/main.py:117-128, model.py:11-59)."""
     from transformers import RobertaConfig, RobertaForSequenceClassification
 
     torch.manual_seed(seed)
     if tiny:
-        hc = RobertaConfig(vocab_size=120, hidden_size=32, num_hidden_layers=2, num_attention_heads=4,
-                           intermediate_size=64, max_position_embeddings=seq + 4, num_labels=2,
+        hc = RobertaConfig(vocab_size=120, hidden_size=tiny_hidden, num_hidden_layers=2, num_attention_heads=4,
+                           intermediate_size=2 * tiny_hidden, max_position_embeddings=seq + 4, num_labels=2,
                            hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     else:
         hc = RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,

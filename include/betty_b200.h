@@ -91,6 +91,11 @@ int bb_plan_neumann_loop(bb_plan* plan, int iterations, float alpha, float* v /*
 int bb_plan_cg_loop(bb_plan* plan, int iterations, float cg_alpha, float* x, float* r, float* p /*direction*/,
                     const float* hp, int64_t n, void* ws, int use_graph, void* stream);
 
+/* ---- K5 tensor-core building block, exposed for unit tests: C (beta)= A.B with operands rounded to bf16,
+ *      fp32 accumulation in TMEM (tcgen05.mma).  A[m][k] = A[m*ars+k*acs], B[k][n] = B[k*brs+n*bcs]; dt: 0 f32, 1 bf16 */
+int bb_gemm_bf16_tc(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs, const void* B,
+                    int dtB, int64_t brs, int64_t bcs, float* C, int64_t crs, int64_t ccs, int beta, void* stream);
+
 const char* bb_version(void);
 
 #ifdef __cplusplus
