@@ -100,9 +100,13 @@ template <int KW, int TPT>  // TPT = tasks per thread (1 or 2)
 __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(const __grid_constant__ SmallConvArgs A) {
   extern __shared__ float sm[];
   const int O = A.CO, C = A.CI;  // here CO = O (rows of dW), CI = C
+  // odd row pitches: tasks of a warp read the same column of different rows/planes -- with W = 32 every
+  // row would otherwise start in the same shared-memory bank
+  const int gp = A.WO | 1, ip = A.W | 1;
+  const int gplane = (A.HO * gp) | 1, iplane = (A.H * ip) | 1;
   const int gsz = O * A.HO * A.WO, isz = C * A.H * A.W;
   float* gs = sm;
-  float* is = sm + gsz;
+  float* is = sm + O * gplane;
   const int tasks = O * C * A.KH;
   int ns = 1;
   if (TPT == 1) {
@@ -128,8 +132,14 @@ __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(const __grid_cons
   for (int n = blockIdx.x; n < A.N; n += gridDim.x) {
     for (int p = 0; p < A.npairs; ++p) {
       __syncthreads();
-      for (int e = threadIdx.x; e < gsz; e += blockDim.x) gs[e] = bb::ldf(A.g[p], (int64_t)n * gsz + e, A.dt_g[p]);
-      for (int e = threadIdx.x; e < isz; e += blockDim.x) is[e] = bb::ldf(A.in[p], (int64_t)n * isz + e, A.dt_in[p]);
+      for (int e = threadIdx.x; e < gsz; e += blockDim.x) {
+        const int pl = e / (A.HO * A.WO), r = e - pl * (A.HO * A.WO), yy = r / A.WO, xx = r - yy * A.WO;
+        gs[pl * gplane + yy * gp + xx] = bb::ldf(A.g[p], (int64_t)n * gsz + e, A.dt_g[p]);
+      }
+      for (int e = threadIdx.x; e < isz; e += blockDim.x) {
+        const int pl = e / (A.H * A.W), r = e - pl * (A.H * A.W), yy = r / A.W, xx = r - yy * A.W;
+        is[pl * iplane + yy * ip + xx] = bb::ldf(A.in[p], (int64_t)n * isz + e, A.dt_in[p]);
+      }
       __syncthreads();
 #pragma unroll
       for (int u = 0; u < TPT; ++u) {
@@ -137,8 +147,8 @@ __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(const __grid_cons
         for (int y = slice[u]; y < A.HO; y += ns) {
           const int hy = y - A.ph + ti[u];
           if (hy < 0 || hy >= A.H) continue;
-          const float* grow = gs + (to[u] * A.HO + y) * A.WO;
-          const float* irow = is + (tc[u] * A.H + hy) * A.W;
+          const float* grow = gs + to[u] * gplane + y * gp;
+          const float* irow = is + tc[u] * iplane + hy * ip;
           float win[KW];
 #pragma unroll
           for (int j = 0; j < KW - 1; ++j) {
@@ -192,15 +202,20 @@ int bb_conv_small_corr(const SmallConvArgs& A, cudaStream_t s) {
   return A.KW == 3 ? launch_corr<16, 3>(A, s) : launch_corr<16, 5>(A, s);
 }
 
+static size_t wgrad_smem_bytes(int O, int C, int H, int W, int HO, int WO) {
+  const size_t gplane = (size_t)(HO * (WO | 1)) | 1, iplane = (size_t)(H * (W | 1)) | 1;
+  return sizeof(float) * (O * gplane + C * iplane);
+}
+
 bool bb_conv_small_wgrad_ok(int O, int C, int H, int W, int HO, int WO, int KH, int KW) {
   if (KW != 3 && KW != 5) return false;
   if (O * C * KH > 512) return false;
-  return sizeof(float) * ((size_t)O * HO * WO + (size_t)C * H * W) <= 48 * 1024;
+  return wgrad_smem_bytes(O, C, H, W, HO, WO) <= 48 * 1024;
 }
 
 int bb_conv_small_wgrad(const SmallConvArgs& A, cudaStream_t s) {
   const int tasks = A.CO * A.CI * A.KH;
-  const size_t smem = sizeof(float) * ((size_t)A.CO * A.HO * A.WO + (size_t)A.CI * A.H * A.W);
+  const size_t smem = wgrad_smem_bytes(A.CO, A.CI, A.H, A.W, A.HO, A.WO);
   int grid = BB_SM_COUNT * 4;
   if (grid > A.N) grid = A.N;
   if (tasks <= 256) {

@@ -100,7 +100,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int d
   if (k_fast) {
     // 8 threads per row, one 16-byte (8 x bf16) chunk each: coalesced along k
     const int chunk = tid & 7;
-#pragma unroll 4
+#pragma unroll 2
     for (int it = 0; it < BM / (NPROD / 8); ++it) {
       const int row = (tid >> 3) + it * (NPROD / 8);
       const int64_t gr = row0 + row, gk = k0 + chunk * 8;
@@ -118,6 +118,11 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int d
           }
         } else {
           const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(src) + off;
+          if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(p);   // already bf16: copy the 16-byte chunk through
+            *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = raw;
+            continue;
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = __bfloat162float(p[e]);
         }
@@ -133,25 +138,41 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int d
       *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
     }
   } else {
-    // one row per thread (consecutive rows are adjacent in memory): coalesced along the row index
+    // one row per thread (consecutive rows are adjacent in memory): every load instruction is coalesced
+    // across the warp.  Loads are issued in batches of 32 before any use so that 32 requests per thread
+    // are in flight (a per-element load->convert->store chain is latency-serialised).
     const int row = tid;
     const int64_t gr = row0 + row;
-#pragma unroll 2
-    for (int chunk = 0; chunk < 8; ++chunk) {
-      float v[8];
+    const bool row_ok = gr < nrows;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+      const int64_t kb = k0 + half * 32;
+      if (dt == BB_F32) {
+        const float* p = reinterpret_cast<const float*>(src) + gr * rs + kb * cs;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int64_t kk = k0 + chunk * 8 + e;
-        v[e] = (gr < nrows && kk < kend) ? bb::ldf(src, gr * rs + kk * cs, dt) : 0.f;
+        for (int e = 0; e < 32; ++e) v[e] = (row_ok && kb + e < kend) ? p[(int64_t)e * cs] : 0.f;
+      } else {
+        const unsigned short* p = reinterpret_cast<const unsigned short*>(src) + gr * rs + kb * cs;
+        unsigned short raw[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) raw[e] = (row_ok && kb + e < kend) ? p[(int64_t)e * cs] : (unsigned short)0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(((uint32_t)raw[e]) << 16);
       }
-      uint4 q;
-      q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
-      *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int chunk = half * 4 + c;
+        uint4 q;
+        q.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]); q.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+        q.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]); q.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+        *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on a 1024-byte boundary of the *shared* address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

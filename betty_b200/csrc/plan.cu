@@ -46,6 +46,12 @@ int dispatch(const bb_node& nd, int pass, cudaStream_t s) {
       return bb_launch_bce(nd, pass, s);
     case BB_OP_EMBEDDING:
       return bb_launch_embedding(nd, pass, s);
+    case BB_OP_DIAGSHIFT: {
+      if (pass != BB_PASS_TAN_BWD) return BB_OK;
+      bb_launch_tally += 1;
+      return bb_mt_axpby(reinterpret_cast<const bb_mt_chunk*>(nd.aux[0]), (int)nd.dims[0], (float)nd.f[0], nullptr, 1.0f,
+                         (void*)s);
+    }
     default:
       return BB_ERR_UNSUPPORTED;
   }

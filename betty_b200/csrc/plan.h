@@ -23,6 +23,7 @@ enum bb_op {
   BB_OP_NLL = 14,       // dims = B,C  aux[0]=int64 target  kind=reduction(0 none,1 mean,2 sum) f[0]=scale
   BB_OP_BCE_LOGITS = 15,// mean reduction               n  aux[0] = fp32 targets
   BB_OP_EMBEDDING = 16, // dims = nidx,D,V,padding_idx  aux[0] = int64 indices
+  BB_OP_DIAGSHIFT = 17, // folded c*sum((w-const)^2): at_w += f[0]*t_w over aux[0] = bb_mt_chunk[dims[0]] {a=t_w, b=at_w}
 };
 
 enum bb_unary_kind { BB_U_RELU = 1, BB_U_GELU = 2, BB_U_TANH = 3, BB_U_SIGMOID = 4, BB_U_POW = 5, BB_U_SCALE = 6 };

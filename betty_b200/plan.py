@@ -18,7 +18,7 @@ from .ir import Graph, Node, UnsupportedGraph, Val, _is_dense, lower_tape
 BB_MAX_DIMS = 6
 OPS = {"unary": 1, "copy": 2, "add2": 3, "mulc": 4, "mul2": 5, "sumall": 6, "gemm": 7, "conv2d": 8,
        "maxpool2d": 9, "batchnorm": 10, "layernorm": 11, "softmax": 12, "logsoftmax": 13, "nll": 14,
-       "bce_logits": 15, "embedding": 16}
+       "bce_logits": 15, "embedding": 16, "diagshift": 17}
 UNARY = {"relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4, "pow": 5, "scale": 6, "neg": 6}
 PASS_BB, PASS_TF, PASS_TB = 0, 1, 2
 
@@ -143,10 +143,11 @@ class HvpPlan:
         for i, n in enumerate(g.nodes):
             r = recs[i]
             r["op"] = OPS[n.op]
-            r["active"] = sum(1 << k for k, v in enumerate(n.ins) if v is not None)
-            r["pad0"] = sum(1 << k for k, v in enumerate(n.ins) if v is not None and v.root.param_index is None)
-            for k, b in enumerate(n.beta[:4]):
-                r["beta"][k] = b
+            if n.op != "diagshift":   # (its inputs are a parameter list, not operand slots)
+                r["active"] = sum(1 << k for k, v in enumerate(n.ins) if v is not None)
+                r["pad0"] = sum(1 << k for k, v in enumerate(n.ins) if v is not None and v.root.param_index is None)
+                for k, b in enumerate(n.beta[:4]):
+                    r["beta"][k] = b
             getattr(self, "_n_" + n.op)(n, r)
         self.recs = recs
         handle = C.c_void_p()
@@ -193,6 +194,19 @@ class HvpPlan:
                 continue
             for d, st in enumerate(t.stride()):
                 r["stride"][s][d] = st
+
+    def _n_diagshift(self, n: Node, r):
+        from .arena import ChunkTable
+
+        ts = [self.buf(p, "t") for p in n.ins]
+        ats = [self.buf(p, "at") for p in n.ins]
+        tab = ChunkTable([t.data_ptr() for t in ts], [t.data_ptr() for t in ats], [t.numel() for t in ts], self.dev,
+                         keep=(ts, ats))
+        self._keep.append(tab.dev)
+        r["aux"][0] = tab.ptr
+        r["dims"][0] = tab.n
+        r["f"][0] = n.attrs["coef"]
+        r["n"] = sum(t.numel() for t in ts)
 
     def _n_unary(self, n: Node, r):
         x = n.ins[0]
@@ -421,6 +435,8 @@ class HvpPlan:
         every result written once (DESIGN.md "Algorithmic bytes").  Base tensors count at their own width
         (2 B under bf16 autocast), tangents/adjoints at 4 B."""
         n = self.g.nodes[i]
+        if n.op == "diagshift":
+            return 12 * sum(p.base.numel() for p in n.ins) if pas == PASS_TB else 0
         out_n = n.out.base.numel()
         total = 0
         uses_base = {"unary": (0,), "mul2": (0, 1), "gemm": (0, 1), "conv2d": (0, 1), "batchnorm": (0,),
@@ -472,9 +488,10 @@ class HvpPlan:
         t, b, i, pas = rows[0]
         n = self.g.nodes[i]
         ach = b / (t * 1e-3) / 1e9 if t > 0 else 0.0
-        top = [{"node": f"{self.g.nodes[j].op}{tuple(self.g.nodes[j].out.base.shape)}:{names[q]}", "ms": round(tt, 4),
+        shp = lambda nd: tuple(nd.out.base.shape) if nd.out is not None else ("params",)
+        top = [{"node": f"{self.g.nodes[j].op}{shp(self.g.nodes[j])}:{names[q]}", "ms": round(tt, 4),
                 "alg_MB": round(bb_ / 1e6, 3)} for tt, bb_, j, q in rows[:6]]
-        return {"bound": "hbm", "kernel": f"{n.op}{tuple(n.out.base.shape)} {names[pas]} ({n.src})",
+        return {"bound": "hbm", "kernel": f"{n.op}{shp(n)} {names[pas]} ({n.src})",
                 "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": None,
                 "peak_source": which, "kernel_ms": t, "kernel_alg_bytes": b,
                 "iteration": {"alg_bytes": it_bytes, "sum_node_ms": it_ms,
@@ -483,7 +500,8 @@ class HvpPlan:
                 "top_nodes": top}
 
     def describe(self) -> List[str]:
-        return [f"{i:4d} {n.op:10s} {n.src:40s} out={tuple(n.out.base.shape)}" for i, n in enumerate(self.g.nodes)]
+        return [f"{i:4d} {n.op:10s} {n.src:40s} out={tuple(n.out.base.shape) if n.out is not None else None}"
+                for i, n in enumerate(self.g.nodes)]
 
     def __del__(self):
         try:

@@ -76,6 +76,18 @@ class Interp:
         self.tangent_backward()
         return [p.at.clone() for p in self.g.params]
 
+    # ---- diagshift: folded c*sum((w-const)^2) terms (ir._fold_quadratic_regularisers) -----------------
+    def tf_diagshift(self, n):
+        pass
+
+    def bb_diagshift(self, n):
+        for p, x in zip(n.ins, n.attrs["xs"]):
+            p.a.add_(n.attrs["coef"] * self.base(x))       # gradient of (coef/2) * sum(x^2)
+
+    def tb_diagshift(self, n):
+        for p in n.ins:
+            p.at.add_(n.attrs["coef"] * p.t)                # curvature coef * I
+
     # ---- unary ------------------------------------------------------------------------------------
     def _d12(self, n: Node, x: torch.Tensor):
         k = n.attrs["kind"]

@@ -27,7 +27,7 @@ def main():
         for i, t in enumerate(ms):
             n = plan.g.nodes[i]
             b = plan.node_bytes(i, pas)
-            rows.append((float(t), pn, i, n.op, tuple(n.out.base.shape), b, n.src))
+            rows.append((float(t), pn, i, n.op, tuple(n.out.base.shape) if n.out is not None else ('params',), b, n.src))
     tot = sum(r[0] for r in rows)
     totb = sum(r[5] for r in rows)
     out = [f"# plan profile: {name} ({desc})", "",
