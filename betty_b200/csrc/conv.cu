@@ -11,6 +11,7 @@
 
 #include "../../include/betty_b200.h"
 #include "conv_small.h"
+#include "gemm_tc.h"
 #include "plan.h"
 #include "tile_gemm.cuh"
 
@@ -145,6 +146,25 @@ __global__ void __launch_bounds__(256) chansum_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) atomicAdd(out + ch, acc);
 }
 
+// ---- tensor-core (tcgen05) implicit-GEMM operands, bf16-autocast graphs with >= 32 channels ----------
+TcSrc pixrow(const void* p, int dt, int CH, int H, int W, const Geom& g, int GH, int GW, int flip) {
+  TcSrc s{};
+  s.p = p; s.dt = dt; s.mode = TC_PIXROW;
+  s.CH = CH; s.H = H; s.W = W; s.KH = g.KH; s.KW = g.KW; s.GH = GH; s.GW = GW; s.py = g.ph; s.px = g.pw; s.flip = flip;
+  return s;
+}
+TcSrc pixk(const void* p, int dt, int CH, int H, int W, int KH, int KW, int GH, int GW, int py, int px) {
+  TcSrc s{};
+  s.p = p; s.dt = dt; s.mode = TC_PIXK;
+  s.CH = CH; s.H = H; s.W = W; s.KH = KH; s.KW = KW; s.GH = GH; s.GW = GW; s.py = py; s.px = px; s.flip = 0;
+  return s;
+}
+TcSrc wdgrad(const void* p, int dt, const Geom& g) {
+  TcSrc s{};
+  s.p = p; s.dt = dt; s.mode = TC_WDGRAD; s.KH = g.KH; s.KW = g.KW; s.C2 = g.C;
+  return s;
+}
+
 }  // namespace
 
 int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
@@ -158,6 +178,20 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   const int64_t P = (int64_t)g.N * g.HO * g.WO, PIN = (int64_t)g.N * g.H * g.W;
   int rc;
   const bool unit = g.sh == 1 && g.sw == 1 && g.dh == 1 && g.dw == 1 && !getenv("BB200_CONV_IGEMM");
+  const bool tc = (nd.kind & 1) && unit && !getenv("BB200_NO_TC") && g.O >= 32;
+  if (pass == BB_PASS_TAN_FWD && tc) {
+    // D[pixel][o] = sum_(c,i,j) im2col(t_x)[pixel][cij] * W[o][cij] + im2col(x)[pixel][cij] * t_W[o][cij]
+    TcGemmArgs G{};
+    G.M = P; G.N = g.O; G.K = CKK;
+    int np = 0;
+    if (actX) { G.a[np] = pixrow(nd.t[0], BB_F32, g.C, g.H, g.W, g, g.HO, g.WO, 0); G.b[np] = tc_strided(nd.base[1], nd.dt[1], CKK, 1); ++np; }
+    if (actW) { G.a[np] = pixrow(nd.base[0], nd.dt[0], g.C, g.H, g.W, g, g.HO, g.WO, 0); G.b[np] = tc_strided(nd.t[1], BB_F32, CKK, 1); ++np; }
+    G.npairs = np;
+    G.out = reinterpret_cast<float*>(nd.t[3]); G.omode = 1; G.OCH = g.O; G.OHW = g.HO * g.WO; G.beta = 0;
+    G.bias = actB ? reinterpret_cast<const float*>(nd.t[2]) : nullptr; G.bias_stride = 1;
+    G.allow_split = 0;
+    return bb_gemm_tc_run(G, s);
+  }
   if (pass == BB_PASS_TAN_FWD && unit && bb_conv_small_corr_ok(g.C, g.O, g.KH, g.KW, (actX ? 1 : 0) + (actW ? 1 : 0))) {
     SmallConvArgs A{};
     int np = 0;
@@ -186,7 +220,19 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   const bool base = pass == BB_PASS_BASE_BWD;
   const void* gy = base ? nd.a[3] : nd.at[3];
   const int need = base ? nd.pad0 : nd.active;
-  if ((need & 1) && unit && bb_conv_small_corr_ok(g.O, g.C, g.KH, g.KW, (!base && actW) ? 2 : 1)) {
+  if ((need & 1) && tc && g.C >= 32) {
+    // D[in-pixel][c] = sum_(o,i,j) g[img,o,y+ph-i,x+pw-j] * W[o][c][i][j]  (+ a_y with t_W)
+    TcGemmArgs G{};
+    G.M = PIN; G.N = g.C; G.K = OKK;
+    int np = 0;
+    G.a[np] = pixrow(gy, BB_F32, g.O, g.HO, g.WO, g, g.H, g.W, 1); G.b[np] = wdgrad(nd.base[1], nd.dt[1], g); ++np;
+    if (!base && actW) { G.a[np] = pixrow(nd.a[3], BB_F32, g.O, g.HO, g.WO, g, g.H, g.W, 1); G.b[np] = wdgrad(nd.t[1], BB_F32, g); ++np; }
+    G.npairs = np;
+    G.out = reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]); G.omode = 1; G.OCH = g.C; G.OHW = g.H * g.W;
+    G.beta = nd.beta[0]; G.bias = nullptr; G.allow_split = 0;
+    rc = bb_gemm_tc_run(G, s);
+    if (rc) return rc;
+  } else if ((need & 1) && unit && bb_conv_small_corr_ok(g.O, g.C, g.KH, g.KW, (!base && actW) ? 2 : 1)) {
     SmallConvArgs A{};
     int np = 0;
     A.in[np] = gy; A.dt_in[np] = BB_F32; A.w[np] = nd.base[1]; A.dt_w[np] = nd.dt[1]; ++np;
@@ -211,7 +257,23 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
     rc = launch(la, lb, sc, g.C, PIN, OKK, np, 1, s);
     if (rc) return rc;
   }
-  if ((need & 2) && unit && bb_conv_small_wgrad_ok(g.O, g.C, g.H, g.W, g.HO, g.WO, g.KH, g.KW)) {
+  if ((need & 2) && tc && nd.beta[1]) {
+    // D[(c,i,j)][o] = sum_pixels im2col(x)[cij][pixel] * at_y[o][pixel]  (+ t_x with a_y); split-K, atomics
+    TcGemmArgs G{};
+    G.M = CKK; G.N = g.O; G.K = P;
+    int np = 0;
+    G.a[np] = pixk(nd.base[0], nd.dt[0], g.C, g.H, g.W, g.KH, g.KW, g.HO, g.WO, g.ph, g.pw);
+    G.b[np] = pixk(gy, BB_F32, g.O, g.HO, g.WO, 1, 1, g.HO, g.WO, 0, 0); ++np;
+    if (!base && actX) {
+      G.a[np] = pixk(nd.t[0], BB_F32, g.C, g.H, g.W, g.KH, g.KW, g.HO, g.WO, g.ph, g.pw);
+      G.b[np] = pixk(nd.a[3], BB_F32, g.O, g.HO, g.WO, 1, 1, g.HO, g.WO, 0, 0); ++np;
+    }
+    G.npairs = np;
+    G.out = reinterpret_cast<float*>(base ? nd.a[1] : nd.at[1]); G.omode = 0; G.ors = 1; G.ocs = CKK;
+    G.beta = 1; G.bias = nullptr; G.allow_split = 1; G.out_dense = 1;
+    rc = bb_gemm_tc_run(G, s);
+    if (rc) return rc;
+  } else if ((need & 2) && unit && bb_conv_small_wgrad_ok(g.O, g.C, g.H, g.W, g.HO, g.WO, g.KH, g.KW)) {
     SmallConvArgs A{};
     int np = 0;
     A.g[np] = gy; A.dt_g[np] = BB_F32; A.in[np] = nd.base[0]; A.dt_in[np] = nd.dt[0]; ++np;

@@ -46,10 +46,10 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
     TcGemmArgs G{};
     G.M = M; G.N = N; G.K = K; G.npairs = npairs;
     for (int p = 0; p < npairs; ++p) {
-      G.a[p] = L[p].p; G.dta[p] = L[p].dt; G.ars[p] = L[p].rs; G.acs[p] = L[p].cs; G.a_kfast[p] = L[p].cs == 1;
-      G.b[p] = R[p].p; G.dtb[p] = R[p].dt; G.brs[p] = R[p].rs; G.bcs[p] = R[p].cs; G.b_kfast[p] = R[p].rs == 1;
+      G.a[p] = tc_strided(L[p].p, L[p].dt, L[p].rs, L[p].cs);
+      G.b[p] = tc_strided(R[p].p, R[p].dt, R[p].cs, R[p].rs);   // rows of the B tile = n
     }
-    G.out = out; G.ors = ors; G.ocs = ocs; G.beta = beta; G.bias = bias; G.bias_stride = bias_stride;
+    G.out = out; G.omode = 0; G.ors = ors; G.ocs = ocs; G.beta = beta; G.bias = bias; G.bias_stride = bias_stride;
     G.allow_split = 1;
     G.out_dense = dense_block(M, N, 1, ors, ocs, 0);
     return bb_gemm_tc_run(G, s);

@@ -25,13 +25,10 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BK = 64, STAGES = 3;   // BN = 64 or 128 (template)
 constexpr int NPROD = 128;                   // producer / epilogue threads
 constexpr int NTHREADS = NPROD + 32;
 constexpr int TILE_BYTES = BM * BK * 2;      // 16 KB per operand per stage
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;
-constexpr int TMEM_COLS = 128;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -86,29 +83,110 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format BF16 (1) @7/@10,
-// a/b major K (0), n_dim = N>>3 @17, m_dim = M>>4 @24
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// a/b major K (0), n_dim = N>>3 @17, m_dim = M>>4 @24 -- see Cfg<BN>::kIdesc
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// Stage one (128 rows x 64 k) operand tile.  Element (row, k) of the tile = src[(row0+row)*rs + (k0+k)*cs].
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int dt, int64_t rs, int64_t cs, int64_t row0,
-                                           int64_t nrows, int64_t k0, int64_t kend, int k_fast, int tid) {
-  if (k_fast) {
-    // 8 threads per row, one 16-byte (8 x bf16) chunk each: coalesced along k
-    const int chunk = tid & 7;
+// ------------------------------------------------------------------------------------------------
+// Operand staging.  One tile = ROWS rows x 64 k of bf16 in the K-major SWIZZLE_128B layout:
+// byte offset(row, k) = row*128 + (((k>>3) ^ (row&7)) << 4) + (k&7)*2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_chunk(uint8_t* tile, int row, int chunk, const float* v) {
+  uint4 q;
+  q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+}
+
+// raw load of one element as float (dt is warp-uniform)
+__device__ __forceinline__ float ld_elem(const void* p, int64_t off, int dt) {
+  return dt == BB_F32 ? reinterpret_cast<const float*>(p)[off]
+                      : __uint_as_float(((uint32_t)reinterpret_cast<const unsigned short*>(p)[off]) << 16);
+}
+
+// --- thread = row: STRIDED (row-contiguous), PIXROW, WDGRAD.  32 loads are issued before any is used. ---
+template <int ROWS>
+__device__ __forceinline__ void stage_by_row(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
+                                             int64_t kend, int tid) {
+  const int row = tid;
+  if (row >= ROWS) return;
+  const int64_t gr = row0 + row;
+  const bool row_ok = gr < nrows;
+  int64_t base = 0;
+  int y = 0, x = 0;
+  const int KK = S.KH * S.KW;
+  if (S.mode == TC_STRIDED) {
+    base = gr * S.rs;
+  } else if (S.mode == TC_PIXROW) {
+    const int64_t g = row_ok ? gr : 0;
+    const int hw = S.GH * S.GW;
+    const int img = (int)(g / hw), q = (int)(g - (int64_t)img * hw);
+    y = q / S.GW;
+    x = q - y * S.GW;
+    base = (int64_t)img * S.CH * S.H * S.W;
+  } else {  // TC_WDGRAD
+    base = (row_ok ? gr : 0) * KK;
+  }
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float v[32];
+    const int64_t kb = k0 + half * 32;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int64_t k = kb + e;
+      bool ok = row_ok && k < kend;
+      int64_t off = 0;
+      if (S.mode == TC_STRIDED) {
+        off = base + k * S.cs;
+      } else {
+        const int kk = (int)k;
+        const int ch = kk / KK, r = kk - ch * KK, i = r / S.KW, j = r - i * S.KW;
+        if (S.mode == TC_PIXROW) {
+          const int sy = S.flip ? y + S.py - i : y - S.py + i;
+          const int sx = S.flip ? x + S.px - j : x - S.px + j;
+          ok = ok && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
+          off = base + ((int64_t)ch * S.H + sy) * S.W + sx;
+        } else {
+          off = (int64_t)ch * S.C2 * KK + base + r;
+        }
+      }
+      v[e] = ok ? ld_elem(S.p, off, S.dt) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) store_chunk(tile, row, half * 4 + c, v + 8 * c);
+  }
+}
+
+// --- 8 threads per row, one 8-element chunk each: STRIDED (k-contiguous) and PIXK ---
+template <int ROWS>
+__device__ __forceinline__ void stage_by_chunk(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
+                                               int64_t kend, int tid) {
+  const int chunk = tid & 7;
+  const int64_t gk = k0 + chunk * 8;
+  // pixel decomposition of this thread's first k (PIXK): shared by all its rows
+  int img = 0, y = 0, x = 0;
+  const int KK = S.KH * S.KW;
+  if (S.mode == TC_PIXK) {
+    const int hw = S.GH * S.GW;
+    const int64_t g = gk < kend ? gk : 0;
+    img = (int)(g / hw);
+    const int q = (int)(g - (int64_t)img * hw);
+    y = q / S.GW;
+    x = q - y * S.GW;
+  }
+  constexpr int RPP = NPROD / 8;  // rows per pass
 #pragma unroll 2
-    for (int it = 0; it < BM / (NPROD / 8); ++it) {
-      const int row = (tid >> 3) + it * (NPROD / 8);
-      const int64_t gr = row0 + row, gk = k0 + chunk * 8;
-      float v[8];
-      if (gr < nrows && gk + 8 <= kend && cs == 1) {
-        const int64_t off = gr * rs + gk;
-        if (dt == BB_F32) {
-          const float* p = reinterpret_cast<const float*>(src) + off;
+  for (int it = 0; it < ROWS / RPP; ++it) {
+    const int row = (tid >> 3) + it * RPP;
+    const int64_t gr = row0 + row;
+    float v[8];
+    if (S.mode == TC_STRIDED) {
+      if (gr < nrows && gk + 8 <= kend) {
+        const int64_t off = gr * S.rs + gk;
+        if (S.dt == BB_F32) {
+          const float* p = reinterpret_cast<const float*>(S.p) + off;
           if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
             const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -117,71 +195,69 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int d
             for (int e = 0; e < 8; ++e) v[e] = p[e];
           }
         } else {
-          const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(src) + off;
+          const unsigned short* p = reinterpret_cast<const unsigned short*>(S.p) + off;
           if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(p);   // already bf16: copy the 16-byte chunk through
-            *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = raw;
+            // already bf16: pass the 16-byte chunk through untouched
+            *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(p);
             continue;
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __bfloat162float(p[e]);
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(((uint32_t)p[e]) << 16);
         }
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int64_t kk = gk + e;
-          v[e] = (gr < nrows && kk < kend) ? bb::ldf(src, gr * rs + kk * cs, dt) : 0.f;
+        for (int e = 0; e < 8; ++e) v[e] = (gr < nrows && gk + e < kend) ? ld_elem(S.p, gr * S.rs + gk + e, S.dt) : 0.f;
+      }
+    } else {  // TC_PIXK: row = (ch,i,j), k = pixel
+      const int rr = (int)(gr < nrows ? gr : 0);
+      const int ch = rr / KK, r = rr - ch * KK, i = r / S.KW, j = r - i * S.KW;
+      int ci = img, cy = y, cx = x;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int sy = S.flip ? cy + S.py - i : cy - S.py + i;
+        const int sx = S.flip ? cx + S.px - j : cx - S.px + j;
+        const bool ok = gr < nrows && gk + e < kend && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
+        v[e] = ok ? ld_elem(S.p, (((int64_t)ci * S.CH + ch) * S.H + sy) * S.W + sx, S.dt) : 0.f;
+        if (++cx == S.GW) {
+          cx = 0;
+          if (++cy == S.GH) { cy = 0; ++ci; }
         }
       }
-      uint4 q;
-      q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
-      *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
     }
-  } else {
-    // one row per thread (consecutive rows are adjacent in memory): every load instruction is coalesced
-    // across the warp.  Loads are issued in batches of 32 before any use so that 32 requests per thread
-    // are in flight (a per-element load->convert->store chain is latency-serialised).
-    const int row = tid;
-    const int64_t gr = row0 + row;
-    const bool row_ok = gr < nrows;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      float v[32];
-      const int64_t kb = k0 + half * 32;
-      if (dt == BB_F32) {
-        const float* p = reinterpret_cast<const float*>(src) + gr * rs + kb * cs;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = (row_ok && kb + e < kend) ? p[(int64_t)e * cs] : 0.f;
-      } else {
-        const unsigned short* p = reinterpret_cast<const unsigned short*>(src) + gr * rs + kb * cs;
-        unsigned short raw[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) raw[e] = (row_ok && kb + e < kend) ? p[(int64_t)e * cs] : (unsigned short)0;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(((uint32_t)raw[e]) << 16);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int chunk = half * 4 + c;
-        uint4 q;
-        q.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]); q.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
-        q.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]); q.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
-        *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
-      }
-    }
+    store_chunk(tile, row, chunk, v);
   }
 }
 
+template <int ROWS>
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
+                                           int64_t kend, int tid) {
+  const bool by_chunk = (S.mode == TC_STRIDED && S.cs == 1) || S.mode == TC_PIXK;
+  if (by_chunk) stage_by_chunk<ROWS>(tile, S, row0, nrows, k0, kend, tid);
+  else stage_by_row<ROWS>(tile, S, row0, nrows, k0, kend, tid);
+}
+
+template <int BN_>
+struct Cfg {
+  static constexpr int kBN = BN_;
+  static constexpr int kBTile = BN_ * BK * 2;
+  static constexpr int kStage = TILE_BYTES + kBTile;
+  static constexpr size_t kSmem = (size_t)STAGES * kStage + 1024 + 128;
+  static constexpr uint32_t kIdesc =
+      (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int BN_>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
+  using C = Cfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on a 1024-byte boundary of the *shared* address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[3], empty[3], accum, tmem slot
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStage);  // full[3], empty[3], accum, tmem slot
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum = smem_u32(bars + 2 * STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN_;
   const int split = blockIdx.z;
   // k range of this split, in whole k-blocks
   const int64_t kblocks_total = (G.K + BK - 1) / BK;
@@ -202,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS));
+                 "r"((uint32_t)BN_));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -217,11 +293,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
       if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
       const int pair = it / nkb;
       const int64_t k0 = (kb_beg + (it % nkb)) * BK;
-      int64_t kend = (kb_end * BK < G.K) ? kb_end * BK : G.K;
-      uint8_t* st = smem + s * STAGE_BYTES;
-      // A tile: rows = m, element(m,k) = A[m*ars + k*acs]; B tile: rows = n, element(n,k) = B[k*brs + n*bcs]
-      stage_tile(st, G.a[pair], G.dta[pair], G.ars[pair], G.acs[pair], m0, G.M, k0, kend, G.a_kfast[pair], tid);
-      stage_tile(st + TILE_BYTES, G.b[pair], G.dtb[pair], G.bcs[pair], G.brs[pair], n0, G.N, k0, kend, G.b_kfast[pair], tid);
+      const int64_t kend = (kb_end * BK < G.K) ? kb_end * BK : G.K;
+      uint8_t* st = smem + s * C::kStage;
+      stage_tile<BM>(st, G.a[pair], m0, G.M, k0, kend, tid);
+      stage_tile<BN_>(st + TILE_BYTES, G.b[pair], n0, G.N, k0, kend, tid);
       fence_proxy_async();
       mbar_arrive(full0 + 8 * s);
     }
@@ -231,8 +306,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
       tc_fence_after();
     }
     const int64_t row = m0 + warp * 32 + lane;
+    int64_t row_base = 0;
+    if (G.omode == 1) {
+      const int64_t r = row < G.M ? row : 0;
+      const int64_t img = r / G.OHW, q = r - img * G.OHW;
+      row_base = img * G.OCH * G.OHW + q;
+    } else {
+      row_base = row * G.ors;
+    }
+    const int64_t col_stride = G.omode == 1 ? (int64_t)G.OHW : G.ocs;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < BN_ / 32; ++c) {
       uint32_t r[32];
       if (total_kb > 0) {
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
@@ -257,7 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
           if (col < G.N) {
             float v = __uint_as_float(r[j]);
             if (G.bias != nullptr && split == 0) v += G.bias[col * G.bias_stride];
-            float* dst = G.out + row * G.ors + col * G.ocs;
+            float* dst = G.out + row_base + col * col_stride;
             if (G.ksplit > 1) atomicAdd(dst, v);
             else *dst = G.beta ? *dst + v : v;
           }
@@ -272,10 +356,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
         const int s = it % STAGES;
         mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + TILE_BYTES;
+        const uint32_t a_addr = smem_u32(smem + s * C::kStage), b_addr = a_addr + TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          umma_bf16(tmem_base, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), C::kIdesc,
+                    (it > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);   // stage free once these MMAs have read it
       }
@@ -287,8 +372,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN_));
   }
+}
+
+template <int BN_>
+int launch_tc(const TcGemmArgs& G, int ksplit, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN_>::kSmem));
+    configured = true;
+  }
+  dim3 grid((unsigned)((G.N + BN_ - 1) / BN_), (unsigned)((G.M + BM - 1) / BM), (unsigned)ksplit);
+  gemm_tc_kernel<BN_><<<grid, NTHREADS, Cfg<BN_>::kSmem, s>>>(G);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
 }
 
 }  // namespace
@@ -298,35 +397,27 @@ bool bb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int64_t batch) {
 }
 
 int bb_gemm_tc_run(const TcGemmArgs& G0, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    configured = true;
-  }
   TcGemmArgs G = G0;
-  const int64_t tiles = ((G.M + BM - 1) / BM) * ((G.N + BN - 1) / BN);
+  const int bn = G.N <= 64 ? 64 : 128;
+  const int64_t tiles = ((G.M + BM - 1) / BM) * ((G.N + bn - 1) / bn);
   const int64_t kblocks = (G.K + BK - 1) / BK;
   int ksplit = 1;
-  if (G.allow_split && tiles < BB_SM_COUNT / 2 && kblocks >= 8) {
-    int64_t want = (BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 4;
+  if (G.allow_split && tiles < BB_SM_COUNT && kblocks >= 8) {
+    int64_t want = (2 * BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 4;
     ksplit = (int)(want < maxs ? want : maxs);
-    if (ksplit > 32) ksplit = 32;
+    if (ksplit > 64) ksplit = 64;
     if (ksplit < 1) ksplit = 1;
   }
-  G.ksplit = ksplit;
   if (ksplit > 1 && !G.beta) {
     if (!G.out_dense) {
-      G.ksplit = ksplit = 1;
+      ksplit = 1;
     } else {
       BB_CUDA_TRY(cudaMemsetAsync(G.out, 0, sizeof(float) * G.M * G.N, s));
       bb_launch_tally += 1;
     }
   }
-  dim3 grid((unsigned)((G.N + BN - 1) / BN), (unsigned)((G.M + BM - 1) / BM), (unsigned)ksplit);
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(G);
-  bb_launch_tally += 1;
-  BB_LAUNCH_CHECK();
-  return BB_OK;
+  G.ksplit = ksplit;
+  return bn == 64 ? launch_tc<64>(G, ksplit, s) : launch_tc<128>(G, ksplit, s);
 }
 
 extern "C" int bb_gemm_bf16_tc(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs,
@@ -334,9 +425,9 @@ extern "C" int bb_gemm_bf16_tc(int64_t M, int64_t N, int64_t K, const void* A, i
                                int beta, void* stream) {
   TcGemmArgs G{};
   G.M = M; G.N = N; G.K = K; G.npairs = 1;
-  G.a[0] = A; G.dta[0] = dtA; G.ars[0] = ars; G.acs[0] = acs; G.a_kfast[0] = acs == 1;
-  G.b[0] = B; G.dtb[0] = dtB; G.brs[0] = brs; G.bcs[0] = bcs; G.b_kfast[0] = brs == 1;
-  G.out = C; G.ors = crs; G.ocs = ccs; G.beta = beta; G.bias = nullptr; G.bias_stride = 0;
+  G.a[0] = tc_strided(A, dtA, ars, acs);
+  G.b[0] = tc_strided(B, dtB, bcs, brs);   // B tile rows = n: elem(n,k) = B[k*brs + n*bcs]
+  G.out = C; G.omode = 0; G.ors = crs; G.ocs = ccs; G.beta = beta; G.bias = nullptr; G.bias_stride = 0;
   G.allow_split = 1;
   G.out_dense = (ccs == 1 && crs == N) || (crs == 1 && ccs == M);
   return bb_gemm_tc_run(G, (cudaStream_t)stream);

@@ -1,26 +1,44 @@
-// Argument block of the tcgen05 dual-product GEMM (gemm_tc.cu).
+// Argument block of the tcgen05 dual-product GEMM / implicit-GEMM convolution kernel (gemm_tc.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// How element (row, k) of an operand tile is found in global memory.
+enum { TC_STRIDED = 0, TC_PIXROW = 1, TC_PIXK = 2, TC_WDGRAD = 3 };
+
+struct TcSrc {
+  const void* p;
+  int dt;            // BB_F32 / BB_BF16 (converted to bf16 while staging)
+  int mode;
+  int64_t rs, cs;    // TC_STRIDED: elem = p[row*rs + k*cs]
+  // convolution gathers over a source tensor [NIMG, CH, H, W] and a KH x KW window:
+  //   TC_PIXROW  row = pixel (img,y,x) of a GH x GW grid, k = (ch,i,j)
+  //   TC_PIXK    row = (ch,i,j),                          k = pixel (img,y,x)
+  //     value = src[img, ch, flip ? y+py-i : y-py+i, flip ? x+px-j : x-px+j]  (0 outside the source)
+  //   TC_WDGRAD  row = c (< C2), k = (o,i,j): value = p[((o*C2 + c)*KH + i)*KW + j]
+  int CH, H, W, KH, KW, GH, GW, py, px, flip, C2;
+};
+
 struct TcGemmArgs {
   int64_t M, N, K;
   int npairs, ksplit;
-  const void* a[2];          // A_p[m][k] = a[p][m*ars + k*acs]
-  int dta[2];
-  int64_t ars[2], acs[2];
-  int a_kfast[2];
-  const void* b[2];          // B_p[k][n] = b[p][k*brs + n*bcs]
-  int dtb[2];
-  int64_t brs[2], bcs[2];
-  int b_kfast[2];
-  float* out;                // D[m][n] = out[m*ors + n*ocs]
+  TcSrc a[2];        // A_p: rows = m
+  TcSrc b[2];        // B_p: rows = n   (D[m][n] += sum_k A[m][k] * B[n][k])
+  float* out;
+  int omode;         // 0: out[m*ors + n*ocs]; 1 (plane): m = pixel (img,q), n = channel: out[(img*OCH + n)*OHW + q]
   int64_t ors, ocs;
+  int OCH, OHW;
   int beta;
-  const float* bias;
+  const float* bias; // indexed by n
   int64_t bias_stride;
   int allow_split, out_dense;
 };
+
+inline TcSrc tc_strided(const void* p, int dt, int64_t rs, int64_t cs) {
+  TcSrc s{};
+  s.p = p; s.dt = dt; s.mode = TC_STRIDED; s.rs = rs; s.cs = cs;
+  return s;
+}
 
 bool bb_gemm_tc_eligible(int64_t M, int64_t N, int64_t K, int64_t batch);
 int bb_gemm_tc_run(const TcGemmArgs& G, cudaStream_t s);

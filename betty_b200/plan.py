@@ -306,6 +306,7 @@ class HvpPlan:
         _, _, HO, WO = n.out.base.shape
         (sh, sw), (ph, pw), (dh, dw) = n.attrs["stride"], n.attrs["padding"], n.attrs["dilation"]
         r["dims"][0:15] = (Nn, Cc, H, Wd, O, KH, KW, HO, WO, sh, sw, ph, pw, dh, dw)
+        r["kind"] = int(X.dtype == torch.bfloat16 or W.dtype == torch.bfloat16)   # bf16 graph -> tensor cores allowed
         self._slot(r, 0, x, X)
         self._slot(r, 1, w, W)
         self._slot(r, 2, b, None)
