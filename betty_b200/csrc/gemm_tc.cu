@@ -100,140 +100,230 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile, int row, int chunk, c
   *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
 }
 
-// raw load of one element as float (dt is warp-uniform)
-__device__ __forceinline__ float ld_elem(const void* p, int64_t off, int dt) {
-  return dt == BB_F32 ? reinterpret_cast<const float*>(p)[off]
-                      : __uint_as_float(((uint32_t)reinterpret_cast<const unsigned short*>(p)[off]) << 16);
-}
+// The staging code is written so that the compiler emits straight-line batches of independent loads
+// (addresses first, then all loads, then convert/pack/store): a per-element "load -> use" chain is
+// latency-serialised and was 10-20x slower.  Mode and dtype are template parameters (one warp-uniform
+// switch per tile), out-of-range elements load from offset 0 and are masked afterwards.
+template <int DT>
+struct Raw;
+template <>
+struct Raw<BB_F32> {
+  using T = float;
+  static __device__ __forceinline__ float cvt(float v) { return v; }
+};
+template <>
+struct Raw<BB_BF16> {
+  using T = unsigned short;
+  static __device__ __forceinline__ float cvt(unsigned short v) { return __uint_as_float(((uint32_t)v) << 16); }
+};
 
-// --- thread = row: STRIDED (row-contiguous), PIXROW, WDGRAD.  32 loads are issued before any is used. ---
-template <int ROWS>
-__device__ __forceinline__ void stage_by_row(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
-                                             int64_t kend, int tid) {
+// --- thread = row: STRIDED (row-contiguous), PIXROW, WDGRAD; two batches of 32 loads per tile ---
+template <int MODE, int DT, int ROWS>
+__device__ __forceinline__ void stage_by_row_t(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
+                                               int64_t kend, int tid) {
+  using R = Raw<DT>;
   const int row = tid;
   if (row >= ROWS) return;
   const int64_t gr = row0 + row;
   const bool row_ok = gr < nrows;
-  int64_t base = 0;
-  int y = 0, x = 0;
+  const typename R::T* p = reinterpret_cast<const typename R::T*>(S.p);
   const int KK = S.KH * S.KW;
-  if (S.mode == TC_STRIDED) {
-    base = gr * S.rs;
-  } else if (S.mode == TC_PIXROW) {
+  int y = 0, x = 0;
+  if (MODE == TC_STRIDED) {
+    p += (row_ok ? gr : 0) * S.rs;
+  } else if (MODE == TC_PIXROW) {
     const int64_t g = row_ok ? gr : 0;
     const int hw = S.GH * S.GW;
     const int img = (int)(g / hw), q = (int)(g - (int64_t)img * hw);
     y = q / S.GW;
     x = q - y * S.GW;
-    base = (int64_t)img * S.CH * S.H * S.W;
+    p += (int64_t)img * S.CH * S.H * S.W;
   } else {  // TC_WDGRAD
-    base = (row_ok ? gr : 0) * KK;
+    p += (row_ok ? gr : 0) * KK;
   }
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
-    float v[32];
     const int64_t kb = k0 + half * 32;
+    int64_t off[32];
+    uint32_t mask = 0;
+    // k -> (ch, i, j), advanced incrementally
+    int ch = 0, i = 0, j = 0;
+    if (MODE != TC_STRIDED) {
+      const int kk = (int)kb;
+      ch = kk / KK;
+      const int r = kk - ch * KK;
+      i = r / S.KW;
+      j = r - i * S.KW;
+    }
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
-      const int64_t k = kb + e;
-      bool ok = row_ok && k < kend;
-      int64_t off = 0;
-      if (S.mode == TC_STRIDED) {
-        off = base + k * S.cs;
+      bool ok = row_ok && (kb + e < kend);
+      int64_t o;
+      if (MODE == TC_STRIDED) {
+        o = (kb + e) * S.cs;
+      } else if (MODE == TC_PIXROW) {
+        const int sy = S.flip ? y + S.py - i : y - S.py + i;
+        const int sx = S.flip ? x + S.px - j : x - S.px + j;
+        ok = ok && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
+        o = ((int64_t)ch * S.H + sy) * S.W + sx;
       } else {
-        const int kk = (int)k;
-        const int ch = kk / KK, r = kk - ch * KK, i = r / S.KW, j = r - i * S.KW;
-        if (S.mode == TC_PIXROW) {
-          const int sy = S.flip ? y + S.py - i : y - S.py + i;
-          const int sx = S.flip ? x + S.px - j : x - S.px + j;
-          ok = ok && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
-          off = base + ((int64_t)ch * S.H + sy) * S.W + sx;
-        } else {
-          off = (int64_t)ch * S.C2 * KK + base + r;
+        o = (int64_t)ch * S.C2 * KK + i * S.KW + j;
+      }
+      off[e] = ok ? o : 0;
+      mask |= (ok ? 1u : 0u) << e;
+      if (MODE != TC_STRIDED) {
+        if (++j == S.KW) {
+          j = 0;
+          if (++i == S.KH) { i = 0; ++ch; }
         }
       }
-      v[e] = ok ? ld_elem(S.p, off, S.dt) : 0.f;
     }
+    typename R::T raw[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) raw[e] = p[off[e]];
+    float v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = ((mask >> e) & 1u) ? R::cvt(raw[e]) : 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) store_chunk(tile, row, half * 4 + c, v + 8 * c);
   }
 }
 
-// --- 8 threads per row, one 8-element chunk each: STRIDED (k-contiguous) and PIXK ---
-template <int ROWS>
-__device__ __forceinline__ void stage_by_chunk(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
-                                               int64_t kend, int tid) {
+// --- 8 threads per row, one 8-element chunk each: STRIDED (k-contiguous) and PIXK; 4 rows per batch ---
+template <int MODE, int DT, int ROWS>
+__device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
+                                                 int64_t kend, int tid) {
+  using R = Raw<DT>;
+  const typename R::T* p = reinterpret_cast<const typename R::T*>(S.p);
   const int chunk = tid & 7;
   const int64_t gk = k0 + chunk * 8;
-  // pixel decomposition of this thread's first k (PIXK): shared by all its rows
-  int img = 0, y = 0, x = 0;
-  const int KK = S.KH * S.KW;
-  if (S.mode == TC_PIXK) {
-    const int hw = S.GH * S.GW;
-    const int64_t g = gk < kend ? gk : 0;
-    img = (int)(g / hw);
-    const int q = (int)(g - (int64_t)img * hw);
-    y = q / S.GW;
-    x = q - y * S.GW;
-  }
-  constexpr int RPP = NPROD / 8;  // rows per pass
-#pragma unroll 2
-  for (int it = 0; it < ROWS / RPP; ++it) {
-    const int row = (tid >> 3) + it * RPP;
-    const int64_t gr = row0 + row;
-    float v[8];
-    if (S.mode == TC_STRIDED) {
-      if (gr < nrows && gk + 8 <= kend) {
-        const int64_t off = gr * S.rs + gk;
-        if (S.dt == BB_F32) {
-          const float* p = reinterpret_cast<const float*>(S.p) + off;
-          if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-            const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  constexpr int RPP = NPROD / 8;  // rows per pass (16)
+  constexpr int PASSES = ROWS / RPP;
+  constexpr int BATCH = 4;        // passes whose loads are in flight together
+  if (MODE == TC_STRIDED) {
+    const bool full_k = gk + 8 <= kend;
+    const bool vec_ok = full_k && ((S.rs * (int64_t)sizeof(typename R::T)) % 16 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p + gk) & 15) == 0);
+#pragma unroll 1
+    for (int b0 = 0; b0 < PASSES; b0 += BATCH) {
+      if (vec_ok) {
+        uint4 raw[BATCH][DT == BB_F32 ? 2 : 1];
+        bool okr[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int row = (tid >> 3) + (b0 + b) * RPP;
+          const int64_t gr = row0 + row;
+          okr[b] = gr < nrows;
+          const uint4* q = reinterpret_cast<const uint4*>(p + (okr[b] ? gr : 0) * S.rs + gk);
+          raw[b][0] = q[0];
+          if (DT == BB_F32) raw[b][DT == BB_F32 ? 1 : 0] = q[1];
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int row = (tid >> 3) + (b0 + b) * RPP;
+          uint4 out;
+          if (DT == BB_F32) {
+            const float* f0 = reinterpret_cast<const float*>(&raw[b][0]);
+            const float* f1 = reinterpret_cast<const float*>(&raw[b][DT == BB_F32 ? 1 : 0]);
+            out.x = pack_bf16(f0[0], f0[1]); out.y = pack_bf16(f0[2], f0[3]);
+            out.z = pack_bf16(f1[0], f1[1]); out.w = pack_bf16(f1[2], f1[3]);
           } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = p[e];
+            out = raw[b][0];   // already bf16: pass the 16-byte chunk through
           }
-        } else {
-          const unsigned short* p = reinterpret_cast<const unsigned short*>(S.p) + off;
-          if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-            // already bf16: pass the 16-byte chunk through untouched
-            *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(p);
-            continue;
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(((uint32_t)p[e]) << 16);
+          if (!okr[b]) out = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = out;
         }
       } else {
+        typename R::T raw[BATCH][8];
+        uint32_t mask = 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (gr < nrows && gk + e < kend) ? ld_elem(S.p, gr * S.rs + gk + e, S.dt) : 0.f;
-      }
-    } else {  // TC_PIXK: row = (ch,i,j), k = pixel
-      const int rr = (int)(gr < nrows ? gr : 0);
-      const int ch = rr / KK, r = rr - ch * KK, i = r / S.KW, j = r - i * S.KW;
-      int ci = img, cy = y, cx = x;
+        for (int b = 0; b < BATCH; ++b) {
+          const int row = (tid >> 3) + (b0 + b) * RPP;
+          const int64_t gr = row0 + row;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int sy = S.flip ? cy + S.py - i : cy - S.py + i;
-        const int sx = S.flip ? cx + S.px - j : cx - S.px + j;
-        const bool ok = gr < nrows && gk + e < kend && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
-        v[e] = ok ? ld_elem(S.p, (((int64_t)ci * S.CH + ch) * S.H + sy) * S.W + sx, S.dt) : 0.f;
-        if (++cx == S.GW) {
-          cx = 0;
-          if (++cy == S.GH) { cy = 0; ++ci; }
+          for (int e = 0; e < 8; ++e) {
+            const bool ok = gr < nrows && gk + e < kend;
+            mask |= (ok ? 1u : 0u) << (b * 8 + e);
+            raw[b][e] = p[ok ? gr * S.rs + gk + e : 0];
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int row = (tid >> 3) + (b0 + b) * RPP;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = ((mask >> (b * 8 + e)) & 1u) ? R::cvt(raw[b][e]) : 0.f;
+          store_chunk(tile, row, chunk, v);
         }
       }
     }
-    store_chunk(tile, row, chunk, v);
+  } else {  // TC_PIXK: row = (ch,i,j), k = pixel
+    const int KK = S.KH * S.KW;
+    const int hw = S.GH * S.GW;
+    const int64_t g = gk < kend ? gk : 0;
+    const int img0 = (int)(g / hw);
+    const int q0 = (int)(g - (int64_t)img0 * hw);
+    const int y0 = q0 / S.GW, x0 = q0 - y0 * S.GW;
+#pragma unroll 1
+    for (int b0 = 0; b0 < PASSES; b0 += BATCH) {
+      typename R::T raw[BATCH][8];
+      uint32_t mask = 0;
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const int row = (tid >> 3) + (b0 + b) * RPP;
+        const int64_t gr = row0 + row;
+        const bool rok = gr < nrows;
+        const int rr = (int)(rok ? gr : 0);
+        const int ch = rr / KK, r = rr - ch * KK, i = r / S.KW, j = r - i * S.KW;
+        int ci = img0, cy = y0, cx = x0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int sy = cy - S.py + i, sx = cx - S.px + j;
+          const bool ok = rok && gk + e < kend && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
+          mask |= (ok ? 1u : 0u) << (b * 8 + e);
+          raw[b][e] = p[ok ? (((int64_t)ci * S.CH + ch) * S.H + sy) * S.W + sx : 0];
+          if (++cx == S.GW) {
+            cx = 0;
+            if (++cy == S.GH) { cy = 0; ++ci; }
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const int row = (tid >> 3) + (b0 + b) * RPP;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = ((mask >> (b * 8 + e)) & 1u) ? R::cvt(raw[b][e]) : 0.f;
+        store_chunk(tile, row, chunk, v);
+      }
+    }
+  }
+}
+
+template <int DT, int ROWS>
+__device__ __forceinline__ void stage_tile_dt(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
+                                              int64_t kend, int tid) {
+  switch (S.mode) {
+    case TC_STRIDED:
+      if (S.cs == 1) stage_by_chunk_t<TC_STRIDED, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      else stage_by_row_t<TC_STRIDED, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      break;
+    case TC_PIXROW:
+      stage_by_row_t<TC_PIXROW, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      break;
+    case TC_PIXK:
+      stage_by_chunk_t<TC_PIXK, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      break;
+    default:
+      stage_by_row_t<TC_WDGRAD, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
   }
 }
 
 template <int ROWS>
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
                                            int64_t kend, int tid) {
-  const bool by_chunk = (S.mode == TC_STRIDED && S.cs == 1) || S.mode == TC_PIXK;
-  if (by_chunk) stage_by_chunk<ROWS>(tile, S, row0, nrows, k0, kend, tid);
-  else stage_by_row<ROWS>(tile, S, row0, nrows, k0, kend, tid);
+  if (S.dt == BB_F32) stage_tile_dt<BB_F32, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+  else stage_tile_dt<BB_BF16, ROWS>(tile, S, row0, nrows, k0, kend, tid);
 }
 
 template <int BN_>
