@@ -14,8 +14,8 @@
 // the last k-block the producer warps turn into the epilogue: tcgen05.ld (32 lanes x 32 columns per warp)
 // -> registers -> strided global store with beta / atomic split-K / bias handling.
 //
-// Roles (160 threads): warps 0-3 producers + epilogue (warp w owns TMEM lanes 32w..32w+31), warp 4 MMA
-// issue + TMEM alloc/dealloc.  3-stage ring, 32 KB per stage.
+// Roles (288 threads): warps 0-7 producers + epilogue (warp w reads TMEM lanes 32*(w%4).. and the (w/4)-th
+// half of the columns), warp 8 MMA issue + TMEM alloc/dealloc.  3-stage ring, 24-32 KB per stage.
 #include <cuda_bf16.h>
 
 #include "../../include/betty_b200.h"
@@ -26,7 +26,7 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, STAGES = 3;   // BN = 64 or 128 (template)
-constexpr int NPROD = 128;                   // producer / epilogue threads
+constexpr int NPROD = 256;                   // producer / epilogue threads (8 warps)
 constexpr int NTHREADS = NPROD + 32;
 constexpr int TILE_BYTES = BM * BK * 2;      // 16 KB per operand per stage
 
@@ -117,79 +117,90 @@ struct Raw<BB_BF16> {
   static __device__ __forceinline__ float cvt(unsigned short v) { return __uint_as_float(((uint32_t)v) << 16); }
 };
 
-// --- thread = row: STRIDED (row-contiguous), PIXROW, WDGRAD; two batches of 32 loads per tile ---
+// --- SEG threads per row, each a contiguous run of BK/SEG k's: STRIDED (row-contiguous), PIXROW, WDGRAD.
+//     All index arithmetic is 32-bit and incremental (one division per thread per tile); loads go out in
+//     batches of 16. ---
 template <int MODE, int DT, int ROWS>
 __device__ __forceinline__ void stage_by_row_t(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
                                                int64_t kend, int tid) {
   using R = Raw<DT>;
-  const int row = tid;
-  if (row >= ROWS) return;
+  constexpr int SEG = NPROD / ROWS;   // 2 (128 rows) or 4 (64 rows)
+  constexpr int EPS = BK / SEG;       // elements per thread: 32 or 16
+  const int row = tid % ROWS, seg = tid / ROWS;
   const int64_t gr = row0 + row;
   const bool row_ok = gr < nrows;
   const typename R::T* p = reinterpret_cast<const typename R::T*>(S.p);
+  const int kb = (int)k0 + seg * EPS;
+  int nvalid = (int)(kend - kb);
+  nvalid = !row_ok ? 0 : (nvalid > EPS ? EPS : (nvalid < 0 ? 0 : nvalid));
   const int KK = S.KH * S.KW;
-  int y = 0, x = 0;
+  // running state
+  int ch = 0, i = 0, j = 0, sy = 0, sx = 0, rowoff = 0;
+  const int dir = S.flip ? -1 : 1;
+  int cs32 = 0;
   if (MODE == TC_STRIDED) {
-    p += (row_ok ? gr : 0) * S.rs;
-  } else if (MODE == TC_PIXROW) {
-    const int64_t g = row_ok ? gr : 0;
-    const int hw = S.GH * S.GW;
-    const int img = (int)(g / hw), q = (int)(g - (int64_t)img * hw);
-    y = q / S.GW;
-    x = q - y * S.GW;
-    p += (int64_t)img * S.CH * S.H * S.W;
-  } else {  // TC_WDGRAD
-    p += (row_ok ? gr : 0) * KK;
-  }
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    const int64_t kb = k0 + half * 32;
-    int64_t off[32];
-    uint32_t mask = 0;
-    // k -> (ch, i, j), advanced incrementally
-    int ch = 0, i = 0, j = 0;
-    if (MODE != TC_STRIDED) {
-      const int kk = (int)kb;
-      ch = kk / KK;
-      const int r = kk - ch * KK;
-      i = r / S.KW;
-      j = r - i * S.KW;
+    p += (row_ok ? gr : 0) * S.rs + (int64_t)kb * S.cs;
+    cs32 = (int)S.cs;
+  } else {
+    ch = kb / KK;
+    const int r = kb - ch * KK;
+    i = r / S.KW;
+    j = r - i * S.KW;
+    if (MODE == TC_PIXROW) {
+      const int64_t g = row_ok ? gr : 0;
+      const int hw = S.GH * S.GW;
+      const int img = (int)(g / hw), q = (int)(g - (int64_t)img * hw);
+      const int y = q / S.GW, x = q - y * S.GW;
+      p += (int64_t)img * S.CH * S.H * S.W;
+      sy = S.flip ? y + S.py - i : y - S.py + i;
+      sx = S.flip ? x + S.px - j : x - S.px + j;
+      rowoff = (ch * S.H + sy) * S.W;
+    } else {  // TC_WDGRAD: off = ch*C2*KK + i*KW + j relative to p + c*KK
+      p += (row_ok ? gr : 0) * KK;
+      rowoff = ch * S.C2 * KK + i * S.KW;
     }
+  }
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      bool ok = row_ok && (kb + e < kend);
-      int64_t o;
+  for (int b = 0; b < EPS / 16; ++b) {
+    int off[16];
+    uint32_t mask = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      bool ok = (b * 16 + e) < nvalid;
+      int o;
       if (MODE == TC_STRIDED) {
-        o = (kb + e) * S.cs;
+        o = (b * 16 + e) * cs32;
       } else if (MODE == TC_PIXROW) {
-        const int sy = S.flip ? y + S.py - i : y - S.py + i;
-        const int sx = S.flip ? x + S.px - j : x - S.px + j;
-        ok = ok && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
-        o = ((int64_t)ch * S.H + sy) * S.W + sx;
+        ok = ok && (unsigned)sy < (unsigned)S.H && (unsigned)sx < (unsigned)S.W;
+        o = rowoff + sx;
+        sx += dir;
+        if (++j == S.KW) {
+          j = 0; sx -= dir * S.KW; sy += dir; rowoff += dir * S.W;
+          if (++i == S.KH) { i = 0; sy -= dir * S.KH; rowoff += (S.H - dir * S.KH) * S.W; }
+        }
       } else {
-        o = (int64_t)ch * S.C2 * KK + i * S.KW + j;
+        o = rowoff + j;
+        if (++j == S.KW) {
+          j = 0; rowoff += S.KW;
+          if (++i == S.KH) { i = 0; rowoff += (S.C2 - 1) * KK; }
+        }
       }
       off[e] = ok ? o : 0;
       mask |= (ok ? 1u : 0u) << e;
-      if (MODE != TC_STRIDED) {
-        if (++j == S.KW) {
-          j = 0;
-          if (++i == S.KH) { i = 0; ++ch; }
-        }
-      }
     }
-    typename R::T raw[32];
+    typename R::T raw[16];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) raw[e] = p[off[e]];
-    float v[32];
+    for (int e = 0; e < 16; ++e) raw[e] = p[off[e]];
+    float v[16];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = ((mask >> e) & 1u) ? R::cvt(raw[e]) : 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) store_chunk(tile, row, half * 4 + c, v + 8 * c);
+    for (int e = 0; e < 16; ++e) v[e] = ((mask >> e) & 1u) ? R::cvt(raw[e]) : 0.f;
+    const int chunk0 = (seg * EPS + b * 16) >> 3;
+    store_chunk(tile, row, chunk0, v);
+    store_chunk(tile, row, chunk0 + 1, v + 8);
   }
 }
 
-// --- 8 threads per row, one 8-element chunk each: STRIDED (k-contiguous) and PIXK; 4 rows per batch ---
+// --- 8 threads per row, one 8-element chunk each: STRIDED (k-contiguous) and PIXK; up to 4 rows per batch ---
 template <int MODE, int DT, int ROWS>
 __device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
                                                  int64_t kend, int tid) {
@@ -197,9 +208,9 @@ __device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, 
   const typename R::T* p = reinterpret_cast<const typename R::T*>(S.p);
   const int chunk = tid & 7;
   const int64_t gk = k0 + chunk * 8;
-  constexpr int RPP = NPROD / 8;  // rows per pass (16)
-  constexpr int PASSES = ROWS / RPP;
-  constexpr int BATCH = 4;        // passes whose loads are in flight together
+  constexpr int RPP = NPROD / 8;      // rows per pass (32)
+  constexpr int PASSES = ROWS / RPP;  // 4 or 2
+  constexpr int BATCH = PASSES < 4 ? PASSES : 4;
   if (MODE == TC_STRIDED) {
     const bool full_k = gk + 8 <= kend;
     const bool vec_ok = full_k && ((S.rs * (int64_t)sizeof(typename R::T)) % 16 == 0) &&
@@ -257,13 +268,27 @@ __device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, 
         }
       }
     }
-  } else {  // TC_PIXK: row = (ch,i,j), k = pixel
+  } else {  // TC_PIXK: row = (ch,i,j), k = pixel.  offset = pixbase[e] + rowconst, both 32-bit
     const int KK = S.KH * S.KW;
     const int hw = S.GH * S.GW;
-    const int64_t g = gk < kend ? gk : 0;
-    const int img0 = (int)(g / hw);
-    const int q0 = (int)(g - (int64_t)img0 * hw);
-    const int y0 = q0 / S.GW, x0 = q0 - y0 * S.GW;
+    int pixbase[8], cy[8], cx[8];
+    {
+      const int64_t g = gk < kend ? gk : 0;
+      int ci = (int)(g / hw);
+      const int q0 = (int)(g - (int64_t)ci * hw);
+      int y = q0 / S.GW, x = q0 - y * S.GW;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool kok = gk + e < kend;
+        cy[e] = kok ? y : -0x40000000;     // pushes sy out of range -> element masked
+        cx[e] = x;
+        pixbase[e] = (ci * S.CH * S.H + y) * S.W + x;
+        if (++x == S.GW) {
+          x = 0;
+          if (++y == S.GH) { y = 0; ++ci; }
+        }
+      }
+    }
 #pragma unroll 1
     for (int b0 = 0; b0 < PASSES; b0 += BATCH) {
       typename R::T raw[BATCH][8];
@@ -275,17 +300,13 @@ __device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, 
         const bool rok = gr < nrows;
         const int rr = (int)(rok ? gr : 0);
         const int ch = rr / KK, r = rr - ch * KK, i = r / S.KW, j = r - i * S.KW;
-        int ci = img0, cy = y0, cx = x0;
+        const int dy = i - S.py, dx = j - S.px;
+        const int rowconst = (ch * S.H + dy) * S.W + dx;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int sy = cy - S.py + i, sx = cx - S.px + j;
-          const bool ok = rok && gk + e < kend && sy >= 0 && sy < S.H && sx >= 0 && sx < S.W;
+          const bool ok = rok && (unsigned)(cy[e] + dy) < (unsigned)S.H && (unsigned)(cx[e] + dx) < (unsigned)S.W;
           mask |= (ok ? 1u : 0u) << (b * 8 + e);
-          raw[b][e] = p[ok ? (((int64_t)ci * S.CH + ch) * S.H + sy) * S.W + sx : 0];
-          if (++cx == S.GW) {
-            cx = 0;
-            if (++cy == S.GH) { cy = 0; ++ci; }
-          }
+          raw[b][e] = p[ok ? pixbase[e] + rowconst : 0];
         }
       }
 #pragma unroll
@@ -337,7 +358,7 @@ struct Cfg {
 };
 
 template <int BN_>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
   using C = Cfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on a 1024-byte boundary of the *shared* address space
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == NPROD / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)BN_));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -376,7 +397,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < NPROD / 32) {
     // ---------------- producers ----------------
     for (int it = 0; it < total_kb; ++it) {
       const int s = it % STAGES;
@@ -395,7 +416,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
       mbar_wait(accum, 0);
       tc_fence_after();
     }
-    const int64_t row = m0 + warp * 32 + lane;
+    // warp w reads TMEM lanes 32*(w%4).. (hardware restriction) and the (w/4)-th half of the columns
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int64_t row = m0 + quarter * 32 + lane;
     int64_t row_base = 0;
     if (G.omode == 1) {
       const int64_t r = row < G.M ? row : 0;
@@ -406,10 +429,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
     }
     const int64_t col_stride = G.omode == 1 ? (int64_t)G.OHW : G.ocs;
 #pragma unroll 1
-    for (int c = 0; c < BN_ / 32; ++c) {
+    for (int c = chalf * (BN_ / 64); c < (chalf + 1) * (BN_ / 64); ++c) {
       uint32_t r[32];
       if (total_kb > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -460,7 +483,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NPROD / 32) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN_));
   }
