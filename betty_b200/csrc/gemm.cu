@@ -64,7 +64,10 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
   StridedStore sc{out, ors, ocs, obs, beta, bias, bias_stride};
 
   const bool small_m = M <= 16, small_n = N <= 16 && !small_m;
-  const int BM = small_m ? 16 : 64, BN = small_n ? 16 : 64;
+  // 64x64 tiles unless that leaves most SMs idle: then 32x32 tiles (4x the CTAs)
+  const int64_t tiles64 = ((M + 63) / 64) * ((N + 63) / 64) * batch;
+  const bool mid = !small_m && !small_n && tiles64 < 2 * BB_SM_COUNT;
+  const int BM = small_m ? 16 : (mid ? 32 : 64), BN = small_n ? 16 : (mid ? 32 : 64);
   const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
   int ksplit = 1;
   if (npairs > 0 && tiles < BB_SM_COUNT && K >= 1024 && dense_block(M, N, batch, ors, ocs, obs)) {
@@ -83,6 +86,8 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
     bb::tile_gemm_kernel<16, 64, 16, 1, 4, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
   else if (small_n)
     bb::tile_gemm_kernel<64, 16, 16, 4, 1, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
+  else if (mid)
+    bb::tile_gemm_kernel<32, 32, 16, 2, 2, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
   else
     bb::tile_gemm_kernel<64, 64, 16, 4, 4, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
   bb_launch_tally += 1;
