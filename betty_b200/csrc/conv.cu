@@ -178,7 +178,7 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   const int64_t P = (int64_t)g.N * g.HO * g.WO, PIN = (int64_t)g.N * g.H * g.W;
   int rc;
   const bool unit = g.sh == 1 && g.sw == 1 && g.dh == 1 && g.dw == 1 && !getenv("BB200_CONV_IGEMM");
-  const bool tc = (nd.kind & 1) && unit && !getenv("BB200_NO_TC") && g.O >= 32;
+  const bool tc = (nd.kind & 1) && unit && !getenv("BB200_NO_TC") && g.O >= 32 && CKK <= 2048 && OKK <= 2048;
   if (pass == BB_PASS_TAN_FWD && tc) {
     // D[pixel][o] = sum_(c,i,j) im2col(t_x)[pixel][cij] * W[o][cij] + im2col(x)[pixel][cij] * t_W[o][cij]
     TcGemmArgs G{};

@@ -17,6 +17,7 @@
 // Roles (288 threads): warps 0-7 producers + epilogue (warp w reads TMEM lanes 32*(w%4).. and the (w/4)-th
 // half of the columns), warp 8 MMA issue + TMEM alloc/dealloc.  3-stage ring, 24-32 KB per stage.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "../../include/betty_b200.h"
 #include "bb_common.cuh"
@@ -127,7 +128,7 @@ struct Raw<BB_BF16> {
 //     batches of 16. ---
 template <int MODE, int DT, int ROWS>
 __device__ __forceinline__ void stage_by_row_t(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
-                                               int64_t kend, int tid) {
+                                               int64_t kend, int tid, const int2* lut) {
   using R = Raw<DT>;
   constexpr int SEG = NPROD / ROWS;   // 2 (128 rows) or 4 (64 rows)
   constexpr int EPS = BK / SEG;       // elements per thread: 32 or 16
@@ -138,32 +139,20 @@ __device__ __forceinline__ void stage_by_row_t(uint8_t* tile, const TcSrc& S, in
   const int kb = (int)k0 + seg * EPS;
   int nvalid = (int)(kend - kb);
   nvalid = !row_ok ? 0 : (nvalid > EPS ? EPS : (nvalid < 0 ? 0 : nvalid));
-  const int KK = S.KH * S.KW;
-  // running state
-  int ch = 0, i = 0, j = 0, sy = 0, sx = 0, rowoff = 0;
-  const int dir = S.flip ? -1 : 1;
-  int cs32 = 0;
+  int y = 0, x = 0, pixoff = 0, cs32 = 0;
   if (MODE == TC_STRIDED) {
     p += (row_ok ? gr : 0) * S.rs + (int64_t)kb * S.cs;
     cs32 = (int)S.cs;
-  } else {
-    ch = kb / KK;
-    const int r = kb - ch * KK;
-    i = r / S.KW;
-    j = r - i * S.KW;
-    if (MODE == TC_PIXROW) {
-      const int64_t g = row_ok ? gr : 0;
-      const int hw = S.GH * S.GW;
-      const int img = (int)(g / hw), q = (int)(g - (int64_t)img * hw);
-      const int y = q / S.GW, x = q - y * S.GW;
-      p += (int64_t)img * S.CH * S.H * S.W;
-      sy = S.flip ? y + S.py - i : y - S.py + i;
-      sx = S.flip ? x + S.px - j : x - S.px + j;
-      rowoff = (ch * S.H + sy) * S.W;
-    } else {  // TC_WDGRAD: off = ch*C2*KK + i*KW + j relative to p + c*KK
-      p += (row_ok ? gr : 0) * KK;
-      rowoff = ch * S.C2 * KK + i * S.KW;
-    }
+  } else if (MODE == TC_PIXROW) {
+    const int64_t g = row_ok ? gr : 0;
+    const int hw = S.GH * S.GW;
+    const int img = (int)(g / hw), q = (int)(g - (int64_t)img * hw);
+    y = q / S.GW;
+    x = q - y * S.GW;
+    p += (int64_t)img * S.CH * S.H * S.W;
+    pixoff = y * S.W + x;
+  } else {  // TC_WDGRAD: offset(k) from the table, relative to p + c*KH*KW
+    p += (row_ok ? gr : 0) * (S.KH * S.KW);
   }
 #pragma unroll
   for (int b = 0; b < EPS / 16; ++b) {
@@ -175,19 +164,15 @@ __device__ __forceinline__ void stage_by_row_t(uint8_t* tile, const TcSrc& S, in
       int o;
       if (MODE == TC_STRIDED) {
         o = (b * 16 + e) * cs32;
-      } else if (MODE == TC_PIXROW) {
-        ok = ok && (unsigned)sy < (unsigned)S.H && (unsigned)sx < (unsigned)S.W;
-        o = rowoff + sx;
-        sx += dir;
-        if (++j == S.KW) {
-          j = 0; sx -= dir * S.KW; sy += dir; rowoff += dir * S.W;
-          if (++i == S.KH) { i = 0; sy -= dir * S.KH; rowoff += (S.H - dir * S.KH) * S.W; }
-        }
       } else {
-        o = rowoff + j;
-        if (++j == S.KW) {
-          j = 0; rowoff += S.KW;
-          if (++i == S.KH) { i = 0; rowoff += (S.C2 - 1) * KK; }
+        // table entry (same for every thread of the warp: a broadcast shared-memory read)
+        const int2 t = lut[ok ? kb + b * 16 + e : 0];
+        if (MODE == TC_PIXROW) {
+          const int sy = y + (t.y >> 16), sx = x + (int)(short)(t.y & 0xffff);
+          ok = ok && (unsigned)sy < (unsigned)S.H && (unsigned)sx < (unsigned)S.W;
+          o = pixoff + t.x;
+        } else {
+          o = t.x;
         }
       }
       off[e] = ok ? o : 0;
@@ -202,6 +187,26 @@ __device__ __forceinline__ void stage_by_row_t(uint8_t* tile, const TcSrc& S, in
     const int chunk0 = (seg * EPS + b * 16) >> 3;
     store_chunk(tile, row, chunk0, v);
     store_chunk(tile, row, chunk0 + 1, v + 8);
+  }
+}
+
+// k -> gather-offset table of a PIXROW / WDGRAD operand, built once per CTA.
+//   PIXROW: .x = ch*H*W + dy*W + dx, .y = (dy << 16) | (dx & 0xffff)   (dy, dx = window displacement)
+//   WDGRAD: .x = ch*C2*KH*KW + i*KW + j
+__device__ __forceinline__ void build_lut(int2* lut, const TcSrc& S, int K, int tid) {
+  const int KK = S.KH * S.KW;
+  for (int k = tid; k < K; k += NTHREADS) {
+    const int ch = k / KK, r = k - ch * KK, i = r / S.KW, j = r - i * S.KW;
+    int2 t;
+    if (S.mode == TC_PIXROW) {
+      const int dy = S.flip ? S.py - i : i - S.py, dx = S.flip ? S.px - j : j - S.px;
+      t.x = ch * S.H * S.W + dy * S.W + dx;
+      t.y = (dy << 16) | (dx & 0xffff);
+    } else {
+      t.x = ch * S.C2 * KK + r;
+      t.y = 0;
+    }
+    lut[k] = t;
   }
 }
 
@@ -328,29 +333,31 @@ __device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, 
 
 template <int DT, int ROWS>
 __device__ __forceinline__ void stage_tile_dt(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
-                                              int64_t kend, int tid) {
+                                              int64_t kend, int tid, const int2* lut) {
   switch (S.mode) {
     case TC_STRIDED:
       if (S.cs == 1) stage_by_chunk_t<TC_STRIDED, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
-      else stage_by_row_t<TC_STRIDED, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      else stage_by_row_t<TC_STRIDED, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
       break;
     case TC_PIXROW:
-      stage_by_row_t<TC_PIXROW, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      stage_by_row_t<TC_PIXROW, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
       break;
     case TC_PIXK:
       stage_by_chunk_t<TC_PIXK, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
       break;
     default:
-      stage_by_row_t<TC_WDGRAD, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      stage_by_row_t<TC_WDGRAD, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
   }
 }
 
 template <int ROWS>
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
-                                           int64_t kend, int tid) {
-  if (S.dt == BB_F32) stage_tile_dt<BB_F32, ROWS>(tile, S, row0, nrows, k0, kend, tid);
-  else stage_tile_dt<BB_BF16, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+                                           int64_t kend, int tid, const int2* lut) {
+  if (S.dt == BB_F32) stage_tile_dt<BB_F32, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
+  else stage_tile_dt<BB_BF16, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
 }
+
+constexpr int kMaxLutK = 2048;   // 2 tables x 8 B x 2048 = 32 KB
 
 template <int BN_>
 struct Cfg {
@@ -362,8 +369,8 @@ struct Cfg {
       (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
-template <int BN_>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
+template <int BN_, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const __grid_constant__ TcGemmArgs G) {
   using C = Cfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on a 1024-byte boundary of the *shared* address space
@@ -371,6 +378,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStage);  // full[3], empty[3], accum, tmem slot
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum = smem_u32(bars + 2 * STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  int2* lut_a = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(bars) + 128);
+  int2* lut_b = lut_a + G.lut_k;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN_;
@@ -384,6 +393,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   const int nkb = (int)(kb_end > kb_beg ? kb_end - kb_beg : 0);
   const int total_kb = nkb * G.npairs;
 
+  if (G.a[0].mode == TC_PIXROW || G.a[0].mode == TC_WDGRAD) build_lut(lut_a, G.a[0], G.lut_k, threadIdx.x);
+  if (G.b[0].mode == TC_PIXROW || G.b[0].mode == TC_WDGRAD) build_lut(lut_b, G.b[0], G.lut_k, threadIdx.x);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, NPROD);
@@ -411,8 +422,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int64_t k0 = (kb_beg + (it % nkb)) * BK;
       const int64_t kend = (kb_end * BK < G.K) ? kb_end * BK : G.K;
       uint8_t* st = smem + s * C::kStage;
-      stage_tile<BM>(st, G.a[pair], m0, G.M, k0, kend, tid);
-      stage_tile<BN_>(st + TILE_BYTES, G.b[pair], n0, G.N, k0, kend, tid);
+      stage_tile<BM>(st, G.a[pair], m0, G.M, k0, kend, tid, lut_a);
+      stage_tile<BN_>(st + TILE_BYTES, G.b[pair], n0, G.N, k0, kend, tid, lut_b);
       fence_proxy_async();
       mbar_arrive(full0 + 8 * s);
     }
@@ -494,15 +505,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   }
 }
 
-template <int BN_>
+template <int BN_, int MINB>
 int launch_tc(const TcGemmArgs& G, int ksplit, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN_>::kSmem));
+    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN_, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(Cfg<BN_>::kSmem + 2 * sizeof(int2) * kMaxLutK)));
     configured = true;
   }
   dim3 grid((unsigned)((G.N + BN_ - 1) / BN_), (unsigned)((G.M + BM - 1) / BM), (unsigned)ksplit);
-  gemm_tc_kernel<BN_><<<grid, NTHREADS, Cfg<BN_>::kSmem, s>>>(G);
+  gemm_tc_kernel<BN_, MINB><<<grid, NTHREADS, Cfg<BN_>::kSmem + 2 * sizeof(int2) * G.lut_k, s>>>(G);
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();
   return BB_OK;
@@ -535,7 +547,14 @@ int bb_gemm_tc_run(const TcGemmArgs& G0, cudaStream_t s) {
     }
   }
   G.ksplit = ksplit;
-  return bn == 64 ? launch_tc<64>(G, ksplit, s) : launch_tc<128>(G, ksplit, s);
+  const bool need_lut = G.a[0].mode == TC_PIXROW || G.a[0].mode == TC_WDGRAD || G.b[0].mode == TC_PIXROW ||
+                        G.b[0].mode == TC_WDGRAD;
+  G.lut_k = need_lut ? (int)G.K : 0;
+  if (G.lut_k > kMaxLutK) return BB_ERR_UNSUPPORTED;
+  // two register budgets are compiled: 1 CTA/SM (no spills) and 2 CTAs/SM (capped, small spills)
+  static const int occ = getenv("BB200_TC_OCC") ? atoi(getenv("BB200_TC_OCC")) : 1;
+  if (occ >= 2) return bn == 64 ? launch_tc<64, 2>(G, ksplit, s) : launch_tc<128, 2>(G, ksplit, s);
+  return bn == 64 ? launch_tc<64, 1>(G, ksplit, s) : launch_tc<128, 1>(G, ksplit, s);
 }
 
 extern "C" int bb_gemm_bf16_tc(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs,

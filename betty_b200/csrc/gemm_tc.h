@@ -32,6 +32,7 @@ struct TcGemmArgs {
   const float* bias; // indexed by n
   int64_t bias_stride;
   int allow_split, out_dense;
+  int lut_k;         // set by bb_gemm_tc_run: entries of the k -> gather-offset tables (0 if unused)
 };
 
 inline TcSrc tc_strided(const void* p, int dt, int64_t rs, int64_t cs) {
