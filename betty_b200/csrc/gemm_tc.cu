@@ -551,8 +551,11 @@ int bb_gemm_tc_run(const TcGemmArgs& G0, cudaStream_t s) {
                         G.b[0].mode == TC_WDGRAD;
   G.lut_k = need_lut ? (int)G.K : 0;
   if (G.lut_k > kMaxLutK) return BB_ERR_UNSUPPORTED;
-  // two register budgets are compiled: 1 CTA/SM (no spills) and 2 CTAs/SM (capped, small spills)
-  static const int occ = getenv("BB200_TC_OCC") ? atoi(getenv("BB200_TC_OCC")) : 1;
+  // Two register budgets are compiled: 1 CTA/SM (156 registers, no spills) and 2 CTAs/SM (capped at 96, a few
+  // spilled words).  Measured on B200: the convolution gathers are issue-latency bound and gain ~20 % from the
+  // second resident CTA (implicit_maml N=800: 16.7 -> 20.2 it/s); plain strided GEMMs are ~3 % faster with 1.
+  static const int forced = getenv("BB200_TC_OCC") ? atoi(getenv("BB200_TC_OCC")) : 0;
+  const int occ = forced ? forced : (need_lut || G.a[0].mode == TC_PIXK ? 2 : 1);
   if (occ >= 2) return bn == 64 ? launch_tc<64, 2>(G, ksplit, s) : launch_tc<128, 2>(G, ksplit, s);
   return bn == 64 ? launch_tc<64, 1>(G, ksplit, s) : launch_tc<128, 1>(G, ksplit, s);
 }
