@@ -33,6 +33,7 @@ WORKLOADS = {
     "implicit_maml_n25": ("implicit_maml", dict(method="neumann", n=25, image="miniimagenet", K=20, alpha=0.01, precision="bf16"), "4-conv mini-ImageNet N=25, Neumann K=20, bf16 autocast"),
     "bert_data_reweighting": ("bert_data_reweighting", dict(method="cg", batch=16, seq=50, K=10, precision="bf16"), "RoBERTa-base B=16xL=50, MWN-weighted CE + 5e-3|w|^2, CG K=10, bf16 autocast"),
     "logistic_regression_hpo": ("logistic_regression_hpo", dict(method="neumann", K=5), "20-dim logistic HPO, Neumann K=5, fp32"),
+    "neural_architecture_search": ("neural_architecture_search", dict(batch=64, c=16, cells=4), "DARTS-style supernet c16 x 4 cells B=64, finite-difference hypergradient (1 call = 1 iter-equivalent), fp32"),
 }
 DEFAULT = "learning_to_reweight"
 L2_BYTES = 126 * 1024 * 1024
@@ -121,6 +122,8 @@ def run_reference(args):
     wl, kw, desc = build_workload(args.workload, "cpu")
     method = wl.lower.config.type
     K = kw.get("K", 1)
+    if method == "darts":
+        return run_reference_fd(args, wl, desc)
     # bounded sample: cap K so that one step stays within a few seconds-to-tens-of-seconds of CPU work
     k_sample = min(K, args.ref_iters)
     if method == "neumann":
@@ -157,6 +160,31 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "HVP-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+    return 0
+
+
+def run_reference_fd(args, wl, desc):
+    from oracle import ref_port
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(min(cores, 32))
+    ref_port.darts(wl.vector, wl.lower, wl.upper, False)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        ref_port.darts(wl.vector, wl.lower, wl.upper, False)
+        n += 1
+        if time.perf_counter() - t0 > args.ref_budget_s:
+            break
+    dt = time.perf_counter() - t0
+    value = n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "HVP-iters/sec", "value": value, "unit": "HVP-iters/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": 1, "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "describe": desc, "K": 1},
+        "cpu_baseline": {"value": value, "unit": "HVP-iters/s", "cores": min(cores, 32), "kind": "port",
+                         "sample": f"{n} finite-difference call(s), torch CPU autograd"},
+        "e2e": {"value": value, "unit": "HVP-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
 
 
@@ -202,8 +230,9 @@ def main():
     E.settings.hvp = args.hvp
     E.settings.cuda_graph = not args.no_graph
     wl, kw, desc = build_workload(args.workload, dev, seed=rank)
+    kw = dict(kw)
     method = wl.lower.config.type
-    K = kw["K"]
+    K = kw.get("K", 1)
 
     def barrier():
         if dist is not None:
@@ -211,7 +240,20 @@ def main():
         torch.cuda.synchronize()
 
     # ---- prologue once (outside the timed region) -------------------------------------------
-    call = E.HypergradientCall(wl.lower, method)
+    if method == "darts":
+        # finite difference: no K-loop to isolate -- one step = one plugin call (two lower fwd/bwd passes on
+        # PyTorch + the K4 kernels), reported as calls/s ("1 call = 1 iter-equivalent")
+        class _FdCall:
+            hvp = None
+            layout = type("L", (), {"n_logical": sum(p.numel() for p in wl.lower.parameters())})()
+
+            def solve(self, vec):
+                return H.darts(vec, wl.lower, wl.upper, False)
+
+        call = _FdCall()
+        K = kw["K"] = 1
+    else:
+        call = E.HypergradientCall(wl.lower, method)
     flush = torch.zeros(L2_BYTES // 4 * 2, device=dev)  # 252 MB > L2, written between steps
 
     for _ in range(args.warmup):
@@ -279,7 +321,7 @@ def main():
     # ---- roofline of the dominant kernel -------------------------------------------------------
     hbm, tf, which = measured_peaks()
     roof = None
-    if hasattr(call.hvp, "roofline"):
+    if call.hvp is not None and hasattr(call.hvp, "roofline"):
         roof = call.hvp.roofline(hbm_gbs=hbm, which=which)
     if roof is None:
         # development mode: the only kernels of ours in the loop are the flat-arena updates
@@ -348,13 +390,25 @@ def cpu_baseline(args, kw):
 
     wl, kw, desc = build_workload(args.workload, "cpu")
     method = wl.lower.config.type
+    if method == "darts":
+        cores = min(os.cpu_count() or 1, 32)
+        torch.set_num_threads(cores)
+        ref_port.darts(wl.vector, wl.lower, wl.upper, False)
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 and time.perf_counter() - t0 < 12.0:
+            ref_port.darts(wl.vector, wl.lower, wl.upper, False)
+            n += 1
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "HVP-iters/s", "cores": cores, "kind": "port",
+                "sample": f"{n} finite-difference call(s) ({dt:.1f} s), fp32, torch CPU autograd"}
     in_grad = ref_port.lower_gradient(wl.lower)
     hvp = ref_port.make_hvp(in_grad, wl.lower.trainable_parameters())
     v = list(wl.vector)
     cores = best_thread_count(hvp, v)
     iters = 0
     t0 = time.perf_counter()
-    while iters < kw["K"] and (time.perf_counter() - t0 < 12.0 or iters < 1):
+    while iters < kw.get("K", 1) and (time.perf_counter() - t0 < 12.0 or iters < 1):
         if method == "neumann":
             ref_port.neumann_series(v, hvp, 1, wl.lower.config.neumann_alpha)
         else:

@@ -46,6 +46,8 @@ int dispatch(const bb_node& nd, int pass, cudaStream_t s) {
       return bb_launch_bce(nd, pass, s);
     case BB_OP_EMBEDDING:
       return bb_launch_embedding(nd, pass, s);
+    case BB_OP_AVGPOOL2D:
+      return bb_launch_avgpool2d(nd, pass, s);
     case BB_OP_DIAGSHIFT: {
       if (pass != BB_PASS_TAN_BWD) return BB_OK;
       bb_launch_tally += 1;

@@ -168,6 +168,54 @@ __global__ void pool_bwd_kernel(float* gx, const int64_t* __restrict__ idx, cons
   atomicAdd(gx + plane * hw_in + idx[i], gy[i]);  // gx is zeroed at the start of the pass
 }
 
+// ---- average pooling (linear; count_include_pad, floor mode) ------------------------------------------
+struct AvgGeom {
+  int H, W, HO, WO, kh, kw, sh, sw, ph, pw;
+  float inv;
+};
+
+__global__ void avgpool_fwd_kernel(const float* __restrict__ tx, float* ty, int64_t nout, AvgGeom g) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nout) return;
+  const int xo = (int)(i % g.WO), yo = (int)((i / g.WO) % g.HO);
+  const int64_t plane = i / ((int64_t)g.WO * g.HO);
+  const float* src = tx + plane * g.H * g.W;
+  float acc = 0.f;
+  for (int a = 0; a < g.kh; ++a) {
+    const int h = yo * g.sh - g.ph + a;
+    if (h < 0 || h >= g.H) continue;
+    for (int b = 0; b < g.kw; ++b) {
+      const int w = xo * g.sw - g.pw + b;
+      if (w >= 0 && w < g.W) acc += src[h * g.W + w];
+    }
+  }
+  ty[i] = acc * g.inv;
+}
+
+// gather form of the adjoint: every input pixel sums the windows that cover it (no atomics)
+__global__ void avgpool_bwd_kernel(float* gx, const float* __restrict__ gy, int64_t nin, AvgGeom g, int beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nin) return;
+  const int w = (int)(i % g.W), h = (int)((i / g.W) % g.H);
+  const int64_t plane = i / ((int64_t)g.W * g.H);
+  const float* src = gy + plane * g.HO * g.WO;
+  float acc = 0.f;
+  for (int a = 0; a < g.kh; ++a) {
+    const int hh = h + g.ph - a;
+    if (hh < 0 || hh % g.sh) continue;
+    const int yo = hh / g.sh;
+    if (yo >= g.HO) continue;
+    for (int b = 0; b < g.kw; ++b) {
+      const int ww = w + g.pw - b;
+      if (ww < 0 || ww % g.sw) continue;
+      const int xo = ww / g.sw;
+      if (xo < g.WO) acc += src[yo * g.WO + xo];
+    }
+  }
+  const float v = acc * g.inv;
+  gx[i] = beta ? gx[i] + v : v;
+}
+
 inline unsigned blocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -264,6 +312,32 @@ int bb_launch_maxpool2d(const bb_node& nd, int pass, cudaStream_t s) {
     pool_bwd_kernel<<<blocks(nout, 256), 256, 0, s>>>(reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]), idx,
                                                       reinterpret_cast<const float*>(base ? nd.a[3] : nd.at[3]), nout,
                                                       hw_in, hw_out);
+  }
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_launch_avgpool2d(const bb_node& nd, int pass, cudaStream_t s) {
+  if (pass == BB_PASS_BASE_BWD && !(nd.pad0 & 1)) return BB_OK;
+  AvgGeom g;
+  const int64_t planes = nd.dims[0];
+  g.H = (int)nd.dims[1]; g.W = (int)nd.dims[2]; g.HO = (int)nd.dims[3]; g.WO = (int)nd.dims[4];
+  g.kh = (int)nd.dims[5]; g.kw = (int)nd.dims[6]; g.sh = (int)nd.dims[7]; g.sw = (int)nd.dims[8];
+  g.ph = (int)nd.dims[9]; g.pw = (int)nd.dims[10];
+  g.inv = (float)nd.f[0];
+  if (pass == BB_PASS_TAN_FWD) {
+    const int64_t nout = planes * g.HO * g.WO;
+    if (nout <= 0) return BB_OK;
+    avgpool_fwd_kernel<<<blocks(nout, 256), 256, 0, s>>>(reinterpret_cast<const float*>(nd.t[0]),
+                                                         reinterpret_cast<float*>(nd.t[3]), nout, g);
+  } else {
+    const bool base = pass == BB_PASS_BASE_BWD;
+    const int64_t nin = planes * g.H * g.W;
+    if (nin <= 0) return BB_OK;
+    avgpool_bwd_kernel<<<blocks(nin, 256), 256, 0, s>>>(reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]),
+                                                        reinterpret_cast<const float*>(base ? nd.a[3] : nd.at[3]), nin, g,
+                                                        nd.beta[0]);
   }
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();

@@ -119,6 +119,17 @@ _BN_OPS = ("aten.native_batch_norm.default", "aten._native_batch_norm_legit.defa
            "aten.miopen_batch_norm.default")
 
 
+def _narrow_interior(t: torch.Tensor, pads, nd: int, shape) -> torch.Tensor:
+    """The un-padded interior of a constant_pad_nd output (pads are given last-dim first)."""
+    for k in range(len(pads) // 2):
+        dim = nd - 1 - k
+        lo = pads[2 * k]
+        if lo < 0 or pads[2 * k + 1] < 0:
+            raise UnsupportedGraph("negative padding (cropping)")
+        t = t.narrow(dim, lo, shape[dim])
+    return t
+
+
 def _is_dense(t: torch.Tensor) -> bool:
     """non-overlapping and dense: some permutation of the dims is contiguous"""
     if t.numel() <= 1:
@@ -196,6 +207,8 @@ class _Lowering:
         if name in ("aten.detach.default", "aten.detach_.default", "aten.lift_fresh.default"):
             return  # output is a constant
         opname = name.split(".")[1]
+        if name in ("aten.add_.Tensor", "aten.sub_.Tensor"):
+            return self._inplace_add(op)
         if opname.endswith("_") and not opname.startswith("_"):
             raise UnsupportedGraph(f"in-place op {name} on a parameter-dependent tensor")
         if name in _VIEW_OPS:
@@ -303,6 +316,40 @@ class _Lowering:
             padding_idx = a[2] if len(a) > 2 else -1
             self.emit("embedding", [w], op.out, name, indices=a[1], padding_idx=padding_idx)
             return
+        if name == "aten.constant_pad_nd.default":
+            x = A(a[0])
+            pads = list(a[1])
+            if len(a) > 2 and float(a[2]) != 0.0:
+                pass   # constant fill value does not matter: it has zero tangent
+            nd = a[0].dim()
+            out = self._new(op.out)                      # root: buffers stay zero outside the interior
+            interior = lambda t, pads=pads, nd=nd, shape=tuple(a[0].shape): _narrow_interior(t, pads, nd, shape)
+            inner = self.alias(out, interior(op.out), interior, full_cover=False)
+            n = Node("copy", [x], inner, {}, src=name)
+            self.nodes.append(n)
+            return
+        if name == "aten.avg_pool2d.default":
+            x = A(a[0])
+            kernel = list(a[1])
+            stride = list(a[2]) if len(a) > 2 and a[2] else kernel
+            padding = list(a[3]) if len(a) > 3 else [0, 0]
+            ceil_mode = bool(a[4]) if len(a) > 4 else False
+            count_include_pad = bool(a[5]) if len(a) > 5 else True
+            divisor = a[6] if len(a) > 6 else None
+            if len(kernel) == 1:
+                kernel = kernel * 2
+            if len(stride) == 1:
+                stride = stride * 2
+            if len(padding) == 1:
+                padding = padding * 2
+            if ceil_mode or (not count_include_pad and any(padding)):
+                raise UnsupportedGraph("avg_pool2d with ceil_mode / count_include_pad=False and padding")
+            self.need_contig(x, name)
+            if a[0].dim() != 4 or not op.out.is_contiguous():
+                raise UnsupportedGraph("avg_pool2d: only contiguous NCHW")
+            self.emit("avgpool2d", [x], op.out, name, kernel=tuple(kernel), stride=tuple(stride), padding=tuple(padding),
+                      divisor=float(divisor) if divisor else float(kernel[0] * kernel[1]))
+            return
         if name == "aten.native_dropout.default":
             x = A(a[0])
             out, mask = op.out
@@ -366,6 +413,35 @@ class _Lowering:
             self.alias(v, op.out, lambda t: t, ident=True)
         else:
             self.emit("unary", [v], op.out, name, kind="scale", scalar=s)
+
+    _READS_INPUT_BASE = {"unary": (0,), "mul2": (0, 1), "softmax": (0,), "logsoftmax": (0,), "bce_logits": (0,)}
+
+    def _inplace_add(self, op):
+        """``x += y`` (residual connections written in place, reference
+        examples/learning_to_reweight/model.py:49).  Lowered as a functional add whose result takes over the
+        tensor object; refused if an already-recorded rule still needs the overwritten values."""
+        name, a, kw = op.name, op.args, op.kwargs
+        alpha = float(kw.get("alpha", 1))
+        sb = -alpha if ".sub_" in name else alpha
+        x, y = self.act(a[0]), self.act(a[1])
+        if x is not None and x.parent is not None:
+            raise UnsupportedGraph("in-place add into a view of a parameter-dependent tensor")
+        if x is not None:
+            for n in self.nodes:
+                for k in self._READS_INPUT_BASE.get(n.op, ()):
+                    if n.ins[k] is not None and n.ins[k].root is x:
+                        raise UnsupportedGraph("in-place add overwrites an activation an earlier op still needs")
+        if y is not None and tuple(a[0].shape) != tuple(a[1].shape):
+            raise UnsupportedGraph("broadcasting in-place add")
+        if x is not None and y is not None:
+            self.emit("add2", [x, y], op.out, name, sa=1.0, sb=sb)       # re-binds id(tensor) to the new value
+        elif x is not None:
+            pass                                                            # x += const: same tangents
+        else:
+            if sb == 1.0 and a[0].stride() == a[1].stride():
+                self.alias(y, op.out, lambda t: t, ident=True)
+            else:
+                self.emit("unary", [y], op.out, name, kind="scale", scalar=sb)
 
     def _gemm(self, op):
         name, a, kw = op.name, op.args, op.kwargs

@@ -18,7 +18,7 @@ from .ir import Graph, Node, UnsupportedGraph, Val, _is_dense, lower_tape
 BB_MAX_DIMS = 6
 OPS = {"unary": 1, "copy": 2, "add2": 3, "mulc": 4, "mul2": 5, "sumall": 6, "gemm": 7, "conv2d": 8,
        "maxpool2d": 9, "batchnorm": 10, "layernorm": 11, "softmax": 12, "logsoftmax": 13, "nll": 14,
-       "bce_logits": 15, "embedding": 16, "diagshift": 17}
+       "bce_logits": 15, "embedding": 16, "diagshift": 17, "avgpool2d": 18}
 UNARY = {"relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4, "pow": 5, "scale": 6, "neg": 6}
 PASS_BB, PASS_TF, PASS_TB = 0, 1, 2
 
@@ -319,6 +319,16 @@ class HvpPlan:
         _, _, HO, WO = n.out.base.shape
         r["dims"][0:3] = (Nn * Cc, H * W, HO * WO)
         r["aux"][0] = self._const(idx, torch.int64).data_ptr()
+        self._slot(r, 0, x, x.base)
+        self._slot(r, 3, n.out, None)
+
+    def _n_avgpool2d(self, n: Node, r):
+        x = n.ins[0]
+        Nn, Cc, H, W = x.base.shape
+        _, _, HO, WO = n.out.base.shape
+        (kh, kw), (sh, sw), (ph, pw) = n.attrs["kernel"], n.attrs["stride"], n.attrs["padding"]
+        r["dims"][0:11] = (Nn * Cc, H, W, HO, WO, kh, kw, sh, sw, ph, pw)
+        r["f"][0] = 1.0 / n.attrs["divisor"]
         self._slot(r, 0, x, x.base)
         self._slot(r, 3, n.out, None)
 

@@ -107,6 +107,48 @@ class FourConv(nn.Module):
         return self.classifier(f.view(f.size(0), -1))
 
 
+class _ResBlock(nn.Module):
+    """CIFAR ResNet basic block with the parameter-free "option A" shortcut and an in-place residual add
+    (structure of reference ``examples/learning_to_reweight/model.py:20-52``)."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.pad = (cout - cin) // 2 if (stride != 1 or cin != cout) else None
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        sc = x if self.pad is None else F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, self.pad, self.pad), "constant", 0)
+        out += sc
+        return F.relu(out)
+
+
+class ResNetCifar(nn.Module):
+    """ResNet-(6n+2) for 32x32 inputs; n=5 is the reference's ResNet32 (``model.py:54-86``)."""
+
+    def __init__(self, n=1, width=16, classes=10):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, width, 3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        blocks, cin = [], width
+        for stage, cout in enumerate((width, 2 * width, 4 * width)):
+            for b in range(n):
+                blocks.append(_ResBlock(cin, cout, 2 if (stage > 0 and b == 0) else 1))
+                cin = cout
+        self.blocks = nn.Sequential(*blocks)
+        self.output = nn.Linear(cin, classes)
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.blocks(out)
+        out = F.avg_pool2d(out, out.size()[3])
+        return self.output(out.view(out.size(0), -1))
+
+
 class MLPNet(nn.Module):
     def __init__(self, din=32, hidden=64, dout=10, depth=2):
         super().__init__()
@@ -239,6 +281,18 @@ def lenet_reweight(device="cpu", method="cg", batch=100, K=20, alpha=1.0, l2=0.0
                  describe=dict(batch=batch, K=K, method=method, model="LeNet-5"))
 
 
+def resnet_reweight(device="cpu", method="cg", batch=16, n=1, width=16, K=5, alpha=1.0, l2=0.05, seed=0):
+    """The reference's own learning_to_reweight model family (ResNet32 = n=5) with the MWN-weighted CE loss."""
+    torch.manual_seed(seed)
+    x = torch.randn(batch, 3, 32, 32)
+    y = torch.randint(0, 10, (batch,))
+    lower = ResNetCifar(n, width, 10)
+    upper = MetaWeightNet(100)
+    cfg = ShimConfig(type=method, neumann_iterations=K, neumann_alpha=alpha, cg_iterations=K, cg_alpha=alpha)
+    return _pair("learning_to_reweight_resnet", lower, _reweighted_ce_step(l2), upper, cfg, (x, y), device,
+                 describe=dict(batch=batch, n=n, width=width, K=K, method=method))
+
+
 def fourconv_imaml(device="cpu", method="neumann", n=25, ways=5, image="omniglot", hidden=64, K=20,
                    alpha=0.01, reg=0.5, precision="fp32", seed=0):
     """Config 3: 4-conv backbone, CE + reg*sum||w-theta||^2 (reference examples/implicit_maml/main.py:87-129)."""
@@ -360,6 +414,7 @@ FACTORIES = {
     "logistic_regression_hpo": logistic_hpo,
     "mlp_reweight": mlp_reweight,
     "learning_to_reweight": lenet_reweight,
+    "learning_to_reweight_resnet": resnet_reweight,
     "implicit_maml": fourconv_imaml,
     "neural_architecture_search": darts_search,
     "bert_data_reweighting": roberta_reweight,

@@ -330,6 +330,29 @@ class Interp:
     def tb_maxpool2d(self, n):
         self._bw_pool(n, "at")
 
+    # ---- avgpool2d (linear) -------------------------------------------------------------------------------
+    def _avg(self, n, t):
+        at = n.attrs
+        return F.avg_pool2d(t, at["kernel"], at["stride"], at["padding"], False, True, None) * (
+            at["kernel"][0] * at["kernel"][1] / at["divisor"])
+
+    def _avg_bw(self, n, g):
+        at = n.attrs
+        x = n.ins[0]
+        ref = torch.zeros(x.shape, dtype=self.dtype, device=g.device)
+        out = torch.ops.aten.avg_pool2d_backward(g.contiguous(), ref, list(at["kernel"]), list(at["stride"]),
+                                                 list(at["padding"]), False, True, None)
+        return out * (at["kernel"][0] * at["kernel"][1] / at["divisor"])
+
+    def tf_avgpool2d(self, n):
+        self.buf(n.out, "t").copy_(self._avg(n, self.buf(n.ins[0], "t")))
+
+    def bb_avgpool2d(self, n):
+        self.put(self.buf(n.ins[0], "a"), self._avg_bw(n, self.buf(n.out, "a")), n.beta[0])
+
+    def tb_avgpool2d(self, n):
+        self.put(self.buf(n.ins[0], "at"), self._avg_bw(n, self.buf(n.out, "at")), n.beta[0])
+
     # ---- batchnorm (batch statistics) / layernorm: y = gamma * xhat + beta --------------------------------
     def _norm_dims(self, n, x):
         if n.op == "batchnorm":

@@ -21,6 +21,9 @@ CASES = {
     "lenet_b300": ("learning_to_reweight", dict(batch=300), 5e-5),
     "fourconv_wide": ("implicit_maml", dict(n=4, hidden=32), 5e-5),   # >16 channels: implicit-GEMM conv path
     "fourconv": ("implicit_maml", dict(n=10, hidden=16), 2e-5),
+    # the reference's own learning_to_reweight model family: strided convs, BN with running stats, in-place
+    # residual adds, strided-slice + zero-pad shortcuts, average pooling
+    "resnet": ("learning_to_reweight_resnet", dict(batch=6, n=1, width=8), 5e-5),
     "fourconv_mini": ("implicit_maml", dict(n=3, hidden=8, image="miniimagenet"), 2e-5),
     "roberta": ("bert_data_reweighting", dict(batch=3, seq=9, tiny=True), 2e-5),
     "fourconv_bf16": ("implicit_maml", dict(n=10, hidden=16, precision="bf16"), 3e-2),

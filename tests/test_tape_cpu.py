@@ -17,6 +17,7 @@ CASES = {
     "fourconv": ("implicit_maml", dict(n=6, hidden=8)),
     "fourconv_mini": ("implicit_maml", dict(n=2, hidden=4, image="miniimagenet")),
     "roberta": ("bert_data_reweighting", dict(batch=3, seq=7, tiny=True)),
+    "resnet": ("learning_to_reweight_resnet", dict(batch=4, n=1, width=4)),
 }
 
 
