@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define BB_OK 0
@@ -25,12 +26,14 @@
 // dtype tags for *base* tensors recorded from the forward pass (tangents/adjoints are always fp32)
 #define BB_F32 0
 #define BB_BF16 1
+#define BB_F16 2
 
 namespace bb {
 
 __device__ __forceinline__ float ldf(const void* p, int64_t i, int dt) {
-  return dt == BB_F32 ? reinterpret_cast<const float*>(p)[i]
-                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  if (dt == BB_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dt == BB_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return __half2float(reinterpret_cast<const __half*>(p)[i]);   // fp16 autocast (reference precision="fp16")
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -122,6 +122,11 @@ struct Raw<BB_BF16> {
   using T = unsigned short;
   static __device__ __forceinline__ float cvt(unsigned short v) { return __uint_as_float(((uint32_t)v) << 16); }
 };
+template <>
+struct Raw<BB_F16> {
+  using T = unsigned short;
+  static __device__ __forceinline__ float cvt(unsigned short v) { return __half2float(__ushort_as_half(v)); }
+};
 
 // --- SEG threads per row, each a contiguous run of BK/SEG k's: STRIDED (row-contiguous), PIXROW, WDGRAD.
 //     All index arithmetic is 32-bit and incremental (one division per thread per tile); loads go out in
@@ -248,8 +253,12 @@ __device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, 
             const float* f1 = reinterpret_cast<const float*>(&raw[b][DT == BB_F32 ? 1 : 0]);
             out.x = pack_bf16(f0[0], f0[1]); out.y = pack_bf16(f0[2], f0[3]);
             out.z = pack_bf16(f1[0], f1[1]); out.w = pack_bf16(f1[2], f1[3]);
-          } else {
+          } else if (DT == BB_BF16) {
             out = raw[b][0];   // already bf16: pass the 16-byte chunk through
+          } else {
+            const unsigned short* h = reinterpret_cast<const unsigned short*>(&raw[b][0]);
+            out.x = pack_bf16(R::cvt(h[0]), R::cvt(h[1])); out.y = pack_bf16(R::cvt(h[2]), R::cvt(h[3]));
+            out.z = pack_bf16(R::cvt(h[4]), R::cvt(h[5])); out.w = pack_bf16(R::cvt(h[6]), R::cvt(h[7]));
           }
           if (!okr[b]) out = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = out;
@@ -354,7 +363,8 @@ template <int ROWS>
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
                                            int64_t kend, int tid, const int2* lut) {
   if (S.dt == BB_F32) stage_tile_dt<BB_F32, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
-  else stage_tile_dt<BB_BF16, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
+  else if (S.dt == BB_BF16) stage_tile_dt<BB_BF16, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
+  else stage_tile_dt<BB_F16, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
 }
 
 constexpr int kMaxLutK = 2048;   // 2 tables x 8 B x 2048 = 32 KB

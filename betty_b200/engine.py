@@ -29,6 +29,9 @@ class Settings:
     # "native": hand-written second-order tape; "autograd" (development only): torch double backward
     hvp: str = os.environ.get("BB200_HVP", "native")
     cuda_graph: bool = True   # capture one K-loop iteration and replay it
+    # mixed second derivative from the tape's boundary adjoint-tangents (one extra pass) instead of autograd's
+    # double backward; automatically off for graphs whose upper dependence the lowering could not capture
+    native_epilogue: bool = os.environ.get("BB200_EPILOGUE", "native") == "native"
     record_events: bool = True
 
 
@@ -139,7 +142,6 @@ class HypergradientCall:
             self.K, self.alpha = int(cfg.cg_iterations), float(cfg.cg_alpha)
         else:
             raise ValueError(method)
-        self.in_loss, self.in_grad, self.tape = lower_gradient(curr, want_tape=(settings.hvp == "native"))
         params = curr.trainable_parameters()
         self.dev = params[0].device
         lay = self.layout = ArenaLayout.like(params)
@@ -147,7 +149,20 @@ class HypergradientCall:
         self.d, self.hd, self.acc, self.out = lay.new(self.dev), lay.new(self.dev), lay.new(self.dev), lay.new(self.dev)
         self.r = lay.new(self.dev) if method == "cg" else None
         self.ws = Workspace.get(self.dev)
-        self.hvp = _make_hvp(curr, self.in_grad, self.tape, lay, self.d, self.hd)
+        self.in_grad = None
+        if settings.hvp == "native":
+            # prologue = the lower forward only (reference neumann.py:31 / cg.py:27), recorded as a tape; the
+            # gradient-with-graph of neumann.py:34 is needed only if the epilogue has to fall back to autograd
+            from .plan import HvpPlan
+            from .trace import record_tape
+
+            self.in_loss, self.tape = record_tape(lambda: curr.training_step_exec(curr.cur_batch), params)
+            self.hvp = HvpPlan(self.tape, params, lay, self.d, self.hd)
+            self.native_epilogue = settings.native_epilogue and self.hvp.g.native_epilogue_ok
+        else:
+            self.in_loss, self.in_grad, self.tape = lower_gradient(curr, want_tape=False)
+            self.hvp = AutogradHvp(self.in_grad, params, lay, self.d, self.hd)
+            self.native_epilogue = False
 
     def solve(self, vector: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         global last_stats
@@ -192,7 +207,31 @@ class HypergradientCall:
         return lay.views(self.out)
 
     def finish(self, prev, x, sync):
+        if self.native_epilogue:
+            return chain_boundary_seeds(self.hvp.mixed_seeds(self.out), prev, sync)
+        if self.in_grad is None:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                self.in_grad = torch.autograd.grad(self.in_loss, self.curr.trainable_parameters(), create_graph=True)
         return mixed_product(self.in_grad, prev, x, sync)
+
+
+def chain_boundary_seeds(seeds, prev, sync: bool):
+    """Finish the native epilogue: ``seeds`` = [(B, d(g.x)/dB)] for every upper-dependent tensor B that enters
+    the lower forward.  -(d^2 L_in/d lambda d w)^T x = -sum_B (dB/d lambda)^T seed_B, one ordinary first-order
+    backward through the (small) upper graph.  ``sync`` goes through ``torch.autograd.backward`` so the upper
+    module's DDP reducer all-reduces it, as in the reference (neumann.py:44-49, cg.py:58-63)."""
+    lam = prev.trainable_parameters()
+    outs = [b for b, _ in seeds]
+    grads = [-(g.to(b.dtype)) for b, g in seeds]
+    if sync:
+        if outs:
+            torch.autograd.backward(outs, grad_tensors=grads, inputs=lam)
+        return None
+    if not outs:
+        return [torch.zeros_like(p) for p in lam]
+    res = torch.autograd.grad(outs, lam, grad_outputs=grads, allow_unused=True)
+    return [torch.zeros_like(p) if r is None else r for r, p in zip(res, lam)]
 
 
 def mixed_product(in_grad, prev, x: Sequence[torch.Tensor], sync: bool):

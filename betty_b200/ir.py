@@ -36,7 +36,7 @@ class Val:
     """A lower-active tensor value."""
 
     __slots__ = ("vid", "base", "param_index", "parent", "viewfn", "full_cover", "name", "t", "a", "at",
-                 "writers", "needed", "zero_init", "ident")
+                 "writers", "needed", "zero_init", "ident", "boundary")
 
     def __init__(self, vid, base, param_index=None, parent=None, viewfn=None, full_cover=True, name="", ident=False):
         self.vid = vid
@@ -51,6 +51,7 @@ class Val:
         self.needed = False
         self.zero_init = False              # root adjoint buffers must be zeroed before BB / TB
         self.ident = ident                  # alias whose buffers are *exactly* the parent's (cast, x + const)
+        self.boundary = False               # upper-dependent constant (requires_grad, not from the lower params)
 
     @property
     def root(self) -> "Val":
@@ -98,6 +99,8 @@ class Graph:
     params: List[Val]
     loss: Val
     stats: Dict[str, int] = field(default_factory=dict)
+    boundaries: List[Val] = field(default_factory=list)   # upper-dependent tensors entering the lower tape
+    native_epilogue_ok: bool = True                        # every such tensor was captured as a boundary value
 
 
 # --------------------------------------------------------------------------------------------------
@@ -150,6 +153,9 @@ class _Lowering:
         self.all_vals: List[Val] = []
         self.nodes: List[Node] = []
         self.params: List[Val] = []
+        self.boundaries: List[Val] = []
+        self.native_epilogue_ok = True
+        self._pending_upper: set = set()
         for i, p in enumerate(tape.params):
             v = self._new(p, param_index=i, name=f"param{i}")
             self.params.append(v)
@@ -163,6 +169,21 @@ class _Lowering:
 
     def act(self, x) -> Optional[Val]:
         return self.vals.get(id(x)) if isinstance(x, torch.Tensor) else None
+
+    def boundary(self, t: torch.Tensor) -> Optional[Val]:
+        """Value for an upper-dependent constant ``t`` (requires_grad, not derived from the lower parameters).
+        It takes part in every rule as an input whose tangent is identically zero; what the tangent-backward
+        pass accumulates into its ``at`` buffer is d(g.x)/dt, the seed of the native epilogue
+        (reference neumann.py:44-54: -(d^2 L_in / d lambda d w)^T x)."""
+        if not (isinstance(t, torch.Tensor) and t.requires_grad and t.is_floating_point()):
+            return None
+        self._pending_upper.discard(id(t))
+        v = self.vals.get(id(t))
+        if v is None:
+            v = self._new(t, name="boundary")
+            v.boundary = True
+            self.boundaries.append(v)
+        return v
 
     def emit(self, op, ins, out_tensor, src, **attrs) -> Node:
         out = self._new(out_tensor) if out_tensor is not None else None
@@ -185,9 +206,15 @@ class _Lowering:
             for a in op.args:
                 if isinstance(a, (list, tuple)):
                     tensors += [x for x in a if isinstance(x, torch.Tensor)]
-            if not any(id(t) in self.vals for t in tensors):
+            if not any(id(t) in self.vals and not self.vals[id(t)].boundary for t in tensors):
                 continue  # constant w.r.t. the lower parameters (data prep, upper module forward, ...)
+            self._pending_upper = {id(t) for t in tensors
+                                   if t.requires_grad and t.is_floating_point() and id(t) not in self.vals}
             self.lower_op(op)
+            if self._pending_upper and op.name not in ("aten.detach.default", "aten.detach_.default"):
+                # an upper-dependent tensor entered an op in a slot this lowering treats as a plain constant:
+                # the K-loop is still exact, but the mixed second derivative must then come from autograd
+                self.native_epilogue_ok = False
         loss = self.vals.get(id(self.tape.loss))
         if loss is None:
             raise UnsupportedGraph("the lower loss does not depend on the lower parameters (or was produced "
@@ -195,6 +222,8 @@ class _Lowering:
         if loss.base.numel() != 1:
             raise UnsupportedGraph("the lower loss must be a scalar")
         g = Graph(self.nodes, self.all_vals, self.params, loss)
+        g.boundaries = self.boundaries
+        g.native_epilogue_ok = self.native_epilogue_ok
         if fold_quadratic:
             _fold_quadratic_regularisers(g)
         _analyse(g)
@@ -375,6 +404,11 @@ class _Lowering:
             x, c = y, a[0]
         else:
             c = a[1]
+        if isinstance(c, torch.Tensor) and c.requires_grad and not is_div and tuple(c.shape) == tuple(x.base.shape) \
+                and c.stride() == x.base.stride() and tuple(op.out.shape) == tuple(c.shape):
+            u = self.boundary(c)
+            self.emit("mul2", [x, u] if c is a[1] else [u, x], op.out, name)
+            return
         if isinstance(c, torch.Tensor):
             cc = c.detach()
             cc = cc if cc.dtype == torch.float64 else cc.to(torch.float32)  # fp64 only in the CPU rule tests
@@ -407,6 +441,12 @@ class _Lowering:
         v, s = (x, sx) if x is not None else (y, sy)
         if tuple(v.base.shape) != tuple(op.out.shape):
             raise UnsupportedGraph("broadcast of the parameter-dependent addend")
+        c = a[1] if x is not None else a[0]
+        if isinstance(c, torch.Tensor) and c.requires_grad and tuple(c.shape) == tuple(op.out.shape) \
+                and c.stride() == v.base.stride():
+            u = self.boundary(c)
+            self.emit("add2", [x, u] if x is not None else [u, y], op.out, name, sa=sx, sb=sy)
+            return
         if s == 1.0 and op.out.stride() == v.base.stride():
             # y = x + const: identity on tangents and adjoints.  The output is a fresh tensor in the
             # forward but aliases x's second-order buffers.
@@ -455,8 +495,9 @@ class _Lowering:
         bias = self.act(bias_t) if bias_t is not None else None
         if bias is not None and (bias.base.dim() != 1 or bias.base.shape[0] != op.out.shape[-1]):
             raise UnsupportedGraph("addmm bias that is not a length-N vector")
-        self.emit("gemm", [self.act(A_t), self.act(B_t), bias], op.out, name, A=A_t, B=B_t,
-                  mv=(name == "aten.mv.default"))
+        va = self.act(A_t) or self.boundary(A_t)
+        vb = self.act(B_t) or self.boundary(B_t)
+        self.emit("gemm", [va, vb, bias], op.out, name, A=A_t, B=B_t, mv=(name == "aten.mv.default"))
 
     def _conv(self, op):
         a = op.args
@@ -540,7 +581,22 @@ def _fold_quadratic_regularisers(g: Graph):
             v = v.parent
         return v if v.param_index is not None else None
 
-    folds: List[Tuple[Val, float, Val]] = []   # (param, coef, x) with term = (coef/2) * sum(x^2), x = w - const
+    def param_of(x: Val):
+        """(param, theta, s_theta) if x == param (+ s_theta * theta with theta an upper-dependent boundary)."""
+        p = ident_chain_to_param(x)
+        if p is not None:
+            return p, None, 0.0
+        n = producer.get(id(x))
+        if n is None or n.op != "add2" or len(consumers.get(id(x.root), [])) != 1:
+            return None
+        for pv, uv, sp, su in ((n.ins[0], n.ins[1], n.attrs["sa"], n.attrs["sb"]),
+                               (n.ins[1], n.ins[0], n.attrs["sb"], n.attrs["sa"])):
+            pp = ident_chain_to_param(pv)
+            if pp is not None and sp == 1.0 and uv.boundary and uv.parent is None:
+                return pp, uv, float(su)
+        return None
+
+    folds: List[Tuple[Val, float, Val, Optional[Val], float]] = []   # (param, coef, x, theta, s_theta)
     removed = set()
     quad_only = set()
     for s_node in g.nodes:
@@ -552,9 +608,10 @@ def _fold_quadratic_regularisers(g: Graph):
         if len(consumers.get(id(pw.out), [])) != 1:
             continue
         x = pw.ins[0]
-        param = ident_chain_to_param(x)
-        if param is None or tuple(x.base.shape) != tuple(param.base.shape):
+        got = param_of(x)
+        if got is None or tuple(x.base.shape) != tuple(got[0].base.shape):
             continue
+        param, theta, s_theta = got
         c, cur, ok = float(s_node.attrs["scale"]), s_node.out, True
         while cur.root is not loss_root:
             cons = consumers.get(id(cur.root), [])
@@ -573,7 +630,7 @@ def _fold_quadratic_regularisers(g: Graph):
             cur = n.out
         if not ok:
             continue
-        folds.append((param, 2.0 * c, x))
+        folds.append((param, 2.0 * c, x, theta, s_theta))
         removed.update((id(pw), id(s_node)))
         quad_only.add(id(s_node.out))
     if not folds:
@@ -596,11 +653,22 @@ def _fold_quadratic_regularisers(g: Graph):
         new_nodes.append(n)
     if id(loss_root) in quad_only:
         return   # the loss is nothing but the regulariser: keep the generic form
-    by_coef: Dict[float, List[Tuple[Val, Val]]] = {}
-    for param, coef, x in folds:
-        by_coef.setdefault(coef, []).append((param, x))
-    shifts = [Node("diagshift", [p for p, _ in items], None, {"coef": coef, "xs": [x for _, x in items]},
-                   src="folded quadratic regulariser") for coef, items in by_coef.items()]
+    # at_target += coef * t_source.  Curvature: target = source = the parameter.  Mixed term of a proximal
+    # regulariser c*sum((w + s*theta)^2): d(g.x)/d theta = 2c*s*x, target = theta's adjoint tangent.
+    by_coef: Dict[float, List[Tuple[Val, Val, Val]]] = {}
+    for param, coef, x, theta, s_theta in folds:
+        by_coef.setdefault(coef, []).append((param, param, x))
+        if theta is not None:
+            by_coef.setdefault(coef * s_theta, []).append((param, theta, None))
+            theta.needed = True
+    shifts = []
+    for coef, items in by_coef.items():
+        for is_theta in (False, True):
+            sel = [(s_, t_, x_) for s_, t_, x_ in items if (t_.boundary) == is_theta]
+            if sel:
+                shifts.append(Node("diagshift", [s_ for s_, _, _ in sel], None,
+                                   {"coef": coef, "targets": [t_ for _, t_, _ in sel], "xs": [x_ for _, _, x_ in sel]},
+                                   src="folded quadratic regulariser" + (" (mixed term)" if is_theta else "")))
     g.nodes = shifts + new_nodes
     g.stats["folded_terms"] = len(folds)
 
@@ -651,6 +719,9 @@ def _analyse(g: Graph):
                 r.zero_init = True
     for p in g.params:
         p.zero_init = True
+    for b in g.boundaries:
+        if b.parent is None:
+            b.zero_init = True    # read only by the epilogue; may have no node writer (folded proximal terms)
     g.stats = {**g.stats, "nodes": len(g.nodes), "values": sum(1 for v in g.values if v.parent is None and v.needed),
                "aliases": sum(1 for v in g.values if v.parent is not None)}
 

@@ -36,7 +36,9 @@ def _dt(t: torch.Tensor) -> int:
         return 0
     if t.dtype == torch.bfloat16:
         return 1
-    raise UnsupportedGraph(f"activation dtype {t.dtype} (only fp32 / bf16 autocast are supported)")
+    if t.dtype == torch.float16:
+        return 2
+    raise UnsupportedGraph(f"activation dtype {t.dtype} (only fp32 and bf16 / fp16 autocast are supported)")
 
 
 def _align(n: int, a: int = 64) -> int:
@@ -69,7 +71,7 @@ class HvpPlan:
     # ------------------------------------------------------------------------------------------
     def _alloc_buffers(self):
         g = self.g
-        roots = [v for v in g.values if v.parent is None and v.needed and v.param_index is None]
+        roots = [v for v in g.values if v.parent is None and (v.needed or v.boundary) and v.param_index is None]
         for v in roots:
             if not _is_dense(v.base):
                 raise UnsupportedGraph(f"activation {v} is not dense (strides {v.base.stride()})")
@@ -198,8 +200,11 @@ class HvpPlan:
     def _n_diagshift(self, n: Node, r):
         from .arena import ChunkTable
 
-        ts = [self.buf(p, "t") for p in n.ins]
-        ats = [self.buf(p, "at") for p in n.ins]
+        ts = [self.buf(p, "t") for p in n.ins]                     # sources: parameter tangents
+        ats = [self.buf(t, "at") for t in n.attrs["targets"]]      # targets: H.d slices, or a boundary's at
+        for a, b in zip(ts, ats):
+            if not (a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()):
+                raise UnsupportedGraph("folded quadratic term over a non-contiguous tensor")
         tab = ChunkTable([t.data_ptr() for t in ts], [t.data_ptr() for t in ats], [t.numel() for t in ts], self.dev,
                          keep=(ts, ats))
         self._keep.append(tab.dev)
@@ -283,7 +288,7 @@ class HvpPlan:
         r["dims"][0:4] = (M, Nn, K, batch)
         # bf16-autocast graph: this product was computed from bf16 operands by the reference too, so the
         # tensor-core (bf16 x bf16 -> fp32) kernel keeps the 1e-2 parity bar; fp32 graphs stay on exact fp32
-        r["kind"] = int(A_t.dtype == torch.bfloat16 or B_t.dtype == torch.bfloat16)
+        r["kind"] = int(A_t.dtype in (torch.bfloat16, torch.float16) or B_t.dtype in (torch.bfloat16, torch.float16))
         for d in range(3):
             r["stride"][0][d], r["stride"][1][d], r["stride"][3][d] = sa[d], sb[d], sc[d]
         self._slot(r, 0, a, A_t)
@@ -306,7 +311,7 @@ class HvpPlan:
         _, _, HO, WO = n.out.base.shape
         (sh, sw), (ph, pw), (dh, dw) = n.attrs["stride"], n.attrs["padding"], n.attrs["dilation"]
         r["dims"][0:15] = (Nn, Cc, H, Wd, O, KH, KW, HO, WO, sh, sw, ph, pw, dh, dw)
-        r["kind"] = int(X.dtype == torch.bfloat16 or W.dtype == torch.bfloat16)   # bf16 graph -> tensor cores allowed
+        r["kind"] = int(X.dtype in (torch.bfloat16, torch.float16) or W.dtype in (torch.bfloat16, torch.float16))  # reduced-precision graph -> tensor cores allowed
         self._slot(r, 0, x, X)
         self._slot(r, 1, w, W)
         self._slot(r, 2, b, None)
@@ -434,6 +439,17 @@ class HvpPlan:
         self._on_side(lambda s: N.call("bb_plan_cg_loop", self.handle, K, cg_alpha, x.data_ptr(), r.data_ptr(),
                                        p.data_ptr(), hp.data_ptr(), self.layout.total, ws.ptr, int(self.use_graph), s))
         self._count_iter(K, 3)
+
+    def mixed_seeds(self, x_arena: torch.Tensor):
+        """Native epilogue, first half: one more tangent forward/backward along x (the solve result).  Returns
+        [(B, d(g.x)/dB)] for every upper-dependent tensor B of the lower forward; `engine.chain_boundary_seeds`
+        pushes them through the upper graph.  Replaces the reference's double backward to lambda
+        (neumann.py:44-54, cg.py:58-68)."""
+        if x_arena.data_ptr() != self.d_arena.data_ptr():
+            self.d_arena.copy_(x_arena)
+        self._on_side(lambda s: N.call("bb_plan_hvp", self.handle, s))
+        self._count_iter(1, 0)
+        return [(b.base, b.at) for b in self.g.boundaries if b.parent is None and b.at is not None]
 
     def profile(self, pas: int) -> np.ndarray:
         ms = np.zeros(len(self.recs), dtype=np.float32)

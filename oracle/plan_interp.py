@@ -20,7 +20,7 @@ class Interp:
     def __init__(self, graph: Graph, dtype=torch.float64):
         self.g, self.dtype = graph, dtype
         for v in graph.values:
-            if v.parent is None and (v.needed or v.param_index is not None):
+            if v.parent is None and (v.needed or v.param_index is not None or v.boundary):
                 shape, stride = v.base.shape, v.base.stride()
                 mk = lambda: torch.zeros_like(v.base, dtype=dtype)  # preserves dense strides
                 v.t, v.a, v.at = mk(), mk(), mk()
@@ -81,12 +81,21 @@ class Interp:
         pass
 
     def bb_diagshift(self, n):
-        for p, x in zip(n.ins, n.attrs["xs"]):
-            p.a.add_(n.attrs["coef"] * self.base(x))       # gradient of (coef/2) * sum(x^2)
+        for tgt, x in zip(n.attrs["targets"], n.attrs["xs"]):
+            if x is not None:
+                tgt.a.add_(n.attrs["coef"] * self.base(x))   # gradient of (coef/2) * sum(x^2) w.r.t. the parameter
 
     def tb_diagshift(self, n):
-        for p in n.ins:
-            p.at.add_(n.attrs["coef"] * p.t)                # curvature coef * I
+        for src, tgt in zip(n.ins, n.attrs["targets"]):
+            tgt.at.add_(n.attrs["coef"] * src.t)             # curvature coef*I (target = parameter) / mixed term (theta)
+
+    def mixed_seeds(self, x: List[torch.Tensor]):
+        """d(g.x)/dB for every boundary value B: one more tangent forward/backward along x."""
+        for b in self.g.boundaries:
+            if b.at is not None:
+                b.at.zero_()
+        self.hvp(x)
+        return [(b.base, b.at) for b in self.g.boundaries if b.at is not None]
 
     # ---- unary ------------------------------------------------------------------------------------
     def _d12(self, n: Node, x: torch.Tensor):

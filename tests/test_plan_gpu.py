@@ -33,6 +33,8 @@ CASES = {
     # 64-channel 3x3 convolutions on the tensor-core implicit-GEMM path (forward / data-grad / weight-grad gathers)
     "fourconv_bf16_tc": ("implicit_maml", dict(n=6, hidden=64, precision="bf16"), 5e-2),
     "fourconv_mini_bf16_tc": ("implicit_maml", dict(n=2, hidden=32, image="miniimagenet", precision="bf16"), 5e-2),
+    "roberta_fp16": ("bert_data_reweighting", dict(batch=3, seq=9, tiny=True, precision="fp16"), 3e-2),
+    "mlp_fp16_tc": ("mlp_reweight", dict(batch=256, din=192, hidden=256, classes=64, precision="fp16"), 4e-2),
     "mlp_bf16_tc": ("mlp_reweight", dict(batch=256, din=192, hidden=256, classes=64, precision="bf16"), 4e-2),
 }
 

@@ -108,3 +108,41 @@ def test_native_descriptors_build_on_cpu(case):
     lo, hi = d.data_ptr(), d.data_ptr() + 4 * d.numel()
     for p in plan.g.params:
         assert lo <= p.t.data_ptr() < hi and p.at.data_ptr() - hv.data_ptr() == p.t.data_ptr() - lo
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_native_epilogue_seeds_reproduce_the_mixed_product(case):
+    """-(d^2 L/d lambda d w)^T x from the boundary adjoint-tangents of one extra pass + a first-order backward
+    through the upper graph == the reference's double backward (neumann.py:50-54), in float64."""
+    from betty_b200.engine import chain_boundary_seeds
+
+    fac, kw = CASES[case]
+    wl = to_double(W.FACTORIES[fac](device="cpu", **kw))
+    loss, tape, params = trace(wl)
+    g = lower_tape(tape)
+    assert g.native_epilogue_ok and len(g.boundaries) >= 1, case
+    it = Interp(g, torch.float64)
+    it.base_backward()
+    x = [torch.randn_like(p) for p in params]
+    lam = wl.upper.trainable_parameters()
+    in_grad = torch.autograd.grad(loss, params, create_graph=True)
+    want = torch.autograd.grad(in_grad, lam, grad_outputs=x, allow_unused=True, retain_graph=True)
+    want = [torch.zeros_like(p) if t is None else -t for t, p in zip(want, lam)]
+    got = chain_boundary_seeds(it.mixed_seeds(x), wl.upper, False)
+    assert rel_l2(got, want) < 1e-9, case
+
+
+def test_uncaptured_upper_dependence_disables_the_native_epilogue():
+    wl = W.mlp_reweight(device="cpu", batch=4)
+    scale = torch.nn.Parameter(torch.tensor(2.0))
+    wl.upper.module.register_parameter("gain", scale)
+
+    def step(p, batch):
+        x, y = batch
+        out = p.module(x)
+        lv = torch.nn.functional.cross_entropy(out, y, reduction="none")
+        return (lv * scale).mean()      # broadcast of a 0-dim upper parameter: not captured as a boundary
+
+    wl.lower._training_step = step
+    _, tape, _ = trace(wl)
+    assert lower_tape(tape).native_epilogue_ok is False
