@@ -32,16 +32,19 @@ def hvp_mode(request):
     E.settings.hvp = old
 
 
-def _tolerance(rec):
-    """1e-4 (fp32 bar of BASELINE.json); for the finite-difference method the reference's own fp32-vs-fp64
-    gap on the same input is the noise floor (SURVEY.md 8c protocol) and the bar is 5x that floor."""
-    if rec["method"] != "darts":
-        return 1e-4
-    w32 = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
-    w64 = to_double(W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"]))
-    floor = rel_l2(ref_port.darts(w32.vector, w32.lower, w32.upper, False),
-                   ref_port.darts(w64.vector, w64.lower, w64.upper, False))
-    return max(1e-4, 5 * floor)
+_FLOOR = {}
+
+
+def _tolerance(rec, case):
+    """1e-4 (fp32 bar of BASELINE.json) or, where the reference's own arithmetic is noisier than that, 5x the
+    reference's fp32-vs-fp64 gap on the same input -- the SURVEY.md 8(c) protocol (CG on small un-shifted
+    problems and the finite-difference method sit at 2e-5...5e-4 in the reference itself)."""
+    if case not in _FLOOR:
+        w32 = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
+        w64 = to_double(W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"]))
+        fn = ref_port.METHODS[rec["method"]]
+        _FLOOR[case] = rel_l2(fn(w32.vector, w32.lower, w32.upper, False), fn(w64.vector, w64.lower, w64.upper, False))
+    return max(1e-4, 5 * _FLOOR[case])
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -49,7 +52,7 @@ def test_engine_matches_reference_golden(case, hvp_mode):
     rec = load_golden(case)
     wl = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
     got = H.jvp_fn_mapping[rec["method"]](wl.vector, wl.lower, wl.upper, False)
-    assert_close(got, rec["hypergrad"], _tolerance(rec), f"{case}[{hvp_mode}]")
+    assert_close(got, rec["hypergrad"], _tolerance(rec, case), f"{case}[{hvp_mode}]")
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -59,7 +62,7 @@ def test_engine_matches_oracle_same_device(case, hvp_mode):
     want = ref_port.METHODS[rec["method"]](wl.vector, wl.lower, wl.upper, False)
     w_before = [p.detach().clone() for p in wl.lower.parameters()]
     got = H.jvp_fn_mapping[rec["method"]](wl.vector, wl.lower, wl.upper, False)
-    assert_close(got, want, _tolerance(rec), f"{case}[{hvp_mode}]")
+    assert_close(got, want, _tolerance(rec, case), f"{case}[{hvp_mode}]")
     # inputs are borrowed: parameters restored / untouched (SURVEY §8b ownership)
     for a, b in zip(wl.lower.parameters(), w_before):
         assert torch.allclose(a, b, rtol=0, atol=1e-6)
