@@ -1,13 +1,17 @@
 """Call-level orchestration shared by the neumann / cg plugins.
 
 One hypergradient call =
-  prologue   lower forward on ``curr.cur_batch`` (recorded as an op tape when the native HVP is on)
-             and ``g = grad_w L_in`` with a graph           (reference neumann.py:31-36, cg.py:27-32)
+  prologue   lower forward on ``curr.cur_batch``, recorded as an aten op tape   (reference neumann.py:31, cg.py:27;
+             the reference's ``grad(..., create_graph=True)`` at :34 / :30 is NOT needed by the native path)
   K-loop     K Hessian-vector products + vector updates      (reference neumann.py:59-66, cg.py:34-56)
-             -> CUDA: flat-arena kernels K1-K3 (csrc/kloop.cu) around either
-                  * the native second-order tape (csrc/plan.cu, K5-K9), or
-                  * (development mode ``hvp="autograd"``) torch's double backward
-  epilogue   ``-(d^2 L_in/d lambda d w)^T x`` through autograd (reference neumann.py:44-54, cg.py:58-68)
+             -> CUDA: the native second-order tape (csrc/plan.cu, K5-K9) + flat-arena kernels K1-K3
+                (csrc/kloop.cu), one CUDA graph per iteration
+  epilogue   ``-(d^2 L_in/d lambda d w)^T x``                 (reference neumann.py:44-54, cg.py:58-68)
+             -> one more tangent forward/backward along x gives d(g.x)/dB for every upper-dependent tensor B of
+                the lower forward; a first-order ``autograd`` backward through the (small) upper graph finishes.
+                Graphs whose upper dependence the lowering cannot capture fall back to the reference's double
+                backward for this step only.
+(development mode ``hvp="autograd"``: H.v by torch's double backward around the same K1-K3 kernels)
 
 There is no CPU path: everything here raises without a CUDA device.
 """
@@ -83,20 +87,15 @@ class Workspace:
         return ws
 
 
-def lower_gradient(curr, want_tape: bool):
-    """Prologue.  Returns (in_grad, tape-or-None)."""
+def lower_gradient(curr):
+    """Reference prologue (neumann.py:31-36, cg.py:27-32): lower loss on the last batch and its gradient with a
+    graph.  Only the development mode ``hvp="autograd"`` and the autograd-epilogue fallback need it."""
     params = curr.trainable_parameters()
-    tape = None
-    if want_tape:
-        from .trace import record_tape
-
-        in_loss, tape = record_tape(lambda: curr.training_step_exec(curr.cur_batch), params)
-    else:
-        in_loss = curr.training_step_exec(curr.cur_batch)
+    in_loss = curr.training_step_exec(curr.cur_batch)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         in_grad = torch.autograd.grad(in_loss, params, create_graph=True)
-    return in_loss, in_grad, tape
+    return in_loss, in_grad
 
 
 class AutogradHvp:
@@ -117,14 +116,6 @@ def _events():
     if not settings.record_events:
         return None, None
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-
-def _make_hvp(curr, in_grad, tape, layout, d_arena, hv_arena):
-    if settings.hvp == "autograd":
-        return AutogradHvp(in_grad, curr.trainable_parameters(), layout, d_arena, hv_arena)
-    from .plan import HvpPlan
-
-    return HvpPlan(tape, curr.trainable_parameters(), layout, d_arena, hv_arena)
 
 
 class HypergradientCall:
@@ -160,7 +151,8 @@ class HypergradientCall:
             self.hvp = HvpPlan(self.tape, params, lay, self.d, self.hd)
             self.native_epilogue = settings.native_epilogue and self.hvp.g.native_epilogue_ok
         else:
-            self.in_loss, self.in_grad, self.tape = lower_gradient(curr, want_tape=False)
+            self.in_loss, self.in_grad = lower_gradient(curr)
+            self.tape = None
             self.hvp = AutogradHvp(self.in_grad, params, lay, self.d, self.hd)
             self.native_epilogue = False
 

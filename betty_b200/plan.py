@@ -6,7 +6,7 @@ drives the C executor (csrc/plan.cu).  After construction the K-loop makes no Py
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch
