@@ -36,6 +36,39 @@ inline bool dense_block(int64_t M, int64_t N, int64_t batch, int64_t rs, int64_t
   return ok && (batch == 1 || bs == M * N);
 }
 
+// ---- vectorised fp32 fast path ----------------------------------------------------------------------------
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// 0: not eligible; otherwise bit0 = A k-fast, bit1 = B k-fast, bit2 = eligible
+int vec_mode(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const Mat* L, const Mat* R) {
+  if (batch != 1 || npairs < 1) return 0;
+  for (int p = 0; p < npairs; ++p) {
+    if (L[p].dt != BB_F32 || R[p].dt != BB_F32 || !aligned16(L[p].p) || !aligned16(R[p].p)) return 0;
+    if (L[p].rs != L[0].rs || L[p].cs != L[0].cs || R[p].rs != R[0].rs || R[p].cs != R[0].cs) return 0;
+  }
+  int mode = 4;
+  if (L[0].cs == 1 && K % 4 == 0 && L[0].rs % 4 == 0) mode |= 1;             // A[m][k], k contiguous
+  else if (!(L[0].rs == 1 && M % 4 == 0 && L[0].cs % 4 == 0)) return 0;       // A[m][k], m contiguous
+  if (R[0].rs == 1 && K % 4 == 0 && R[0].cs % 4 == 0) mode |= 2;             // B[k][n], k contiguous
+  else if (!(R[0].cs == 1 && N % 4 == 0 && R[0].rs % 4 == 0)) return 0;       // B[k][n], n contiguous
+  return mode;
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_vec(int mode, const bb::VecOperands& op, const StridedStore& sc, int64_t M, int64_t N, int64_t K, int npairs,
+               int ksplit, dim3 grid, cudaStream_t s) {
+  constexpr int T = (BM / TM) * (BN / TN);
+  switch (mode & 3) {
+    case 0: bb::tile_gemm_vec_kernel<BM, BN, TM, TN, false, false, StridedStore><<<grid, T, 0, s>>>(op, sc, M, N, K, npairs, ksplit); break;
+    case 1: bb::tile_gemm_vec_kernel<BM, BN, TM, TN, true, false, StridedStore><<<grid, T, 0, s>>>(op, sc, M, N, K, npairs, ksplit); break;
+    case 2: bb::tile_gemm_vec_kernel<BM, BN, TM, TN, false, true, StridedStore><<<grid, T, 0, s>>>(op, sc, M, N, K, npairs, ksplit); break;
+    default: bb::tile_gemm_vec_kernel<BM, BN, TM, TN, true, true, StridedStore><<<grid, T, 0, s>>>(op, sc, M, N, K, npairs, ksplit);
+  }
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
 // out (M x N) (beta)= sum_p L_p (M x K) . R_p (K x N)  [+ bias]
 int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const Mat* L, const Mat* R, float* out,
              int64_t ors, int64_t ocs, int64_t obs, int beta, const float* bias, int64_t bias_stride,
@@ -82,6 +115,17 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
     bb_launch_tally += 1;
   }
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)(batch * ksplit));
+  const int vmode = (small_m || small_n || getenv("BB200_NO_VEC_GEMM")) ? 0 : vec_mode(M, N, K, batch, npairs, L, R);
+  if (vmode) {
+    bb::VecOperands op{};
+    for (int p = 0; p < npairs; ++p) {
+      op.a[p] = reinterpret_cast<const float*>(L[p].p);
+      op.b[p] = reinterpret_cast<const float*>(R[p].p);
+    }
+    op.ars = L[0].rs; op.acs = L[0].cs; op.brs = R[0].rs; op.bcs = R[0].cs;
+    return mid ? launch_vec<32, 32, 2, 2>(vmode, op, sc, M, N, K, npairs, ksplit, grid, s)
+               : launch_vec<64, 64, 4, 4>(vmode, op, sc, M, N, K, npairs, ksplit, grid, s);
+  }
   if (small_m)
     bb::tile_gemm_kernel<16, 64, 16, 1, 4, StridedLoad, StridedLoad, StridedStore><<<grid, 256, 0, s>>>(la, lb, sc, M, N, K, npairs, ksplit);
   else if (small_n)
