@@ -18,8 +18,10 @@ namespace {
 
 constexpr int PX = 4;  // output pixels per thread along x
 
-template <int OP, int KW>
-__global__ void __launch_bounds__(256) conv_small_corr_kernel(const __grid_constant__ SmallConvArgs A) {
+// OP = padded channel count of the shared-memory weight rows (8 / 16), CO_T = channels actually accumulated
+// (compile time, so a 6-channel layer issues 6/8 of the FMAs), F32IN = every input map is fp32.
+template <int OP, int KW, int CO_T, bool F32IN>
+__global__ void __launch_bounds__(256, 2) conv_small_corr_kernel(const __grid_constant__ SmallConvArgs A) {
   extern __shared__ float wsm[];  // [npairs][K][OP], K = CI*KH*KW
   const int K = A.CI * A.KH * KW;
   for (int e = threadIdx.x; e < A.npairs * K * OP; e += blockDim.x) {
@@ -44,6 +46,19 @@ __global__ void __launch_bounds__(256) conv_small_corr_kernel(const __grid_const
   const int n = (int)(gid / ((int64_t)G * A.HO));
   const int x0 = xg * PX;
 
+  // column validity of the PX+KW-1 inputs this thread reads in every row: hoisted out of the channel / row loops
+  // (a 0/1 multiplier and a clamped column instead of per-load predicates)
+  constexpr int NV = PX + KW - 1;
+  float fm[NV];
+  int col[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const int xx = x0 - A.pw + q;
+    const bool ok = xx >= 0 && xx < A.W;
+    fm[q] = ok ? 1.f : 0.f;
+    col[q] = ok ? xx : 0;
+  }
+
   float acc[OP][PX];
 #pragma unroll
   for (int o = 0; o < OP; ++o)
@@ -52,29 +67,32 @@ __global__ void __launch_bounds__(256) conv_small_corr_kernel(const __grid_const
 
   for (int p = 0; p < A.npairs; ++p) {
     const float* wp = wsm + (int64_t)p * K * OP;
+    const float* inf = reinterpret_cast<const float*>(A.in[p]);
     for (int ci = 0; ci < A.CI; ++ci) {
       const int64_t plane = ((int64_t)n * A.CI + ci) * A.H;
       for (int i = 0; i < A.KH; ++i) {
         const int hy = y - A.ph + i;
         if (hy < 0 || hy >= A.H) continue;
-        float v[PX + KW - 1];
+        const int64_t rowb = (plane + hy) * A.W;
+        float v[NV];
 #pragma unroll
-        for (int q = 0; q < PX + KW - 1; ++q) {
-          const int xx = x0 - A.pw + q;
-          v[q] = (xx >= 0 && xx < A.W) ? bb::ldf(A.in[p], (plane + hy) * A.W + xx, A.dt_in[p]) : 0.f;
+        for (int q = 0; q < NV; ++q) {
+          if (F32IN) v[q] = inf[rowb + col[q]] * fm[q];
+          else v[q] = bb::ldf(A.in[p], rowb + col[q], A.dt_in[p]) * fm[q];
         }
         const float* wr = wp + (int64_t)((ci * A.KH + i) * KW) * OP;
 #pragma unroll
         for (int j = 0; j < KW; ++j) {
 #pragma unroll
           for (int o = 0; o < OP; o += 4) {
+            if (o >= CO_T) break;
             const float4 w4 = *reinterpret_cast<const float4*>(wr + j * OP + o);
 #pragma unroll
             for (int q = 0; q < PX; ++q) {
               acc[o + 0][q] = fmaf(v[q + j], w4.x, acc[o + 0][q]);
-              acc[o + 1][q] = fmaf(v[q + j], w4.y, acc[o + 1][q]);
-              acc[o + 2][q] = fmaf(v[q + j], w4.z, acc[o + 2][q]);
-              acc[o + 3][q] = fmaf(v[q + j], w4.w, acc[o + 3][q]);
+              if (o + 1 < CO_T) acc[o + 1][q] = fmaf(v[q + j], w4.y, acc[o + 1][q]);
+              if (o + 2 < CO_T) acc[o + 2][q] = fmaf(v[q + j], w4.z, acc[o + 2][q]);
+              if (o + 3 < CO_T) acc[o + 3][q] = fmaf(v[q + j], w4.w, acc[o + 3][q]);
             }
           }
         }
@@ -83,7 +101,7 @@ __global__ void __launch_bounds__(256) conv_small_corr_kernel(const __grid_const
   }
 #pragma unroll
   for (int o = 0; o < OP; ++o) {
-    if (o >= A.CO) break;
+    if (o >= A.CO || o >= CO_T) break;
     const float b = A.bias ? A.bias[o] : 0.f;
     float* dst = A.out + (((int64_t)n * A.CO + o) * A.HO + y) * A.WO + x0;
 #pragma unroll
@@ -177,13 +195,17 @@ __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(const __grid_cons
   }
 }
 
-template <int OP, int KW>
+template <int OP, int KW, int CO_T>
 int launch_corr(const SmallConvArgs& A, cudaStream_t s) {
   const int K = A.CI * A.KH * KW;
   const size_t smem = sizeof(float) * (size_t)A.npairs * K * OP;
   const int G = (A.WO + PX - 1) / PX;
   const int64_t total = (int64_t)A.N * A.HO * G;
-  conv_small_corr_kernel<OP, KW><<<(unsigned)((total + 255) / 256), 256, smem, s>>>(A);
+  bool f32 = true;
+  for (int p = 0; p < A.npairs; ++p) f32 = f32 && A.dt_in[p] == BB_F32;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (f32) conv_small_corr_kernel<OP, KW, CO_T, true><<<grid, 256, smem, s>>>(A);
+  else conv_small_corr_kernel<OP, KW, CO_T, false><<<grid, 256, smem, s>>>(A);
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();
   return BB_OK;
@@ -198,8 +220,9 @@ bool bb_conv_small_corr_ok(int CI, int CO, int KH, int KW, int npairs) {
 }
 
 int bb_conv_small_corr(const SmallConvArgs& A, cudaStream_t s) {
-  if (A.CO <= 8) return A.KW == 3 ? launch_corr<8, 3>(A, s) : launch_corr<8, 5>(A, s);
-  return A.KW == 3 ? launch_corr<16, 3>(A, s) : launch_corr<16, 5>(A, s);
+  if (A.CO == 6) return A.KW == 3 ? launch_corr<8, 3, 6>(A, s) : launch_corr<8, 5, 6>(A, s);   // LeNet: 6 maps
+  if (A.CO <= 8) return A.KW == 3 ? launch_corr<8, 3, 8>(A, s) : launch_corr<8, 5, 8>(A, s);
+  return A.KW == 3 ? launch_corr<16, 3, 16>(A, s) : launch_corr<16, 5, 16>(A, s);
 }
 
 static size_t wgrad_smem_bytes(int O, int C, int H, int W, int HO, int WO) {
