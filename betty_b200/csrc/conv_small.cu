@@ -167,20 +167,37 @@ __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(const __grid_cons
           if (hy < 0 || hy >= A.H) continue;
           const float* grow = gs + to[u] * gplane + y * gp;
           const float* irow = is + tc[u] * iplane + hy * ip;
-          float win[KW];
+          // sliding window over the input row, 4 output pixels per step: win[u + j] = in[x + u + j - pw]
+          float win[KW + 3];
 #pragma unroll
           for (int j = 0; j < KW - 1; ++j) {
             const int xx = j - A.pw;
-            win[j + 1] = (xx >= 0 && xx < A.W) ? irow[xx] : 0.f;  // pre-shifted: next step shifts left
+            win[j] = (xx >= 0 && xx < A.W) ? irow[xx] : 0.f;
           }
-          for (int x = 0; x < A.WO; ++x) {
+          int x = 0;
+          for (; x + 4 <= A.WO; x += 4) {
+            float gv[4];
 #pragma unroll
-            for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const int xx = x + u4 + KW - 1 - A.pw;
+              win[KW - 1 + u4] = (xx >= 0 && xx < A.W) ? irow[xx] : 0.f;
+              gv[u4] = grow[x + u4];
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4)
+#pragma unroll
+              for (int j = 0; j < KW; ++j) acc[u][j] = fmaf(gv[u4], win[u4 + j], acc[u][j]);
+#pragma unroll
+            for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 4];
+          }
+          for (; x < A.WO; ++x) {   // tail
             const int xx = x + KW - 1 - A.pw;
             win[KW - 1] = (xx >= 0 && xx < A.W) ? irow[xx] : 0.f;
             const float gv = grow[x];
 #pragma unroll
             for (int j = 0; j < KW; ++j) acc[u][j] = fmaf(gv, win[j], acc[u][j]);
+#pragma unroll
+            for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
           }
         }
       }
