@@ -88,6 +88,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
+// MN-major SWIZZLE_128B descriptor (operand stored with the M/N index contiguous): canonical layout
+// ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in bf16 elements -- an atom is 8 k-rows x 64 mn (1024 B), atoms of one
+// 64-wide mn block are consecutive along k (SBO = 1024 B), the next mn block starts LBO bytes later.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format BF16 (1) @7/@10,
 // a/b major K (0), n_dim = N>>3 @17, m_dim = M>>4 @24 -- see Cfg<BN>::kIdesc
 
@@ -340,12 +353,79 @@ __device__ __forceinline__ void stage_by_chunk_t(uint8_t* tile, const TcSrc& S, 
   }
 }
 
+// --- MN-major tile from a source whose ROWS are adjacent in memory (rs == 1): element(row,k) = p[row + k*cs].
+//     One 8-row chunk (16 B of bf16) per (k, chunk): the global read is contiguous, no transposition is needed,
+//     the tensor core reads the tile through an MN-major descriptor.  byte(row,k) = ((row/64)*8 + k/8)*1024 +
+//     (k%8)*128 + ((((row%64)/8) ^ (k%8)) << 4) + (row%8)*2
+template <int DT, int ROWS>
+__device__ __forceinline__ void stage_mn_t(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
+                                           int64_t kend, int tid) {
+  using R = Raw<DT>;
+  const typename R::T* p = reinterpret_cast<const typename R::T*>(S.p);
+  constexpr int CPR = ROWS / 8;                 // 8-row chunks per k
+  constexpr int TOTAL = CPR * BK;               // chunks per tile
+  constexpr int PER = TOTAL / NPROD;            // 4 (128 rows) or 2 (64 rows)
+  constexpr int VEC = DT == BB_F32 ? 2 : 1;     // 16-byte loads per chunk
+  const bool vec_ok = ((S.cs * (int64_t)sizeof(typename R::T)) % 16 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p + row0) & 15) == 0) && (row0 + ROWS <= nrows);
+  auto dst_of = [&](int c, int k) {
+    const int blk = c >> 3, cc = c & 7, kb = k >> 3, r = k & 7;
+    return reinterpret_cast<uint4*>(tile + (blk * (BK / 8) + kb) * 1024 + r * 128 + ((cc ^ r) << 4));
+  };
+  if (vec_ok) {
+    uint4 raw[PER][VEC];
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int q = tid + it * NPROD;
+      const int c = q % CPR, k = q / CPR;
+      const int64_t gk = (k0 + k < kend) ? k0 + k : k0;
+      const uint4* src = reinterpret_cast<const uint4*>(p + row0 + c * 8 + gk * S.cs);
+      raw[it][0] = src[0];
+      if (VEC == 2) raw[it][VEC - 1] = src[1];
+    }
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int q = tid + it * NPROD;
+      const int c = q % CPR, k = q / CPR;
+      uint4 out;
+      if (DT == BB_F32) {
+        const float* f0 = reinterpret_cast<const float*>(&raw[it][0]);
+        const float* f1 = reinterpret_cast<const float*>(&raw[it][VEC - 1]);
+        out.x = pack_bf16(f0[0], f0[1]); out.y = pack_bf16(f0[2], f0[3]);
+        out.z = pack_bf16(f1[0], f1[1]); out.w = pack_bf16(f1[2], f1[3]);
+      } else if (DT == BB_BF16) {
+        out = raw[it][0];
+      } else {
+        const unsigned short* h = reinterpret_cast<const unsigned short*>(&raw[it][0]);
+        out.x = pack_bf16(R::cvt(h[0]), R::cvt(h[1])); out.y = pack_bf16(R::cvt(h[2]), R::cvt(h[3]));
+        out.z = pack_bf16(R::cvt(h[4]), R::cvt(h[5])); out.w = pack_bf16(R::cvt(h[6]), R::cvt(h[7]));
+      }
+      if (k0 + k >= kend) out = make_uint4(0, 0, 0, 0);
+      *dst_of(c, k) = out;
+    }
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < PER; ++it) {
+      const int q = tid + it * NPROD;
+      const int c = q % CPR, k = q / CPR;
+      const int64_t gk = k0 + k, gr = row0 + c * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (gk < kend && gr + e < nrows) ? R::cvt(p[gr + e + gk * S.cs]) : 0.f;
+      uint4 out;
+      out.x = pack_bf16(v[0], v[1]); out.y = pack_bf16(v[2], v[3]); out.z = pack_bf16(v[4], v[5]); out.w = pack_bf16(v[6], v[7]);
+      *dst_of(c, k) = out;
+    }
+  }
+}
+
 template <int DT, int ROWS>
 __device__ __forceinline__ void stage_tile_dt(uint8_t* tile, const TcSrc& S, int64_t row0, int64_t nrows, int64_t k0,
                                               int64_t kend, int tid, const int2* lut) {
   switch (S.mode) {
     case TC_STRIDED:
       if (S.cs == 1) stage_by_chunk_t<TC_STRIDED, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
+      else if (S.mn_major) stage_mn_t<DT, ROWS>(tile, S, row0, nrows, k0, kend, tid);
       else stage_by_row_t<TC_STRIDED, DT, ROWS>(tile, S, row0, nrows, k0, kend, tid, lut);
       break;
     case TC_PIXROW:
@@ -493,13 +573,19 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const __grid_co
     if (lane == 0) {
       for (int it = 0; it < total_kb; ++it) {
         const int s = it % STAGES;
+        const int pair = it / nkb;
+        const bool a_mn = G.a[pair].mn_major != 0, b_mn = G.b[pair].mn_major != 0;
+        const uint32_t idesc = C::kIdesc | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
         mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * C::kStage), b_addr = a_addr + TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          umma_bf16(tmem_base, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), C::kIdesc,
-                    (it > 0 || k > 0) ? 1u : 0u);
+          // K-major tiles advance 32 B per 16-wide k-step inside the 128-byte rows; MN-major tiles advance two
+          // 1024-byte k-atoms
+          const uint64_t da = a_mn ? make_desc_mn(a_addr + k * 2048, (BK / 8) * 1024) : make_desc(a_addr + k * 32);
+          const uint64_t db = b_mn ? make_desc_mn(b_addr + k * 2048, (BK / 8) * 1024) : make_desc(b_addr + k * 32);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);   // stage free once these MMAs have read it
       }
@@ -557,6 +643,12 @@ int bb_gemm_tc_run(const TcGemmArgs& G0, cudaStream_t s) {
     }
   }
   G.ksplit = ksplit;
+  // row-contiguous strided operands (transposed views) are staged MN-major: contiguous 16-byte reads, no transpose
+  static const bool no_mn = getenv("BB200_TC_NO_MN") != nullptr;
+  for (int p = 0; p < G.npairs; ++p) {
+    G.a[p].mn_major = (!no_mn && G.a[p].mode == TC_STRIDED && G.a[p].rs == 1 && G.a[p].cs != 1) ? 1 : 0;
+    G.b[p].mn_major = (!no_mn && G.b[p].mode == TC_STRIDED && G.b[p].rs == 1 && G.b[p].cs != 1) ? 1 : 0;
+  }
   const bool need_lut = G.a[0].mode == TC_PIXROW || G.a[0].mode == TC_WDGRAD || G.b[0].mode == TC_PIXROW ||
                         G.b[0].mode == TC_WDGRAD;
   G.lut_k = need_lut ? (int)G.K : 0;

@@ -17,6 +17,7 @@ struct TcSrc {
   //     value = src[img, ch, flip ? y+py-i : y-py+i, flip ? x+px-j : x-px+j]  (0 outside the source)
   //   TC_WDGRAD  row = c (< C2), k = (o,i,j): value = p[((o*C2 + c)*KH + i)*KW + j]
   int CH, H, W, KH, KW, GH, GW, py, px, flip, C2;
+  int mn_major;      // set by bb_gemm_tc_run: stage this (row-contiguous) operand in the MN-major smem layout
 };
 
 struct TcGemmArgs {
