@@ -103,9 +103,9 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
   const int BM = small_m ? 16 : (mid ? 32 : 64), BN = small_n ? 16 : (mid ? 32 : 64);
   const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
   int ksplit = 1;
-  if (npairs > 0 && tiles < BB_SM_COUNT && K >= 1024 && dense_block(M, N, batch, ors, ocs, obs)) {
+  if (npairs > 0 && tiles < BB_SM_COUNT && K >= 256 && dense_block(M, N, batch, ors, ocs, obs)) {
     int64_t want = (2 * BB_SM_COUNT + tiles - 1) / tiles;
-    int64_t maxs = K / 256;
+    int64_t maxs = K / 64;
     ksplit = (int)(want < maxs ? want : maxs);
     if (ksplit > 64) ksplit = 64;
     if (ksplit < 1) ksplit = 1;
