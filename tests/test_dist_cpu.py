@@ -43,7 +43,22 @@ def _worker(rank, world, port, out_dir):
     local = [-t for t in torch.autograd.grad(in_grad, wl.upper.trainable_parameters(), grad_outputs=xs, retain_graph=True)]
     assert E.mixed_product(in_grad, wl.upper, xs, True) is None
     synced = [p.grad.clone() for p in wl.upper.trainable_parameters()]
-    torch.save({"local": local, "synced": synced}, os.path.join(out_dir, f"r{rank}.pt"))
+
+    # the native epilogue (boundary seeds -> first-order backward through the DDP-wrapped upper module) must give
+    # the same all-reduced result; the seeds come from the torch interpreter here (the CUDA plan needs a GPU)
+    from betty_b200.ir import lower_tape
+    from betty_b200.trace import record_tape
+    from oracle.plan_interp import Interp
+
+    for p in wl.upper.trainable_parameters():
+        p.grad = None
+    params = wl.lower.trainable_parameters()
+    loss, tape = record_tape(lambda: wl.lower.training_step_exec(wl.lower.cur_batch), params)
+    it = Interp(lower_tape(tape), torch.float32)
+    it.base_backward()
+    assert E.chain_boundary_seeds(it.mixed_seeds([t.detach() for t in xs]), wl.upper, True) is None
+    synced_native = [p.grad.clone() for p in wl.upper.trainable_parameters()]
+    torch.save({"local": local, "synced": synced, "synced_native": synced_native}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -56,5 +71,9 @@ def test_sync_epilogue_allreduces_local_solves(tmp_path):
     for i, s in enumerate(recs[0]["synced"]):
         mean = (recs[0]["local"][i] + recs[1]["local"][i]) / 2
         assert torch.allclose(s, mean, rtol=1e-5, atol=1e-7)
+    for a, b in zip(recs[0]["synced_native"], recs[0]["synced"]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    for a, b in zip(recs[0]["synced_native"], recs[1]["synced_native"]):
+        assert torch.equal(a, b)
     # and the local solves really differ (no hidden communication in the K-loop)
     assert not torch.allclose(recs[0]["local"][0], recs[1]["local"][0])

@@ -88,3 +88,29 @@ def test_get_grads_walks_the_path(hvp_mode):
     v = torch.autograd.grad(upper_loss, wl.lower.trainable_parameters())
     want = ref_port.cg(v, wl.lower, wl.upper, False)
     assert_close(got, want, 1e-4, "get_grads")
+
+
+@pytest.mark.parametrize("method", ["neumann", "cg"])
+@pytest.mark.parametrize("K", [0, 1, 2])
+def test_degenerate_iteration_counts(method, K):
+    """K = 0 (no H.v at all), 1 (no graph replay) and 2 against the oracle."""
+    wl = W.mlp_reweight(device="cuda", method=method, K=K, alpha=0.3 if method == "neumann" else 1.0)
+    want = ref_port.METHODS[method](wl.vector, wl.lower, wl.upper, False)
+    got = H.jvp_fn_mapping[method](wl.vector, wl.lower, wl.upper, False)
+    if float(torch.cat([w.reshape(-1) for w in want]).norm()) == 0.0:
+        assert float(torch.cat([g.reshape(-1) for g in got]).norm()) == 0.0
+    else:
+        assert_close(got, want, 1e-4, f"{method} K={K}")
+
+
+def test_non_contiguous_and_borrowed_direction():
+    """`vector` is borrowed: non-contiguous inputs are accepted and never modified (SURVEY 8b ownership)."""
+    wl = W.mlp_reweight(device="cuda", method="cg", K=3)
+    vec = [v.t().contiguous().t() if v.dim() == 2 else v for v in wl.vector]   # same values, column-major storage
+    assert any(not v.is_contiguous() for v in vec)
+    keep = [v.clone() for v in vec]
+    want = ref_port.cg(wl.vector, wl.lower, wl.upper, False)
+    got = H.cg(vec, wl.lower, wl.upper, False)
+    assert_close(got, want, 1e-4, "non-contiguous v")
+    for a, b in zip(vec, keep):
+        assert torch.equal(a, b)
