@@ -112,6 +112,19 @@ class AutogradHvp:
         pack(self.layout, hv, self.hv_arena)
 
 
+class _nvtx:
+    """NVTX range around a call phase (visible in nsys / ncu timelines; free when no profiler is attached)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+
+
 def _events():
     if not settings.record_events:
         return None, None
@@ -147,8 +160,10 @@ class HypergradientCall:
             from .plan import HvpPlan
             from .trace import record_tape
 
-            self.in_loss, self.tape = record_tape(lambda: curr.training_step_exec(curr.cur_batch), params)
-            self.hvp = HvpPlan(self.tape, params, lay, self.d, self.hd)
+            with _nvtx("betty_b200:prologue:trace"):
+                self.in_loss, self.tape = record_tape(lambda: curr.training_step_exec(curr.cur_batch), params)
+            with _nvtx("betty_b200:prologue:plan"):
+                self.hvp = HvpPlan(self.tape, params, lay, self.d, self.hd)
             self.native_epilogue = settings.native_epilogue and self.hvp.g.native_epilogue_ok
         else:
             self.in_loss, self.in_grad = lower_gradient(curr)
@@ -161,6 +176,7 @@ class HypergradientCall:
         lay, s, n = self.layout, stream_ptr(), self.layout.total
         K, alpha, hvp = self.K, self.alpha, self.hvp
         d, hd, acc = self.d, self.hd, self.acc
+        torch.cuda.nvtx.range_push(f"betty_b200:kloop:{self.method}:K={K}")
         pack(lay, vector, d)
         e0, e1 = _events()
         if self.method == "neumann":
@@ -195,12 +211,14 @@ class HypergradientCall:
             if e1 is not None:
                 e1.record()
             N.call("bb_scale", self.out.data_ptr(), acc.data_ptr(), alpha, n, s)
+        torch.cuda.nvtx.range_pop()
         last_stats = CallStats(self.method, K, lay.n_logical, e0, e1, getattr(hvp, "launches_per_iter", 0))
         return lay.views(self.out)
 
     def finish(self, prev, x, sync):
         if self.native_epilogue:
-            return chain_boundary_seeds(self.hvp.mixed_seeds(self.out), prev, sync)
+            with _nvtx("betty_b200:epilogue:native"):
+                return chain_boundary_seeds(self.hvp.mixed_seeds(self.out), prev, sync)
         if self.in_grad is None:
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
