@@ -11,6 +11,8 @@
 
 #include "../../include/betty_b200.h"
 #include "conv_small.h"
+#include "conv_tma.h"
+#include "gemm_tma.h"
 #include "gemm_tc.h"
 #include "plan.h"
 #include "tile_gemm.cuh"
@@ -179,6 +181,17 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   int rc;
   const bool unit = g.sh == 1 && g.sw == 1 && g.dh == 1 && g.dw == 1 && !getenv("BB200_CONV_IGEMM");
   const bool tc = (nd.kind & 1) && unit && !getenv("BB200_NO_TC") && g.O >= 32 && CKK <= 2048 && OKK <= 2048;
+  // preferred tensor-core route: NHWC bf16 packs + TMA box loads (conv_tma.cu)
+  bool tma_done = false;
+  if (unit && bb_conv_tma_ok(nd, pass)) {
+    rc = bb_conv_tma_run(nd, pass, s);
+    if (rc == BB_OK) {
+      if (pass == BB_PASS_TAN_FWD) return BB_OK;
+      tma_done = true;
+    } else if (rc != BB_DECLINED) {
+      return rc;
+    }
+  }
   if (pass == BB_PASS_TAN_FWD && tc) {
     // D[pixel][o] = sum_(c,i,j) im2col(t_x)[pixel][cij] * W[o][cij] + im2col(x)[pixel][cij] * t_W[o][cij]
     TcGemmArgs G{};
@@ -219,7 +232,7 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   }
   const bool base = pass == BB_PASS_BASE_BWD;
   const void* gy = base ? nd.a[3] : nd.at[3];
-  const int need = base ? nd.pad0 : nd.active;
+  const int need = (base ? nd.pad0 : nd.active) & (tma_done ? ~3 : ~0);
   if ((need & 1) && tc && g.C >= 32) {
     // D[in-pixel][c] = sum_(o,i,j) g[img,o,y+ph-i,x+pw-j] * W[o][c][i][j]  (+ a_y with t_W)
     TcGemmArgs G{};

@@ -11,6 +11,7 @@
 
 #include "../../include/betty_b200.h"
 #include "gemm_tc.h"
+#include "gemm_tma.h"
 #include "plan.h"
 #include "tile_gemm.cuh"
 
@@ -75,7 +76,20 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
              cudaStream_t s, bool tensor_cores = false) {
   if (M <= 0 || N <= 0 || batch <= 0) return BB_OK;
   if (tensor_cores && npairs > 0 && bb_gemm_tc_eligible(M, N, K, batch)) {
-    // bf16-autocast configuration: tcgen05 path (operands rounded to bf16, fp32 accumulation in TMEM)
+    // bf16-autocast configuration: tcgen05 path (operands rounded to bf16, fp32 accumulation in TMEM).
+    // Preferred: operands packed to TMA-addressable bf16 and fed by the TMA unit (gemm_tma.cu); the software-staged
+    // kernel takes what that launcher declines (no scratch, odd shapes).
+    static const bool no_tma = getenv("BB200_NO_TMA") != nullptr;
+    if (!no_tma) {
+      TmaView a[2], b[2];
+      for (int p = 0; p < npairs; ++p) {
+        a[p] = TmaView{L[p].p, L[p].dt, L[p].rs, L[p].cs};
+        b[p] = TmaView{R[p].p, R[p].dt, R[p].cs, R[p].rs};   // rows of the B view = n
+      }
+      const int rc = bb_gemm_tma_run(M, N, K, npairs, a, b, out, ors, ocs, beta, bias, bias_stride,
+                                     dense_block(M, N, 1, ors, ocs, 0), s);
+      if (rc != BB_DECLINED) return rc;
+    }
     TcGemmArgs G{};
     G.M = M; G.N = N; G.K = K; G.npairs = npairs;
     for (int p = 0; p < npairs; ++p) {

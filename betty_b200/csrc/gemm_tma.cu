@@ -1,0 +1,511 @@
+// K5/K6 tensor-core path, TMA-fed: dual-product GEMM and stride-1 convolution (forward / input-gradient form) on
+// tcgen05.mma with operands brought into shared memory by the TMA unit.
+//
+//   D[m][n] (beta/atomic)= sum over up to two operand pairs p of  sum_k A_p[m][k] * B_p[n][k]   (+ bias[n])
+//
+// The software-staged kernel in gemm_tc.cu spends >95 % of its time in the producer warps (address arithmetic,
+// 4-byte gathers, bf16 conversion, swizzled stores; ncu: tensor pipe ~1 %).  Here every operand is first made
+// TMA-addressable -- bf16, unit stride along one matrix dimension, 16-byte aligned rows; base activations and
+// autocast weight copies already are, tangents / adjoints (fp32 arena slices) go through a streaming pack kernel --
+// and one elected thread issues cp.async.bulk.tensor loads that land in the SWIZZLE_128B layout the UMMA
+// descriptors read:
+//   K-major operand  (k contiguous in memory): one box of 64 k x ROWS rows      -> rows of 128 B
+//   MN-major operand (m/n contiguous):         ROWS/64 boxes of 64 mn x 64 k    -> 8x64 atoms, SBO 1024 B, LBO 8 KB
+//   convolution A    (NHWC bf16 activations):  one 4-D box 64 ch x Wb x Hb x 1 per (tap, channel block); the
+//                    window displacement is a coordinate offset, zero padding is TMA out-of-bounds fill
+// so transposed views cost nothing and an implicit-GEMM convolution is nine shifted box loads per 64 channels.
+//
+// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM alloc + MMA issue (one lane), warps 2-5 =
+// epilogue (tcgen05.ld 32 lanes x 32 columns, warp w owns TMEM lanes 32*(w%4)..).  3-4 stage mbarrier ring; two
+// CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/betty_b200.h"
+#include "bb_common.cuh"
+#include "gemm_tma.h"
+#include "plan.h"
+#include "tc_ptx.cuh"
+#include "tma.h"
+
+thread_local BbScratch bb_scratch = {nullptr, 0, 0};
+
+namespace {
+
+using namespace bbtc;
+
+constexpr int BM = 128, BK = 64;
+constexpr int NTHREADS = 192;
+constexpr int A_TILE = BM * BK * 2;   // 16 KB
+
+template <int BN_>
+struct Cfg {
+  static constexpr int kStages = BN_ == 64 ? 4 : 3;
+  static constexpr int kBTile = BN_ * BK * 2;
+  static constexpr int kStage = A_TILE + kBTile;
+  static constexpr size_t kSmem = (size_t)kStages * kStage + 1024 + 256;
+};
+
+template <int BN_>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_constant__ TmaGemmArgs G) {
+  using C = Cfg<BN_>;
+  constexpr int STAGES = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStage);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN_;
+  const int split = blockIdx.z;
+  const int64_t kblocks_total = (G.K + BK - 1) / BK;
+  const int64_t kb_per = (kblocks_total + G.ksplit - 1) / G.ksplit;
+  const int64_t kb_beg = (int64_t)split * kb_per;
+  int64_t kb_end = kb_beg + kb_per;
+  if (kb_end > kblocks_total) kb_end = kblocks_total;
+  const int nkb = (int)(kb_end > kb_beg ? kb_end - kb_beg : 0);
+  const int total_kb = nkb * G.npairs;
+
+  const bool conv = G.a_kind[0] == TMA_CONV;
+  int m0 = 0, img = 0, h0 = 0;
+  if (conv) {
+    img = blockIdx.y / G.tiles_per_img;
+    h0 = (blockIdx.y - img * G.tiles_per_img) * G.Hb;
+  } else {
+    m0 = blockIdx.y * BM;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)BN_);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int p = 0; p < G.npairs; ++p) {
+        tma_prefetch_desc(&G.a[p]);
+        tma_prefetch_desc(&G.b[p]);
+      }
+      for (int it = 0; it < total_kb; ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+        const int pair = it / nkb;
+        const int kb = (int)kb_beg + (it - pair * nkb);
+        const int k0 = kb * BK;
+        const uint32_t bar = full0 + 8 * s;
+        const uint32_t sa = smem_u32(smem + s * C::kStage), sb = sa + A_TILE;
+        mbar_expect_tx(bar, G.a_bytes + G.b_bytes);
+        const int ak = G.a_kind[pair];
+        if (ak == TMA_KMAJ) {
+          tma_load_2d(sa, &G.a[pair], bar, k0, m0);
+        } else if (ak == TMA_MNMAJ) {
+          tma_load_2d(sa, &G.a[pair], bar, m0, k0);
+          tma_load_2d(sa + 8192, &G.a[pair], bar, m0 + 64, k0);
+        } else {
+          const int tap = kb / G.cblocks, cb = kb - tap * G.cblocks;
+          const int i = tap / G.KW, j = tap - i * G.KW;
+          const int dy = G.flip ? G.ph - i : i - G.ph, dx = G.flip ? G.pw - j : j - G.pw;
+          tma_load_4d(sa, &G.a[pair], bar, cb * 64, dx, h0 + dy, img);
+        }
+        if (G.b_kind[pair] == TMA_KMAJ) {
+          tma_load_2d(sb, &G.b[pair], bar, k0, n0);
+        } else {
+#pragma unroll
+          for (int q = 0; q < BN_ / 64; ++q) tma_load_2d(sb + q * 8192, &G.b[pair], bar, n0 + q * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      for (int it = 0; it < total_kb; ++it) {
+        const int s = it % STAGES;
+        const int pair = it / nkb;
+        const bool a_mn = G.a_kind[pair] == TMA_MNMAJ, b_mn = G.b_kind[pair] == TMA_MNMAJ;
+        const uint32_t idesc = idesc_bf16(BM, BN_, a_mn, b_mn);
+        mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * C::kStage), b_addr = a_addr + A_TILE;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = a_mn ? desc_mn(a_addr + k * 2048, 8192) : desc_k(a_addr + k * 32);
+          const uint64_t db = b_mn ? desc_mn(b_addr + k * 2048, 8192) : desc_k(b_addr + k * 32);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);
+      }
+      if (total_kb > 0) umma_commit(accum);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    if (total_kb > 0) {
+      mbar_wait(accum, 0, 100);
+      tc_fence_after();
+    }
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    bool row_ok;
+    int64_t row_base, col_stride;
+    if (G.omode == 1) {
+      const int64_t q = (int64_t)h0 * G.Wb + r;   // Wb == output width
+      row_ok = r < G.Wb * G.Hb && q < G.OHW;
+      row_base = (int64_t)img * G.OCH * G.OHW + q;
+      col_stride = G.OHW;
+    } else {
+      const int64_t row = (int64_t)m0 + r;
+      row_ok = row < G.M;
+      row_base = row * G.ors;
+      col_stride = G.ocs;
+    }
+    const bool vec = G.omode == 0 && G.ocs == 1 && G.ksplit == 1 && (G.ors & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(G.out) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN_ / 32; ++c) {
+      uint32_t v[32];
+      if (total_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (!row_ok) continue;
+      const int col0 = n0 + c * 32;
+      if (col0 >= G.N) continue;
+      if (G.bias != nullptr && split == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < G.N) v[j] = __float_as_uint(__uint_as_float(v[j]) + G.bias[(int64_t)(col0 + j) * G.bias_stride]);
+      }
+      float* dst = G.out + row_base + (int64_t)col0 * col_stride;
+      if (vec && col0 + 32 <= G.N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          float4* q = reinterpret_cast<float4*>(dst + j);
+          if (G.beta) {
+            const float4 old = *q;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *q = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + j < G.N) {
+            float* q = dst + (int64_t)j * col_stride;
+            const float o = __uint_as_float(v[j]);
+            if (G.ksplit > 1) atomicAdd(q, o);
+            else *q = G.beta ? *q + o : o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)BN_);
+  }
+}
+
+template <int BN_>
+int launch_tma(const TmaGemmArgs& G, int64_t mtiles, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tma_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN_>::kSmem));
+    configured = true;
+  }
+  dim3 grid((unsigned)((G.N + BN_ - 1) / BN_), (unsigned)mtiles, (unsigned)G.ksplit);
+  gemm_tma_kernel<BN_><<<grid, NTHREADS, Cfg<BN_>::kSmem, s>>>(G);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+std::mutex g_map_mu;
+std::unordered_map<std::string, CUtensorMap> g_maps;
+
+int encode_cached(CUtensorMap* out, int rank, const void* p, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box) {
+  std::string key(reinterpret_cast<const char*>(&p), sizeof(p));
+  key.append(reinterpret_cast<const char*>(dims), sizeof(cuuint64_t) * rank);
+  key.append(reinterpret_cast<const char*>(strides), sizeof(cuuint64_t) * (rank - 1));
+  key.append(reinterpret_cast<const char*>(box), sizeof(cuuint32_t) * rank);
+  std::lock_guard<std::mutex> lock(g_map_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return BB_OK;
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return BB_ERR_UNSUPPORTED;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  alignas(64) CUtensorMap m;
+  const CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(p), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return BB_ERR_ARG;
+  if (g_maps.size() > 65536) g_maps.clear();
+  g_maps.emplace(std::move(key), m);
+  *out = m;
+  return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// one thread = 8 consecutive destination elements (16 bytes)
+template <bool VEC>
+__global__ void __launch_bounds__(256) pack2d_kernel(const void* __restrict__ src, int dt, int64_t os, int64_t is,
+                                                     int64_t outer, int64_t inner, uint4* __restrict__ dst, int64_t dp8) {
+  const int64_t total = outer * dp8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = t / dp8, i0 = (t - o * dp8) * 8;
+    float v[8];
+    if (VEC) {   // fp32, is == 1, rows 16-byte aligned, inner % 8 == 0
+      const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + o * os + i0);
+      const float4 a = bb::ld4_stream(reinterpret_cast<const float*>(q)), b = bb::ld4_stream(reinterpret_cast<const float*>(q + 1));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (i0 + e < inner) ? bb::ldf(src, o * os + (i0 + e) * is, dt) : 0.f;
+    }
+    uint4 out;
+    out.x = pack_bf16(v[0], v[1]); out.y = pack_bf16(v[2], v[3]); out.z = pack_bf16(v[4], v[5]); out.w = pack_bf16(v[6], v[7]);
+    dst[t] = out;
+  }
+}
+
+// NCHW -> NHWC bf16: block = 64 channels x 64 pixels of one image through shared memory
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const void* __restrict__ src, int dt, int C, int HW,
+                                                        __nv_bfloat16* __restrict__ dst, int Cp) {
+  __shared__ float tile[64][65];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+  const int64_t sbase = (int64_t)img * C * HW;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int c = c0 + ty + k * 4, p = p0 + tx;
+    tile[ty + k * 4][tx] = (c < C && p < HW) ? bb::ldf(src, sbase + (int64_t)c * HW + p, dt) : 0.f;
+  }
+  __syncthreads();
+  // write: 32 threads cover 64 channels (2 each) of one pixel; 8 pixels per pass
+  const int cx = (threadIdx.x & 31) * 2, py = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int pl = py + k * 8, p = p0 + pl;
+    if (p < HW) {
+      const uint32_t w = pack_bf16(tile[cx][pl], tile[cx + 1][pl]);
+      *reinterpret_cast<uint32_t*>(dst + ((int64_t)img * HW + p) * Cp + c0 + cx) = w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_convw_kernel(const void* __restrict__ src, int dt, int O, int C, int taps,
+                                                         int transpose, __nv_bfloat16* __restrict__ dst, int Qp) {
+  const int R = transpose ? C : O, Q = transpose ? O : C;
+  const int64_t total = (int64_t)R * taps * Qp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(t % Qp);
+    const int64_t rt = t / Qp;
+    const int tap = (int)(rt % taps), r = (int)(rt / taps);
+    float v = 0.f;
+    if (q < Q) {
+      const int o = transpose ? q : r, c = transpose ? r : q;
+      v = bb::ldf(src, ((int64_t)o * C + c) * taps + tap, dt);
+    }
+    dst[t] = __float2bfloat16(v);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
+
+// Make one operand view TMA-addressable.  On return *mat/*pitch describe a bf16 row-major matrix whose rows are the
+// view's rows (kind TMA_KMAJ, pitch >= K) or the view's k (kind TMA_MNMAJ, pitch >= R).
+int prepare_operand(const TmaView& v, int64_t R, int64_t K, const void** mat, int64_t* pitch, int* kind, cudaStream_t s) {
+  if (v.cs == 1 || v.rs != 1) {
+    // K-major (or neither stride unit: gathered into K-major)
+    *kind = TMA_KMAJ;
+    if (v.cs == 1 && v.dt == BB_BF16 && v.rs % 8 == 0 && v.rs >= K && aligned16(v.p)) {
+      *mat = v.p; *pitch = v.rs;
+      return BB_OK;
+    }
+    const int64_t dp = round8(K);
+    void* d = bb_scratch_alloc((size_t)R * dp * 2);
+    if (!d) return BB_DECLINED;
+    *mat = d; *pitch = dp;
+    return bb_pack2d(v.p, v.dt, v.rs, v.cs, R, K, d, dp, s);
+  }
+  *kind = TMA_MNMAJ;
+  if (v.dt == BB_BF16 && v.cs % 8 == 0 && v.cs >= R && aligned16(v.p)) {
+    *mat = v.p; *pitch = v.cs;
+    return BB_OK;
+  }
+  const int64_t dp = round8(R);
+  void* d = bb_scratch_alloc((size_t)K * dp * 2);
+  if (!d) return BB_DECLINED;
+  *mat = d; *pitch = dp;
+  return bb_pack2d(v.p, v.dt, v.cs, 1, K, R, d, dp, s);
+}
+
+}  // namespace
+
+int bb_tma_map_2d(CUtensorMap* out, const void* p, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  return encode_cached(out, 2, p, dims, strides, box);
+}
+
+int bb_tma_map_nhwc(CUtensorMap* out, const void* p, int N, int H, int W, int Cp, int bw, int bh) {
+  const cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+  const cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, 1u};
+  return encode_cached(out, 4, p, dims, strides, box);
+}
+
+int bb_pack2d(const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner, void* dst, int64_t dp,
+              cudaStream_t s) {
+  if (outer <= 0 || inner <= 0) return BB_OK;
+  const int64_t dp8 = dp / 8, total = outer * dp8;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 8 * BB_SM_COUNT) blocks = 8 * BB_SM_COUNT;
+  const bool vec = dt == BB_F32 && is == 1 && inner % 8 == 0 && dp == inner && os % 4 == 0 && aligned16(src);
+  if (vec) pack2d_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(src, dt, os, is, outer, inner, reinterpret_cast<uint4*>(dst), dp8);
+  else pack2d_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(src, dt, os, is, outer, inner, reinterpret_cast<uint4*>(dst), dp8);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_pack_nhwc(const void* src, int dt, int N, int C, int HW, void* dst, int Cp, cudaStream_t s) {
+  dim3 grid((unsigned)((HW + 63) / 64), (unsigned)(Cp / 64), (unsigned)N);
+  pack_nhwc_kernel<<<grid, 256, 0, s>>>(src, dt, C, HW, reinterpret_cast<__nv_bfloat16*>(dst), Cp);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_pack_convw(const void* src, int dt, int O, int C, int taps, int transpose, void* dst, int Qp, cudaStream_t s) {
+  const int64_t total = (int64_t)(transpose ? C : O) * taps * Qp;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 4 * BB_SM_COUNT) blocks = 4 * BB_SM_COUNT;
+  pack_convw_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dt, O, C, taps, transpose, reinterpret_cast<__nv_bfloat16*>(dst), Qp);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+int bb_gemm_tma_launch(TmaGemmArgs& G, int bn, int64_t mtiles, cudaStream_t s) {
+  return bn == 64 ? launch_tma<64>(G, mtiles, s) : launch_tma<128>(G, mtiles, s);
+}
+
+int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* A, const TmaView* B, float* out,
+                    int64_t ors, int64_t ocs, int beta, const float* bias, int64_t bias_stride, bool out_dense,
+                    cudaStream_t s) {
+  if (npairs < 1 || npairs > 2 || M < 64 || N < 64 || K < 64) return BB_DECLINED;
+  if (M > INT32_MAX / 2 || N > INT32_MAX / 2 || K > INT32_MAX / 2) return BB_DECLINED;
+  if (encode_fn() == nullptr || bb_scratch.base == nullptr) return BB_DECLINED;
+  // scratch need, worst case (every operand packed, either layout); plan.py sizes the scratch with the same bound
+  {
+    const size_t need = (size_t)npairs * 2 * (size_t)((M + 8) * (K + 8) + (N + 8) * (K + 8)) + 4096;
+    if (need > bb_scratch.bytes) return BB_DECLINED;
+  }
+  bb_scratch_reset();
+  alignas(64) TmaGemmArgs G;
+  memset(&G, 0, sizeof(G));
+  const int bn = N <= 64 ? 64 : 128;
+  for (int p = 0; p < npairs; ++p) {
+    const void* mat;
+    int64_t pitch;
+    int kind, rc;
+    rc = prepare_operand(A[p], M, K, &mat, &pitch, &kind, s);
+    if (rc) return rc;
+    G.a_kind[p] = kind;
+    rc = kind == TMA_KMAJ ? bb_tma_map_2d(&G.a[p], mat, M, K, pitch, BM) : bb_tma_map_2d(&G.a[p], mat, K, M, pitch, 64);
+    if (rc) return rc;
+    rc = prepare_operand(B[p], N, K, &mat, &pitch, &kind, s);
+    if (rc) return rc;
+    G.b_kind[p] = kind;
+    rc = kind == TMA_KMAJ ? bb_tma_map_2d(&G.b[p], mat, N, K, pitch, bn) : bb_tma_map_2d(&G.b[p], mat, K, N, pitch, 64);
+    if (rc) return rc;
+  }
+  G.M = M; G.N = N; G.K = K; G.npairs = npairs;
+  G.a_bytes = A_TILE; G.b_bytes = (uint32_t)bn * BK * 2;
+  G.out = out; G.omode = 0; G.ors = ors; G.ocs = ocs; G.beta = beta; G.bias = bias; G.bias_stride = bias_stride;
+  const int64_t mtiles = (M + BM - 1) / BM;
+  const int64_t tiles = mtiles * ((N + bn - 1) / bn);
+  const int64_t kblocks = (K + BK - 1) / BK;
+  int ksplit = 1;
+  if (tiles < BB_SM_COUNT && kblocks >= 8) {
+    int64_t want = (2 * BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 4;
+    ksplit = (int)(want < maxs ? want : maxs);
+    if (ksplit > 32) ksplit = 32;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit > 1 && !beta) {
+    if (!out_dense) {
+      ksplit = 1;
+    } else {
+      BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * M * N, s));
+      bb_launch_tally += 1;
+    }
+  }
+  G.ksplit = ksplit;
+  return bb_gemm_tma_launch(G, bn, mtiles, s);
+}
+
+extern "C" int bb_gemm_bf16_tma(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs,
+                                const void* B, int dtB, int64_t brs, int64_t bcs, float* C, int64_t crs, int64_t ccs,
+                                int beta, void* scratch, int64_t scratch_bytes, void* stream) {
+  const BbScratch saved = bb_scratch;
+  bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(scratch), (size_t)scratch_bytes, 0};
+  const TmaView a{A, dtA, ars, acs}, b{B, dtB, bcs, brs};   // rows of the B view = n
+  const bool dense = (ccs == 1 && crs == N) || (crs == 1 && ccs == M);
+  const int rc = bb_gemm_tma_run(M, N, K, 1, &a, &b, C, crs, ccs, beta, nullptr, 0, dense, (cudaStream_t)stream);
+  bb_scratch = saved;
+  return rc;
+}

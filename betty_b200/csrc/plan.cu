@@ -7,12 +7,15 @@
 #include "../../include/betty_b200.h"
 #include "bb_common.cuh"
 #include "plan.h"
+#include "tma.h"
 
 struct bb_plan {
   std::vector<bb_node> nodes;
   std::vector<void*> zero_ptr[3];
   std::vector<int64_t> zero_bytes[3];
   int launches[3] = {0, 0, 0};
+  void* scratch = nullptr;      // bf16 operand packs of the TMA-fed tensor-core path (tma.h)
+  int64_t scratch_bytes = 0;
 };
 
 namespace {
@@ -61,6 +64,7 @@ int dispatch(const bb_node& nd, int pass, cudaStream_t s) {
 
 int run_pass(bb_plan* p, int pass, cudaStream_t s) {
   if (pass < 0 || pass > 2) return BB_ERR_ARG;
+  bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(p->scratch), (size_t)p->scratch_bytes, 0};
   const int tally0 = bb_launch_tally;
   for (size_t i = 0; i < p->zero_ptr[pass].size(); ++i) {
     BB_CUDA_TRY(cudaMemsetAsync(p->zero_ptr[pass][i], 0, (size_t)p->zero_bytes[pass][i], s));
@@ -146,6 +150,13 @@ int bb_plan_set_zero_regions(bb_plan* plan, int pass, void* const* ptrs, const i
   return BB_OK;
 }
 
+int bb_plan_set_scratch(bb_plan* plan, void* ptr, int64_t bytes) {
+  if (!plan || bytes < 0) return BB_ERR_ARG;
+  plan->scratch = ptr;
+  plan->scratch_bytes = bytes;
+  return BB_OK;
+}
+
 int bb_plan_run(bb_plan* plan, int pass, void* stream) {
   if (!plan) return BB_ERR_ARG;
   return run_pass(plan, pass, (cudaStream_t)stream);
@@ -166,6 +177,7 @@ int bb_plan_hvp(bb_plan* plan, void* stream) {
 int bb_plan_profile(bb_plan* plan, int pass, float* ms_per_node, void* stream) {
   if (!plan || pass < 0 || pass > 2 || !ms_per_node) return BB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(plan->scratch), (size_t)plan->scratch_bytes, 0};
   const int n = (int)plan->nodes.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) BB_CUDA_TRY(cudaEventCreate(&e));

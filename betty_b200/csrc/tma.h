@@ -1,0 +1,31 @@
+// Host-side helpers of the TMA-fed tensor-core path (gemm_tma.cu, conv_tma.cu): tensor-map encoding through the
+// driver entry point (no link-time dependency on libcuda), a cache of encoded maps, and the per-plan scratch the
+// bf16 operand packs are written to.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// Scratch for packed (bf16, TMA-addressable) copies of operands.  Owned by the caller of the plan (Python allocates
+// it once per plan, bb_plan_set_scratch); the executor publishes it here for the node launchers.  Every launcher
+// bump-allocates from offset 0: launches on one stream are ordered, so the previous node's packs are dead.
+struct BbScratch {
+  uint8_t* base;
+  size_t bytes;
+  size_t used;
+};
+extern thread_local BbScratch bb_scratch;
+
+inline void bb_scratch_reset() { bb_scratch.used = 0; }
+inline void* bb_scratch_alloc(size_t bytes) {
+  const size_t at = (bb_scratch.used + 255) & ~(size_t)255;
+  if (bb_scratch.base == nullptr || at + bytes > bb_scratch.bytes) return nullptr;
+  bb_scratch.used = at + bytes;
+  return bb_scratch.base + at;
+}
+
+// bf16 row-major matrix [rows][cols], `pitch` elements between rows (multiple of 8, base 16-byte aligned):
+// box = (64 columns, box_rows rows), SWIZZLE_128B.  Returns 0 or an error code.
+int bb_tma_map_2d(CUtensorMap* out, const void* p, int64_t rows, int64_t cols, int64_t pitch, int box_rows);
+// bf16 NHWC tensor [N][H][W][Cp] (Cp multiple of 64): box = (64 channels, bw, bh, 1), SWIZZLE_128B.
+int bb_tma_map_nhwc(CUtensorMap* out, const void* p, int N, int H, int W, int Cp, int bw, int bh);

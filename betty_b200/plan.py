@@ -58,6 +58,7 @@ class HvpPlan:
         self.layout, self.d_arena, self.hv_arena = layout, d_arena, hv_arena
         self.use_graph = settings.cuda_graph if cuda_graph is None else cuda_graph
         self.tape = tape                      # keeps the base activations alive
+        self.dry_run = dry_run
         self.g: Graph = lower_tape(tape)
         self._keep: List[torch.Tensor] = []   # constants / scratch referenced by raw pointer
         self._alloc_buffers()
@@ -162,11 +163,39 @@ class HvpPlan:
             nb = (C.c_int64 * len(ts))(*[t.numel() * t.element_size() for t in ts])
             return ptrs, nb, len(ts)
 
+        # scratch of the TMA-fed tensor-core kernels (bf16 operand packs; csrc/gemm_tma.cu, conv_tma.cu): the largest
+        # single node's need, since packs never outlive their node
+        need = max([self._tma_scratch_bytes(r) for r in recs] + [0])
+        if need and not self.dry_run:
+            self.tma_scratch = torch.empty(need, dtype=torch.uint8, device=self.dev)
+            N.call("bb_plan_set_scratch", self.handle, self.tma_scratch.data_ptr(), need)
+
         zb = [self.A["z"]] if self.zero_bytes else []
         zt = ([self.AT["z"]] if self.zero_bytes else []) + [self.hv_arena]
         for pas, ts in ((PASS_BB, zb), (PASS_TF, []), (PASS_TB, zt)):
             ptrs, nb, cnt = regions(ts)
             N.call("bb_plan_set_zero_regions", self.handle, pas, ptrs, nb, cnt)
+
+    @staticmethod
+    def _tma_scratch_bytes(r) -> int:
+        """Upper bound of the bf16 pack bytes one node's launch needs (mirrors the checks in gemm_tma.cu / conv_tma.cu)."""
+        if not (int(r["kind"]) & 1):
+            return 0
+        if int(r["op"]) == OPS["gemm"]:
+            M, Nn, K, batch = (int(x) for x in r["dims"][0:4])
+            if batch != 1:
+                return 0
+            pad = lambda a, b: (a + 8) * (b + 8)
+            return 2 * 2 * max(pad(M, K) + pad(Nn, K), pad(M, Nn) + pad(K, Nn), pad(K, M) + pad(Nn, M)) + 8192
+        if int(r["op"]) == OPS["conv2d"]:
+            Nn, Cc, H, W, O, KH, KW, HO, WO = (int(x) for x in r["dims"][0:9])
+            unit = all(int(x) == 1 for x in (r["dims"][9], r["dims"][10], r["dims"][13], r["dims"][14]))
+            if not (unit and KH * KW <= 9 and 32 <= Cc <= 64 and 32 <= O <= 64 and 4 <= WO <= 64 and W <= 128):
+                return 0          # bb_conv_tma_ok() declines: software-staged / SIMT kernels, no packs
+            cp, op = _align(Cc, 64), _align(O, 64)
+            acts = 2 * Nn * H * W * cp + 2 * Nn * HO * WO * op
+            return 2 * (acts + 4 * op * KH * KW * cp) + 16384
+        return 0
 
     # ---- per-op descriptor builders -----------------------------------------------------------
     def _ew_layout(self, r, out: Val, operands: List[Optional[torch.Tensor]]):

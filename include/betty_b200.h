@@ -79,6 +79,9 @@ int bb_node_bytes(void);
 int bb_plan_create(const struct bb_node* nodes, int n_nodes, bb_plan** out);
 int bb_plan_destroy(bb_plan* plan);
 int bb_plan_set_zero_regions(bb_plan* plan, int pass, void* const* ptrs, const int64_t* bytes, int n);
+/* device scratch for the bf16 operand packs of the TMA-fed tensor-core kernels (caller-owned, >= the largest
+ * node's need; without it those nodes use the software-staged kernel) */
+int bb_plan_set_scratch(bb_plan* plan, void* ptr, int64_t bytes);
 int bb_plan_run(bb_plan* plan, int pass, void* stream);
 int bb_plan_launch_count(const bb_plan* plan, int pass);
 /* eager run of one pass with a CUDA event pair around every node: ms_per_node[n_nodes] */
@@ -95,6 +98,12 @@ int bb_plan_cg_loop(bb_plan* plan, int iterations, float cg_alpha, float* x, flo
  *      fp32 accumulation in TMEM (tcgen05.mma).  A[m][k] = A[m*ars+k*acs], B[k][n] = B[k*brs+n*bcs]; dt: 0 f32, 1 bf16 */
 int bb_gemm_bf16_tc(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs, const void* B,
                     int dtB, int64_t brs, int64_t bcs, float* C, int64_t crs, int64_t ccs, int beta, void* stream);
+
+/* same contract, operands made TMA-addressable (bf16 packs written to `scratch`) and loaded by the TMA unit;
+ * returns 1 if the shape is declined (M, N or K < 64, scratch too small) */
+int bb_gemm_bf16_tma(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs, const void* B,
+                     int dtB, int64_t brs, int64_t bcs, float* C, int64_t crs, int64_t ccs, int beta, void* scratch,
+                     int64_t scratch_bytes, void* stream);
 
 const char* bb_version(void);
 
