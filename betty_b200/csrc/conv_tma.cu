@@ -191,11 +191,61 @@ int launch_corr(const Geo& g, int npairs, const void* const* src_nhwc, int SH, i
   return bb_gemm_tma_launch(G, bn, (int64_t)g.N * G.tiles_per_img, s);
 }
 
+// ---- first-layer convolutions (few input channels, input is data: no tangent, no input gradient) -------------------
+// With C*KH*KW <= 64 the reduction fits one k-block, so the im2col matrix is materialised once per pass as bf16
+// [pixels][k] (TMA-addressable, any stride / dilation) and both products are plain GEMMs on gemm_tma_kernel:
+//   TF  t_y[pixel][o]  = Xcol[pixel][k] . t_W[o][k]        (NCHW plane output)
+//   TB  at_W[o][k]     = sum_pixels at_y[pixel][o] * Xcol[pixel][k]      (both operands MN-major, split-K)
+bool small_c_ok(const bb_node& nd) {
+  const int64_t C = nd.dims[1], O = nd.dims[4], KH = nd.dims[5], KW = nd.dims[6];
+  if (nd.active & 1) return false;                    // t_x / at_x exist: not a data-input layer
+  if (!(nd.active & 2)) return false;
+  return C * KH * KW <= 64 && C * KH * KW >= 8 && O >= 32 && O <= 128 && nd.dims[0] * nd.dims[7] * nd.dims[8] >= 128;
+}
+
+size_t small_c_scratch(const bb_node& nd) {
+  const int64_t P = nd.dims[0] * nd.dims[7] * nd.dims[8], O = nd.dims[4];
+  const int64_t kp = (nd.dims[1] * nd.dims[5] * nd.dims[6] + 7) / 8 * 8, op = (O + 63) / 64 * 64;
+  return (size_t)(2 * P * kp + 2 * P * op + 2 * (O + 8) * (kp + 8) + 16384);
+}
+
+int run_small_c(const bb_node& nd, int pass, cudaStream_t s) {
+  Im2colGeom ig;
+  ig.N = (int)nd.dims[0]; ig.C = (int)nd.dims[1]; ig.H = (int)nd.dims[2]; ig.W = (int)nd.dims[3];
+  ig.KH = (int)nd.dims[5]; ig.KW = (int)nd.dims[6]; ig.HO = (int)nd.dims[7]; ig.WO = (int)nd.dims[8];
+  ig.sh = (int)nd.dims[9]; ig.sw = (int)nd.dims[10]; ig.ph = (int)nd.dims[11]; ig.pw = (int)nd.dims[12];
+  ig.dh = (int)nd.dims[13]; ig.dw = (int)nd.dims[14];
+  const int O = (int)nd.dims[4];
+  const int64_t CKK = (int64_t)ig.C * ig.KH * ig.KW, P = (int64_t)ig.N * ig.HO * ig.WO;
+  const int kp = (int)((CKK + 7) / 8 * 8), op = (O + 63) / 64 * 64;
+  if (small_c_scratch(nd) > bb_scratch.bytes) return BB_DECLINED;
+  bb_scratch_reset();
+  void* xcol = bb_scratch_alloc((size_t)P * kp * 2);
+  if (!xcol) return BB_DECLINED;
+  int rc = bb_pack_im2col(nd.base[0], nd.dt[0], ig, xcol, kp, s);
+  if (rc) return rc;
+  if (pass == BB_PASS_TAN_FWD) {
+    const TmaView a{xcol, BB_BF16, kp, 1};                 // rows = pixels
+    const TmaView b{nd.t[1], BB_F32, CKK, 1};              // rows = o
+    return bb_gemm_tma_run(P, O, CKK, 1, &a, &b, reinterpret_cast<float*>(nd.t[3]), 0, 0, 0,
+                           (nd.active & 4) ? reinterpret_cast<const float*>(nd.t[2]) : nullptr, 1, false, s,
+                           ig.HO * ig.WO, 32);
+  }
+  void* gy = bb_scratch_alloc((size_t)P * op * 2);
+  if (!gy) return BB_DECLINED;
+  if ((rc = bb_pack_nhwc(nd.at[3], BB_F32, ig.N, O, ig.HO * ig.WO, gy, op, s))) return rc;
+  const TmaView a{gy, BB_BF16, 1, op};                     // rows = o, k = pixel
+  const TmaView b{xcol, BB_BF16, 1, kp};                   // rows = k of the window, k = pixel
+  return bb_gemm_tma_run(O, CKK, P, 1, &a, &b, reinterpret_cast<float*>(nd.at[1]), CKK, 1, nd.beta[1], nullptr, 0, true, s,
+                         0, 8);
+}
+
 }  // namespace
 
 bool bb_conv_tma_ok(const bb_node& nd, int pass) {
   static const bool off = getenv("BB200_NO_TMA") != nullptr || getenv("BB200_NO_TC") != nullptr;
   if (off || !(nd.kind & 1) || bb_scratch.base == nullptr || pass == BB_PASS_BASE_BWD) return false;
+  if (small_c_ok(nd)) return true;
   const int C = (int)nd.dims[1], H = (int)nd.dims[2], W = (int)nd.dims[3], O = (int)nd.dims[4];
   const int KH = (int)nd.dims[5], KW = (int)nd.dims[6], HO = (int)nd.dims[7], WO = (int)nd.dims[8];
   if (nd.dims[9] != 1 || nd.dims[10] != 1 || nd.dims[13] != 1 || nd.dims[14] != 1) return false;
@@ -207,12 +257,14 @@ bool bb_conv_tma_ok(const bb_node& nd, int pass) {
 }
 
 size_t bb_conv_tma_scratch(const bb_node& nd) {
+  if (small_c_ok(nd)) return small_c_scratch(nd);
   const int64_t N = nd.dims[0], H = nd.dims[2], W = nd.dims[3], KH = nd.dims[5], KW = nd.dims[6], HO = nd.dims[7],
                 WO = nd.dims[8];
   return (size_t)(2 * (2 * N * H * W * 64 + 2 * N * HO * WO * 64) + 2 * 4 * 64 * KH * KW * 64 + 16384);
 }
 
 int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
+  if (small_c_ok(nd)) return run_small_c(nd, pass, s);
   Geo g;
   g.N = (int)nd.dims[0]; g.C = (int)nd.dims[1]; g.H = (int)nd.dims[2]; g.W = (int)nd.dims[3]; g.O = (int)nd.dims[4];
   g.KH = (int)nd.dims[5]; g.KW = (int)nd.dims[6]; g.HO = (int)nd.dims[7]; g.WO = (int)nd.dims[8];

@@ -12,6 +12,7 @@
 #include "../../include/betty_b200.h"
 #include "gemm_tc.h"
 #include "gemm_tma.h"
+#include "tma.h"
 #include "plan.h"
 #include "tile_gemm.cuh"
 
@@ -209,6 +210,7 @@ int bb_launch_gemm(const bb_node& nd, int pass, cudaStream_t s) {
   const Mat tB{nd.t[1], BB_F32, sb[0], sb[1], sb[2]};
   int rc;
   const bool tc = (nd.kind & 1) && !getenv("BB200_NO_TC");   // set by plan.py for bf16-autocast graphs
+  bb_scratch_reset();   // operand packs of the TMA-fed path live for one node
   if (pass == BB_PASS_TAN_FWD) {
     Mat L[2], R[2];
     int np = 0;

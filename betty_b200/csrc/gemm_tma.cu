@@ -34,6 +34,7 @@
 #include "tma.h"
 
 thread_local BbScratch bb_scratch = {nullptr, 0, 0};
+thread_local uint64_t bb_scratch_gen = 0;
 
 namespace {
 
@@ -168,6 +169,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
       row_ok = r < G.Wb * G.Hb && q < G.OHW;
       row_base = (int64_t)img * G.OCH * G.OHW + q;
       col_stride = G.OHW;
+    } else if (G.omode == 2) {
+      const int64_t row = (int64_t)m0 + r;
+      row_ok = row < G.M;
+      const int64_t im = row / G.OHW;
+      row_base = im * G.OCH * G.OHW + (row - im * G.OHW);
+      col_stride = G.OHW;
     } else {
       const int64_t row = (int64_t)m0 + r;
       row_ok = row < G.M;
@@ -296,25 +303,37 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// one thread = 8 consecutive destination elements (16 bytes)
-template <bool VEC>
-__global__ void __launch_bounds__(256) pack2d_kernel(const void* __restrict__ src, int dt, int64_t os, int64_t is,
-                                                     int64_t outer, int64_t inner, uint4* __restrict__ dst, int64_t dp8) {
-  const int64_t total = outer * dp8;
+// dst[o][i] = bf16(src[o*os + i*is]); one thread = 8 consecutive destination elements (16 bytes).  Up to four
+// operands per launch (blockIdx.y = job): a dual product needs at most four packs, and launches -- not bytes -- are
+// what a 1 us pack costs.
+struct PackJob {
+  const void* src;
+  uint4* dst;
+  int64_t os, is, outer, inner, dp8;
+  int dt, vec;   // vec: fp32, is == 1, rows 16-byte aligned, inner % 8 == 0, dp == inner
+};
+struct PackJobs {
+  PackJob j[4];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) pack2d_kernel(const __grid_constant__ PackJobs J) {
+  const PackJob& q = J.j[blockIdx.y];
+  const int64_t total = q.outer * q.dp8;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = t / dp8, i0 = (t - o * dp8) * 8;
+    const int64_t o = t / q.dp8, i0 = (t - o * q.dp8) * 8;
     float v[8];
-    if (VEC) {   // fp32, is == 1, rows 16-byte aligned, inner % 8 == 0
-      const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + o * os + i0);
-      const float4 a = bb::ld4_stream(reinterpret_cast<const float*>(q)), b = bb::ld4_stream(reinterpret_cast<const float*>(q + 1));
+    if (q.vec) {
+      const float* f = reinterpret_cast<const float*>(q.src) + o * q.os + i0;
+      const float4 a = bb::ld4_stream(f), b = bb::ld4_stream(f + 4);
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (i0 + e < inner) ? bb::ldf(src, o * os + (i0 + e) * is, dt) : 0.f;
+      for (int e = 0; e < 8; ++e) v[e] = (i0 + e < q.inner) ? bb::ldf(q.src, o * q.os + (i0 + e) * q.is, q.dt) : 0.f;
     }
     uint4 out;
     out.x = pack_bf16(v[0], v[1]); out.y = pack_bf16(v[2], v[3]); out.z = pack_bf16(v[4], v[5]); out.w = pack_bf16(v[6], v[7]);
-    dst[t] = out;
+    q.dst[t] = out;
   }
 }
 
@@ -360,35 +379,131 @@ __global__ void __launch_bounds__(256) pack_convw_kernel(const void* __restrict_
   }
 }
 
+// im2col: one thread = one pixel x 8 consecutive k
+__global__ void __launch_bounds__(256) pack_im2col_kernel(const void* __restrict__ src, int dt, const Im2colGeom g,
+                                                          uint4* __restrict__ dst, int kp8) {
+  const int64_t P = (int64_t)g.N * g.HO * g.WO, total = P * kp8;
+  const int KK = g.KH * g.KW, CKK = g.C * KK;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = t / kp8;
+    const int k0 = (int)(t - pix * kp8) * 8;
+    const int hw = g.HO * g.WO;
+    const int img = (int)(pix / hw), q = (int)(pix - (int64_t)img * hw), y = q / g.WO, x = q - y * g.WO;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      float val = 0.f;
+      if (k < CKK) {
+        const int c = k / KK, r = k - c * KK, i = r / g.KW, j = r - i * g.KW;
+        const int h = y * g.sh - g.ph + i * g.dh, w = x * g.sw - g.pw + j * g.dw;
+        if ((unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W)
+          val = bb::ldf(src, (((int64_t)img * g.C + c) * g.H + h) * g.W + w, dt);
+      }
+      v[e] = val;
+    }
+    uint4 out;
+    out.x = pack_bf16(v[0], v[1]); out.y = pack_bf16(v[2], v[3]); out.z = pack_bf16(v[4], v[5]); out.w = pack_bf16(v[6], v[7]);
+    dst[t] = out;
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
 
+// Packs already written to the scratch since the last bb_scratch_reset() (= by earlier launches of the same node):
+// the output adjoints of a Linear feed both its input-gradient and its weight-gradient products, and a K-major view
+// and its transposed MN-major view are the same bytes.
+struct PackKey {
+  const void* src;
+  int64_t os, is, outer, inner;
+  int dt;
+  void* dst;
+};
+thread_local PackKey t_cache[16];
+thread_local int t_ncache = 0;
+thread_local uint64_t t_cache_gen = 0;   // bb_scratch_gen the entries belong to
+
+void* cached_pack(const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner) {
+  if (t_cache_gen != bb_scratch_gen) {   // scratch was reset since
+    t_ncache = 0;
+    t_cache_gen = bb_scratch_gen;
+  }
+  for (int i = 0; i < t_ncache; ++i) {
+    const PackKey& k = t_cache[i];
+    if (k.src == src && k.dt == dt && k.os == os && k.is == is && k.outer == outer && k.inner == inner) return k.dst;
+  }
+  return nullptr;
+}
+
+int queue_pack(PackJobs& J, const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner, void** dst,
+               int64_t* dp) {
+  *dp = round8(inner);
+  if (void* hit = cached_pack(src, dt, os, is, outer, inner)) {
+    *dst = hit;
+    return BB_OK;
+  }
+  void* d = bb_scratch_alloc((size_t)outer * *dp * 2);
+  if (!d || J.n >= 4) return BB_DECLINED;
+  PackJob& q = J.j[J.n++];
+  q.src = src; q.dst = reinterpret_cast<uint4*>(d); q.os = os; q.is = is; q.outer = outer; q.inner = inner;
+  q.dp8 = *dp / 8; q.dt = dt;
+  q.vec = (dt == BB_F32 && is == 1 && inner % 8 == 0 && os % 4 == 0 && aligned16(src)) ? 1 : 0;
+  if (t_ncache < 16) t_cache[t_ncache++] = PackKey{src, os, is, outer, inner, dt, d};
+  *dst = d;
+  return BB_OK;
+}
+
+int flush_packs(const PackJobs& J, cudaStream_t s) {
+  if (J.n == 0) return BB_OK;
+  int64_t most = 0;
+  for (int i = 0; i < J.n; ++i) {
+    const int64_t t = J.j[i].outer * J.j[i].dp8;
+    if (t > most) most = t;
+  }
+  int64_t blocks = (most + 255) / 256;
+  if (blocks > 8 * BB_SM_COUNT) blocks = 8 * BB_SM_COUNT;
+  if (blocks < 1) blocks = 1;
+  pack2d_kernel<<<dim3((unsigned)blocks, (unsigned)J.n), 256, 0, s>>>(J);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+inline bool direct_k(const TmaView& v, int64_t K) {
+  return v.cs == 1 && v.dt == BB_BF16 && v.rs % 8 == 0 && v.rs >= K && aligned16(v.p);
+}
+inline bool direct_mn(const TmaView& v, int64_t R) {
+  return v.rs == 1 && v.cs != 1 && v.dt == BB_BF16 && v.cs % 8 == 0 && v.cs >= R && aligned16(v.p);
+}
+size_t pack_bytes(const TmaView& v, int64_t R, int64_t K) {
+  if (v.cs == 1 || v.rs != 1) return direct_k(v, K) ? 0 : (size_t)R * round8(K) * 2;
+  return direct_mn(v, R) ? 0 : (size_t)K * round8(R) * 2;
+}
+
 // Make one operand view TMA-addressable.  On return *mat/*pitch describe a bf16 row-major matrix whose rows are the
-// view's rows (kind TMA_KMAJ, pitch >= K) or the view's k (kind TMA_MNMAJ, pitch >= R).
-int prepare_operand(const TmaView& v, int64_t R, int64_t K, const void** mat, int64_t* pitch, int* kind, cudaStream_t s) {
+// view's rows (kind TMA_KMAJ, pitch >= K) or the view's k (kind TMA_MNMAJ, pitch >= R); packs are queued in J.
+int prepare_operand(PackJobs& J, const TmaView& v, int64_t R, int64_t K, const void** mat, int64_t* pitch, int* kind) {
+  void* d = nullptr;
   if (v.cs == 1 || v.rs != 1) {
     // K-major (or neither stride unit: gathered into K-major)
     *kind = TMA_KMAJ;
-    if (v.cs == 1 && v.dt == BB_BF16 && v.rs % 8 == 0 && v.rs >= K && aligned16(v.p)) {
+    if (direct_k(v, K)) {
       *mat = v.p; *pitch = v.rs;
       return BB_OK;
     }
-    const int64_t dp = round8(K);
-    void* d = bb_scratch_alloc((size_t)R * dp * 2);
-    if (!d) return BB_DECLINED;
-    *mat = d; *pitch = dp;
-    return bb_pack2d(v.p, v.dt, v.rs, v.cs, R, K, d, dp, s);
+    const int rc = queue_pack(J, v.p, v.dt, v.rs, v.cs, R, K, &d, pitch);
+    *mat = d;
+    return rc;
   }
   *kind = TMA_MNMAJ;
-  if (v.dt == BB_BF16 && v.cs % 8 == 0 && v.cs >= R && aligned16(v.p)) {
+  if (direct_mn(v, R)) {
     *mat = v.p; *pitch = v.cs;
     return BB_OK;
   }
-  const int64_t dp = round8(R);
-  void* d = bb_scratch_alloc((size_t)K * dp * 2);
-  if (!d) return BB_DECLINED;
-  *mat = d; *pitch = dp;
-  return bb_pack2d(v.p, v.dt, v.cs, 1, K, R, d, dp, s);
+  const int rc = queue_pack(J, v.p, v.dt, v.cs, 1, K, R, &d, pitch);
+  *mat = d;
+  return rc;
 }
 
 }  // namespace
@@ -410,15 +525,13 @@ int bb_tma_map_nhwc(CUtensorMap* out, const void* p, int N, int H, int W, int Cp
 int bb_pack2d(const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner, void* dst, int64_t dp,
               cudaStream_t s) {
   if (outer <= 0 || inner <= 0) return BB_OK;
-  const int64_t dp8 = dp / 8, total = outer * dp8;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 8 * BB_SM_COUNT) blocks = 8 * BB_SM_COUNT;
-  const bool vec = dt == BB_F32 && is == 1 && inner % 8 == 0 && dp == inner && os % 4 == 0 && aligned16(src);
-  if (vec) pack2d_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(src, dt, os, is, outer, inner, reinterpret_cast<uint4*>(dst), dp8);
-  else pack2d_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(src, dt, os, is, outer, inner, reinterpret_cast<uint4*>(dst), dp8);
-  bb_launch_tally += 1;
-  BB_LAUNCH_CHECK();
-  return BB_OK;
+  PackJobs J{};
+  PackJob& q = J.j[0];
+  J.n = 1;
+  q.src = src; q.dst = reinterpret_cast<uint4*>(dst); q.os = os; q.is = is; q.outer = outer; q.inner = inner;
+  q.dp8 = dp / 8; q.dt = dt;
+  q.vec = (dt == BB_F32 && is == 1 && inner % 8 == 0 && dp == inner && os % 4 == 0 && aligned16(src)) ? 1 : 0;
+  return flush_packs(J, s);
 }
 
 int bb_pack_nhwc(const void* src, int dt, int N, int C, int HW, void* dst, int Cp, cudaStream_t s) {
@@ -439,53 +552,78 @@ int bb_pack_convw(const void* src, int dt, int O, int C, int taps, int transpose
   return BB_OK;
 }
 
+int bb_pack_im2col(const void* src, int dt, const Im2colGeom& g, void* dst, int kp, cudaStream_t s) {
+  const int64_t total = (int64_t)g.N * g.HO * g.WO * (kp / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 16 * BB_SM_COUNT) blocks = 16 * BB_SM_COUNT;
+  if (blocks < 1) blocks = 1;
+  pack_im2col_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dt, g, reinterpret_cast<uint4*>(dst), kp / 8);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
 int bb_gemm_tma_launch(TmaGemmArgs& G, int bn, int64_t mtiles, cudaStream_t s) {
   return bn == 64 ? launch_tma<64>(G, mtiles, s) : launch_tma<128>(G, mtiles, s);
 }
 
 int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* A, const TmaView* B, float* out,
                     int64_t ors, int64_t ocs, int beta, const float* bias, int64_t bias_stride, bool out_dense,
-                    cudaStream_t s) {
-  if (npairs < 1 || npairs > 2 || M < 64 || N < 64 || K < 64) return BB_DECLINED;
+                    cudaStream_t s, int plane_ohw, int min_n) {
+  if (npairs < 1 || npairs > 2 || M < 64 || N < min_n || K < 8) return BB_DECLINED;
+  if (K < 64 && min_n >= 64) return BB_DECLINED;
   if (M > INT32_MAX / 2 || N > INT32_MAX / 2 || K > INT32_MAX / 2) return BB_DECLINED;
   if (encode_fn() == nullptr || bb_scratch.base == nullptr) return BB_DECLINED;
-  // scratch need, worst case (every operand packed, either layout); plan.py sizes the scratch with the same bound
+  // scratch admission: bytes of the operands that need a pack (plan.py sizes the scratch with an upper bound of this)
   {
-    const size_t need = (size_t)npairs * 2 * (size_t)((M + 8) * (K + 8) + (N + 8) * (K + 8)) + 4096;
-    if (need > bb_scratch.bytes) return BB_DECLINED;
+    size_t need = 1024;
+    for (int p = 0; p < npairs; ++p) need += pack_bytes(A[p], M, K) + pack_bytes(B[p], N, K) + 512;
+    if (bb_scratch.used + need > bb_scratch.bytes) return BB_DECLINED;
   }
-  bb_scratch_reset();
   alignas(64) TmaGemmArgs G;
   memset(&G, 0, sizeof(G));
-  const int bn = N <= 64 ? 64 : 128;
+  // 128-wide N tiles unless that leaves most SMs idle; split-K (memset + atomics) only if even 64-wide tiles do
+  const int64_t mtiles = (M + BM - 1) / BM;
+  int bn = N <= 64 ? 64 : 128;
+  if (bn == 128 && mtiles * ((N + 127) / 128) < BB_SM_COUNT) bn = 64;
+  PackJobs J{};
+  const void* amat[2];
+  const void* bmat[2];
+  int64_t apitch[2], bpitch[2];
   for (int p = 0; p < npairs; ++p) {
-    const void* mat;
-    int64_t pitch;
-    int kind, rc;
-    rc = prepare_operand(A[p], M, K, &mat, &pitch, &kind, s);
+    int rc = prepare_operand(J, A[p], M, K, &amat[p], &apitch[p], &G.a_kind[p]);
     if (rc) return rc;
-    G.a_kind[p] = kind;
-    rc = kind == TMA_KMAJ ? bb_tma_map_2d(&G.a[p], mat, M, K, pitch, BM) : bb_tma_map_2d(&G.a[p], mat, K, M, pitch, 64);
+    rc = prepare_operand(J, B[p], N, K, &bmat[p], &bpitch[p], &G.b_kind[p]);
     if (rc) return rc;
-    rc = prepare_operand(B[p], N, K, &mat, &pitch, &kind, s);
+  }
+  {
+    const int rc = flush_packs(J, s);
     if (rc) return rc;
-    G.b_kind[p] = kind;
-    rc = kind == TMA_KMAJ ? bb_tma_map_2d(&G.b[p], mat, N, K, pitch, bn) : bb_tma_map_2d(&G.b[p], mat, K, N, pitch, 64);
+  }
+  for (int p = 0; p < npairs; ++p) {
+    int rc = G.a_kind[p] == TMA_KMAJ ? bb_tma_map_2d(&G.a[p], amat[p], M, K, apitch[p], BM)
+                                     : bb_tma_map_2d(&G.a[p], amat[p], K, M, apitch[p], 64);
+    if (rc) return rc;
+    rc = G.b_kind[p] == TMA_KMAJ ? bb_tma_map_2d(&G.b[p], bmat[p], N, K, bpitch[p], bn)
+                                 : bb_tma_map_2d(&G.b[p], bmat[p], K, N, bpitch[p], 64);
     if (rc) return rc;
   }
   G.M = M; G.N = N; G.K = K; G.npairs = npairs;
   G.a_bytes = A_TILE; G.b_bytes = (uint32_t)bn * BK * 2;
   G.out = out; G.omode = 0; G.ors = ors; G.ocs = ocs; G.beta = beta; G.bias = bias; G.bias_stride = bias_stride;
-  const int64_t mtiles = (M + BM - 1) / BM;
+  if (plane_ohw > 0) {
+    G.omode = 2; G.OCH = (int)N; G.OHW = plane_ohw;
+  }
   const int64_t tiles = mtiles * ((N + bn - 1) / bn);
   const int64_t kblocks = (K + BK - 1) / BK;
   int ksplit = 1;
-  if (tiles < BB_SM_COUNT && kblocks >= 8) {
-    int64_t want = (2 * BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 4;
+  if (2 * tiles < BB_SM_COUNT && kblocks >= 16) {
+    int64_t want = (BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 8;
     ksplit = (int)(want < maxs ? want : maxs);
-    if (ksplit > 32) ksplit = 32;
+    if (ksplit > 2 * BB_SM_COUNT) ksplit = 2 * BB_SM_COUNT;
     if (ksplit < 1) ksplit = 1;
   }
+  if (plane_ohw > 0) ksplit = 1;
   if (ksplit > 1 && !beta) {
     if (!out_dense) {
       ksplit = 1;
@@ -503,9 +641,11 @@ extern "C" int bb_gemm_bf16_tma(int64_t M, int64_t N, int64_t K, const void* A, 
                                 int beta, void* scratch, int64_t scratch_bytes, void* stream) {
   const BbScratch saved = bb_scratch;
   bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(scratch), (size_t)scratch_bytes, 0};
+  bb_scratch_reset();
   const TmaView a{A, dtA, ars, acs}, b{B, dtB, bcs, brs};   // rows of the B view = n
   const bool dense = (ccs == 1 && crs == N) || (crs == 1 && ccs == M);
   const int rc = bb_gemm_tma_run(M, N, K, 1, &a, &b, C, crs, ccs, beta, nullptr, 0, dense, (cudaStream_t)stream);
   bb_scratch = saved;
+  bb_scratch_reset();
   return rc;
 }

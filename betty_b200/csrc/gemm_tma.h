@@ -15,9 +15,11 @@ struct TmaView {
 
 // D[m][n] (beta)= sum_p sum_k A_p[m][k] * B_p[n][k]  (+ bias[n]),  out[m*ors + n*ocs].
 // Operands that are not already TMA-addressable bf16 are packed into bb_scratch first.
+// plane_ohw > 0: the rows are pixels (img, q) of planes with plane_ohw pixels and the output is NCHW,
+// out[(img*N + n)*plane_ohw + q] (ors / ocs unused).  min_n: smallest N accepted (64 for Linear layers).
 int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* A, const TmaView* B, float* out,
                     int64_t ors, int64_t ocs, int beta, const float* bias, int64_t bias_stride, bool out_dense,
-                    cudaStream_t s);
+                    cudaStream_t s, int plane_ohw = 0, int min_n = 64);
 
 enum { TMA_KMAJ = 0, TMA_MNMAJ = 1, TMA_CONV = 2 };
 
@@ -30,7 +32,8 @@ struct alignas(64) TmaGemmArgs {
   // TMA_CONV: the M tile is a (Wb x Hb) box of pixels of one image, the k-blocks walk (tap, 64-channel block)
   int Wb, Hb, tiles_per_img, KW, ph, pw, flip, cblocks;
   float* out;
-  int omode;                   // 0: out[m*ors + n*ocs]; 1 (plane): out[(img*OCH + n)*OHW + pixel]
+  int omode;                   // 0: out[m*ors + n*ocs]; 1 (plane, TMA_CONV tiles): out[(img*OCH + n)*OHW + pixel];
+                               // 2 (plane, flat rows): m = img*OHW + q
   int64_t ors, ocs;
   int OCH, OHW;
   int beta;
@@ -49,3 +52,8 @@ int bb_pack_nhwc(const void* src, int dt, int N, int C, int HW, void* dst, int C
 // conv weights W[o][c][i][j] (dt) -> dst[r][tap][q] bf16, q padded to Qp:
 //   transpose = 0: r = o, q = c (forward operand);  transpose = 1: r = c, q = o (input-gradient operand)
 int bb_pack_convw(const void* src, int dt, int O, int C, int taps, int transpose, void* dst, int Qp, cudaStream_t s);
+// im2col of an NCHW tensor: dst[pixel (img,y,x) of the HO x WO grid][k = (c,i,j)] bf16, pitch kp (>= C*KH*KW, mult of 8)
+struct Im2colGeom {
+  int N, C, H, W, KH, KW, HO, WO, sh, sw, ph, pw, dh, dw;
+};
+int bb_pack_im2col(const void* src, int dt, const Im2colGeom& g, void* dst, int kp, cudaStream_t s);

@@ -65,6 +65,7 @@ int dispatch(const bb_node& nd, int pass, cudaStream_t s) {
 int run_pass(bb_plan* p, int pass, cudaStream_t s) {
   if (pass < 0 || pass > 2) return BB_ERR_ARG;
   bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(p->scratch), (size_t)p->scratch_bytes, 0};
+  bb_scratch_reset();
   const int tally0 = bb_launch_tally;
   for (size_t i = 0; i < p->zero_ptr[pass].size(); ++i) {
     BB_CUDA_TRY(cudaMemsetAsync(p->zero_ptr[pass][i], 0, (size_t)p->zero_bytes[pass][i], s));
@@ -178,6 +179,7 @@ int bb_plan_profile(bb_plan* plan, int pass, float* ms_per_node, void* stream) {
   if (!plan || pass < 0 || pass > 2 || !ms_per_node) return BB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(plan->scratch), (size_t)plan->scratch_bytes, 0};
+  bb_scratch_reset();
   const int n = (int)plan->nodes.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) BB_CUDA_TRY(cudaEventCreate(&e));

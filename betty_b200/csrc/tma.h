@@ -15,8 +15,12 @@ struct BbScratch {
   size_t used;
 };
 extern thread_local BbScratch bb_scratch;
+extern thread_local uint64_t bb_scratch_gen;   // bumped by every reset: invalidates the launcher's pack cache
 
-inline void bb_scratch_reset() { bb_scratch.used = 0; }
+inline void bb_scratch_reset() {
+  bb_scratch.used = 0;
+  ++bb_scratch_gen;
+}
 inline void* bb_scratch_alloc(size_t bytes) {
   const size_t at = (bb_scratch.used + 255) & ~(size_t)255;
   if (bb_scratch.base == nullptr || at + bytes > bb_scratch.bytes) return nullptr;

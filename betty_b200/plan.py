@@ -186,10 +186,16 @@ class HvpPlan:
             if batch != 1:
                 return 0
             pad = lambda a, b: (a + 8) * (b + 8)
-            return 2 * 2 * max(pad(M, K) + pad(Nn, K), pad(M, Nn) + pad(K, Nn), pad(K, M) + pad(Nn, M)) + 8192
+            # packs live for the whole node (TB: both adjoints, both weights, both inputs) and the launcher's
+            # admission check counts either layout of every operand of the launch at hand
+            return 2 * 4 * (pad(M, K) + pad(Nn, K) + pad(M, Nn)) + 16384
         if int(r["op"]) == OPS["conv2d"]:
             Nn, Cc, H, W, O, KH, KW, HO, WO = (int(x) for x in r["dims"][0:9])
             unit = all(int(x) == 1 for x in (r["dims"][9], r["dims"][10], r["dims"][13], r["dims"][14]))
+            ckk, act = Cc * KH * KW, int(r["active"])
+            if not (act & 1) and (act & 2) and 8 <= ckk <= 64 and 32 <= O <= 128 and Nn * HO * WO >= 128:
+                kp, opad = _align(ckk, 8), _align(O, 64)      # data-input layer: im2col matrix + packed at_y
+                return 2 * Nn * HO * WO * (kp + opad) + 2 * (O + 8) * (kp + 8) + 16384 + 8192
             if not (unit and KH * KW <= 9 and 32 <= Cc <= 64 and 32 <= O <= 64 and 4 <= WO <= 64 and W <= 128):
                 return 0          # bb_conv_tma_ok() declines: software-staged / SIMT kernels, no packs
             cp, op = _align(Cc, 64), _align(O, 64)
