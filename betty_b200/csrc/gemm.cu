@@ -76,11 +76,21 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
              int64_t ors, int64_t ocs, int64_t obs, int beta, const float* bias, int64_t bias_stride,
              cudaStream_t s, bool tensor_cores = false) {
   if (M <= 0 || N <= 0 || batch <= 0) return BB_OK;
+  static const bool no_tma = getenv("BB200_NO_TMA") != nullptr;
+  if (tensor_cores && npairs > 0 && batch > 1 && !no_tma) {
+    // batched products (attention): TMA-fed tcgen05 kernel, one grid.z slice per batch
+    TmaView a[2], b[2];
+    for (int p = 0; p < npairs; ++p) {
+      a[p] = TmaView{L[p].p, L[p].dt, L[p].rs, L[p].cs, L[p].bs};
+      b[p] = TmaView{R[p].p, R[p].dt, R[p].cs, R[p].rs, R[p].bs};
+    }
+    const int rc = bb_gemm_tma_run(M, N, K, npairs, a, b, out, ors, ocs, beta, bias, bias_stride, false, s, 0, 64, batch, obs);
+    if (rc != BB_DECLINED) return rc;
+  }
   if (tensor_cores && npairs > 0 && bb_gemm_tc_eligible(M, N, K, batch)) {
     // bf16-autocast configuration: tcgen05 path (operands rounded to bf16, fp32 accumulation in TMEM).
     // Preferred: operands packed to TMA-addressable bf16 and fed by the TMA unit (gemm_tma.cu); the software-staged
     // kernel takes what that launcher declines (no scratch, odd shapes).
-    static const bool no_tma = getenv("BB200_NO_TMA") != nullptr;
     if (!no_tma) {
       TmaView a[2], b[2];
       for (int p = 0; p < npairs; ++p) {

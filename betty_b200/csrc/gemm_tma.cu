@@ -44,27 +44,31 @@ constexpr int BM = 128, BK = 64;
 constexpr int NTHREADS = 192;
 constexpr int A_TILE = BM * BK * 2;   // 16 KB
 
+constexpr int MAX_STAGES = 8;
+
 template <int BN_>
 struct Cfg {
-  static constexpr int kStages = BN_ == 64 ? 4 : 3;
+  static constexpr int kStagesShared = BN_ == 64 ? 4 : 3;   // two CTAs per SM
+  static constexpr int kStagesDeep = BN_ == 64 ? 8 : 6;     // one CTA per SM, ~190 KB in flight
   static constexpr int kBTile = BN_ * BK * 2;
   static constexpr int kStage = A_TILE + kBTile;
-  static constexpr size_t kSmem = (size_t)kStages * kStage + 1024 + 256;
+  static constexpr size_t smem(int stages) { return (size_t)stages * kStage + 1024 + 256; }
 };
 
 template <int BN_>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_constant__ TmaGemmArgs G) {
   using C = Cfg<BN_>;
-  constexpr int STAGES = C::kStages;
+  const int STAGES = G.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStage);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum = smem_u32(bars + 2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES), accum = smem_u32(bars + 2 * MAX_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * BN_;
-  const int split = blockIdx.z;
+  const int bz = blockIdx.z / G.ksplit;            // batch index (ksplit == 1 when batched)
+  const int split = blockIdx.z - bz * G.ksplit;
   const int64_t kblocks_total = (G.K + BK - 1) / BK;
   const int64_t kb_per = (kblocks_total + G.ksplit - 1) / G.ksplit;
   const int64_t kb_beg = (int64_t)split * kb_per;
@@ -114,21 +118,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
         mbar_expect_tx(bar, G.a_bytes + G.b_bytes);
         const int ak = G.a_kind[pair];
         if (ak == TMA_KMAJ) {
-          tma_load_2d(sa, &G.a[pair], bar, k0, m0);
+          tma_load_3d(sa, &G.a[pair], bar, k0, m0, bz);
         } else if (ak == TMA_MNMAJ) {
-          tma_load_2d(sa, &G.a[pair], bar, m0, k0);
-          tma_load_2d(sa + 8192, &G.a[pair], bar, m0 + 64, k0);
+          tma_load_3d(sa, &G.a[pair], bar, m0, k0, bz);
+          tma_load_3d(sa + 8192, &G.a[pair], bar, m0 + 64, k0, bz);
         } else {
           const int tap = kb / G.cblocks, cb = kb - tap * G.cblocks;
           const int i = tap / G.KW, j = tap - i * G.KW;
           const int dy = G.flip ? G.ph - i : i - G.ph, dx = G.flip ? G.pw - j : j - G.pw;
           tma_load_4d(sa, &G.a[pair], bar, cb * 64, dx, h0 + dy, img);
         }
+        const int bzb = ak == TMA_CONV ? 0 : bz;
         if (G.b_kind[pair] == TMA_KMAJ) {
-          tma_load_2d(sb, &G.b[pair], bar, k0, n0);
+          tma_load_3d(sb, &G.b[pair], bar, k0, n0, bzb);
         } else {
 #pragma unroll
-          for (int q = 0; q < BN_ / 64; ++q) tma_load_2d(sb + q * 8192, &G.b[pair], bar, n0 + q * 64, k0);
+          for (int q = 0; q < BN_ / 64; ++q) tma_load_3d(sb + q * 8192, &G.b[pair], bar, n0 + q * 64, k0, bzb);
         }
       }
     }
@@ -178,10 +183,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
     } else {
       const int64_t row = (int64_t)m0 + r;
       row_ok = row < G.M;
-      row_base = row * G.ors;
+      row_base = (int64_t)bz * G.obs + row * G.ors;
       col_stride = G.ocs;
     }
-    const bool vec = G.omode == 0 && G.ocs == 1 && G.ksplit == 1 && (G.ors & 3) == 0 &&
+    const bool vec = G.omode == 0 && G.ocs == 1 && G.ksplit == 1 && (G.ors & 3) == 0 && (G.obs & 3) == 0 &&
                      ((reinterpret_cast<uintptr_t>(G.out) & 15) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN_ / 32; ++c) {
@@ -235,14 +240,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
 }
 
 template <int BN_>
-int launch_tma(const TmaGemmArgs& G, int64_t mtiles, cudaStream_t s) {
+int launch_tma(TmaGemmArgs& G, int64_t mtiles, cudaStream_t s, int batch) {
+  using C = Cfg<BN_>;
   static bool configured = false;
   if (!configured) {
-    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tma_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN_>::kSmem));
+    BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tma_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)C::smem(C::kStagesDeep)));
     configured = true;
   }
-  dim3 grid((unsigned)((G.N + BN_ - 1) / BN_), (unsigned)mtiles, (unsigned)G.ksplit);
-  gemm_tma_kernel<BN_><<<grid, NTHREADS, Cfg<BN_>::kSmem, s>>>(G);
+  dim3 grid((unsigned)((G.N + BN_ - 1) / BN_), (unsigned)mtiles, (unsigned)(G.ksplit * batch));
+  // A grid that does not fill the machine is latency-bound on its k-loop (each TMA round trip is ~1.5 us): give the
+  // lone CTA of each SM the whole shared memory as prefetch depth.  Full grids keep two CTAs per SM instead, so one
+  // CTA's epilogue overlaps the other's main loop.
+  static const int forced = getenv("BB200_TMA_STAGES") ? atoi(getenv("BB200_TMA_STAGES")) : 0;
+  const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+  G.stages = ctas <= BB_SM_COUNT ? C::kStagesDeep : C::kStagesShared;
+  if (forced >= 2 && forced <= C::kStagesDeep) G.stages = forced;
+  gemm_tma_kernel<BN_><<<grid, NTHREADS, C::smem(G.stages), s>>>(G);
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();
   return BB_OK;
@@ -310,7 +324,8 @@ struct PackJob {
   const void* src;
   uint4* dst;
   int64_t os, is, outer, inner, dp8;
-  int dt, vec;   // vec: fp32, is == 1, rows 16-byte aligned, inner % 8 == 0, dp == inner
+  int64_t batch, sbs;   // batches (>= 1) and source batch stride; destination batches are dense (outer*dp8 chunks)
+  int dt, vec;          // vec: fp32, is == 1, rows 16-byte aligned, inner % 8 == 0, dp == inner
 };
 struct PackJobs {
   PackJob j[4];
@@ -319,17 +334,19 @@ struct PackJobs {
 
 __global__ void __launch_bounds__(256) pack2d_kernel(const __grid_constant__ PackJobs J) {
   const PackJob& q = J.j[blockIdx.y];
-  const int64_t total = q.outer * q.dp8;
+  const int64_t per = q.outer * q.dp8, total = per * q.batch;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = t / q.dp8, i0 = (t - o * q.dp8) * 8;
+    const int64_t b = t / per, tb = t - b * per;
+    const int64_t o = tb / q.dp8, i0 = (tb - o * q.dp8) * 8;
+    const int64_t sb = b * q.sbs;
     float v[8];
     if (q.vec) {
-      const float* f = reinterpret_cast<const float*>(q.src) + o * q.os + i0;
+      const float* f = reinterpret_cast<const float*>(q.src) + sb + o * q.os + i0;
       const float4 a = bb::ld4_stream(f), b = bb::ld4_stream(f + 4);
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (i0 + e < q.inner) ? bb::ldf(q.src, o * q.os + (i0 + e) * q.is, q.dt) : 0.f;
+      for (int e = 0; e < 8; ++e) v[e] = (i0 + e < q.inner) ? bb::ldf(q.src, sb + o * q.os + (i0 + e) * q.is, q.dt) : 0.f;
     }
     uint4 out;
     out.x = pack_bf16(v[0], v[1]); out.y = pack_bf16(v[2], v[3]); out.z = pack_bf16(v[4], v[5]); out.w = pack_bf16(v[6], v[7]);
@@ -416,7 +433,7 @@ inline int64_t round8(int64_t x) { return (x + 7) / 8 * 8; }
 // and its transposed MN-major view are the same bytes.
 struct PackKey {
   const void* src;
-  int64_t os, is, outer, inner;
+  int64_t os, is, outer, inner, batch, sbs;
   int dt;
   void* dst;
 };
@@ -424,32 +441,36 @@ thread_local PackKey t_cache[16];
 thread_local int t_ncache = 0;
 thread_local uint64_t t_cache_gen = 0;   // bb_scratch_gen the entries belong to
 
-void* cached_pack(const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner) {
+void* cached_pack(const PackKey& want) {
   if (t_cache_gen != bb_scratch_gen) {   // scratch was reset since
     t_ncache = 0;
     t_cache_gen = bb_scratch_gen;
   }
   for (int i = 0; i < t_ncache; ++i) {
     const PackKey& k = t_cache[i];
-    if (k.src == src && k.dt == dt && k.os == os && k.is == is && k.outer == outer && k.inner == inner) return k.dst;
+    if (k.src == want.src && k.dt == want.dt && k.os == want.os && k.is == want.is && k.outer == want.outer &&
+        k.inner == want.inner && k.batch == want.batch && k.sbs == want.sbs)
+      return k.dst;
   }
   return nullptr;
 }
 
-int queue_pack(PackJobs& J, const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner, void** dst,
-               int64_t* dp) {
+int queue_pack(PackJobs& J, const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner, int64_t batch,
+               int64_t sbs, void** dst, int64_t* dp) {
   *dp = round8(inner);
-  if (void* hit = cached_pack(src, dt, os, is, outer, inner)) {
+  PackKey key{src, os, is, outer, inner, batch, batch > 1 ? sbs : 0, dt, nullptr};
+  if (void* hit = cached_pack(key)) {
     *dst = hit;
     return BB_OK;
   }
-  void* d = bb_scratch_alloc((size_t)outer * *dp * 2);
+  void* d = bb_scratch_alloc((size_t)batch * outer * *dp * 2);
   if (!d || J.n >= 4) return BB_DECLINED;
   PackJob& q = J.j[J.n++];
   q.src = src; q.dst = reinterpret_cast<uint4*>(d); q.os = os; q.is = is; q.outer = outer; q.inner = inner;
-  q.dp8 = *dp / 8; q.dt = dt;
-  q.vec = (dt == BB_F32 && is == 1 && inner % 8 == 0 && os % 4 == 0 && aligned16(src)) ? 1 : 0;
-  if (t_ncache < 16) t_cache[t_ncache++] = PackKey{src, os, is, outer, inner, dt, d};
+  q.dp8 = *dp / 8; q.dt = dt; q.batch = batch; q.sbs = key.sbs;
+  q.vec = (dt == BB_F32 && is == 1 && inner % 8 == 0 && os % 4 == 0 && key.sbs % 4 == 0 && aligned16(src)) ? 1 : 0;
+  key.dst = d;
+  if (t_ncache < 16) t_cache[t_ncache++] = key;
   *dst = d;
   return BB_OK;
 }
@@ -458,7 +479,7 @@ int flush_packs(const PackJobs& J, cudaStream_t s) {
   if (J.n == 0) return BB_OK;
   int64_t most = 0;
   for (int i = 0; i < J.n; ++i) {
-    const int64_t t = J.j[i].outer * J.j[i].dp8;
+    const int64_t t = J.j[i].batch * J.j[i].outer * J.j[i].dp8;
     if (t > most) most = t;
   }
   int64_t blocks = (most + 255) / 256;
@@ -470,49 +491,62 @@ int flush_packs(const PackJobs& J, cudaStream_t s) {
   return BB_OK;
 }
 
-inline bool direct_k(const TmaView& v, int64_t K) {
-  return v.cs == 1 && v.dt == BB_BF16 && v.rs % 8 == 0 && v.rs >= K && aligned16(v.p);
+// An operand after preparation: a bf16 matrix (per batch) whose rows are the view's rows (TMA_KMAJ, pitch >= K) or the
+// view's k (TMA_MNMAJ, pitch >= R), `bstride` elements between batches.
+struct Prepared {
+  const void* mat;
+  int64_t pitch, bstride;
+  int kind;
+};
+
+inline bool batch_ok(const TmaView& v, int64_t batch) { return batch == 1 || (v.bs % 8 == 0 && v.bs > 0); }
+inline bool direct_k(const TmaView& v, int64_t K, int64_t batch) {
+  return v.cs == 1 && v.dt == BB_BF16 && v.rs % 8 == 0 && v.rs >= K && aligned16(v.p) && batch_ok(v, batch);
 }
-inline bool direct_mn(const TmaView& v, int64_t R) {
-  return v.rs == 1 && v.cs != 1 && v.dt == BB_BF16 && v.cs % 8 == 0 && v.cs >= R && aligned16(v.p);
+inline bool direct_mn(const TmaView& v, int64_t R, int64_t batch) {
+  return v.rs == 1 && v.cs != 1 && v.dt == BB_BF16 && v.cs % 8 == 0 && v.cs >= R && aligned16(v.p) && batch_ok(v, batch);
 }
-size_t pack_bytes(const TmaView& v, int64_t R, int64_t K) {
-  if (v.cs == 1 || v.rs != 1) return direct_k(v, K) ? 0 : (size_t)R * round8(K) * 2;
-  return direct_mn(v, R) ? 0 : (size_t)K * round8(R) * 2;
+size_t pack_bytes(const TmaView& v, int64_t R, int64_t K, int64_t batch) {
+  if (v.cs == 1 || v.rs != 1) return direct_k(v, K, batch) ? 0 : (size_t)batch * R * round8(K) * 2;
+  return direct_mn(v, R, batch) ? 0 : (size_t)batch * K * round8(R) * 2;
 }
 
-// Make one operand view TMA-addressable.  On return *mat/*pitch describe a bf16 row-major matrix whose rows are the
-// view's rows (kind TMA_KMAJ, pitch >= K) or the view's k (kind TMA_MNMAJ, pitch >= R); packs are queued in J.
-int prepare_operand(PackJobs& J, const TmaView& v, int64_t R, int64_t K, const void** mat, int64_t* pitch, int* kind) {
+// Make one operand view TMA-addressable; packs are queued in J.
+int prepare_operand(PackJobs& J, const TmaView& v, int64_t R, int64_t K, int64_t batch, Prepared* out) {
   void* d = nullptr;
   if (v.cs == 1 || v.rs != 1) {
     // K-major (or neither stride unit: gathered into K-major)
-    *kind = TMA_KMAJ;
-    if (direct_k(v, K)) {
-      *mat = v.p; *pitch = v.rs;
+    out->kind = TMA_KMAJ;
+    if (direct_k(v, K, batch)) {
+      out->mat = v.p; out->pitch = v.rs; out->bstride = batch > 1 ? v.bs : R * v.rs;
       return BB_OK;
     }
-    const int rc = queue_pack(J, v.p, v.dt, v.rs, v.cs, R, K, &d, pitch);
-    *mat = d;
+    const int rc = queue_pack(J, v.p, v.dt, v.rs, v.cs, R, K, batch, v.bs, &d, &out->pitch);
+    out->mat = d; out->bstride = R * out->pitch;
     return rc;
   }
-  *kind = TMA_MNMAJ;
-  if (direct_mn(v, R)) {
-    *mat = v.p; *pitch = v.cs;
+  out->kind = TMA_MNMAJ;
+  if (direct_mn(v, R, batch)) {
+    out->mat = v.p; out->pitch = v.cs; out->bstride = batch > 1 ? v.bs : K * v.cs;
     return BB_OK;
   }
-  const int rc = queue_pack(J, v.p, v.dt, v.cs, 1, K, R, &d, pitch);
-  *mat = d;
+  const int rc = queue_pack(J, v.p, v.dt, v.cs, 1, K, R, batch, v.bs, &d, &out->pitch);
+  out->mat = d; out->bstride = K * out->pitch;
   return rc;
 }
 
 }  // namespace
 
+int bb_tma_map_3d(CUtensorMap* out, const void* p, int64_t batch, int64_t rows, int64_t cols, int64_t pitch,
+                  int64_t bstride, int box_rows) {
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)bstride * 2};
+  const cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  return encode_cached(out, 3, p, dims, strides, box);
+}
+
 int bb_tma_map_2d(CUtensorMap* out, const void* p, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
-  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-  return encode_cached(out, 2, p, dims, strides, box);
+  return bb_tma_map_3d(out, p, 1, rows, cols, pitch, rows * pitch, box_rows);
 }
 
 int bb_tma_map_nhwc(CUtensorMap* out, const void* p, int N, int H, int W, int Cp, int bw, int bh) {
@@ -529,7 +563,7 @@ int bb_pack2d(const void* src, int dt, int64_t os, int64_t is, int64_t outer, in
   PackJob& q = J.j[0];
   J.n = 1;
   q.src = src; q.dst = reinterpret_cast<uint4*>(dst); q.os = os; q.is = is; q.outer = outer; q.inner = inner;
-  q.dp8 = dp / 8; q.dt = dt;
+  q.dp8 = dp / 8; q.dt = dt; q.batch = 1; q.sbs = 0;
   q.vec = (dt == BB_F32 && is == 1 && inner % 8 == 0 && dp == inner && os % 4 == 0 && aligned16(src)) ? 1 : 0;
   return flush_packs(J, s);
 }
@@ -563,21 +597,28 @@ int bb_pack_im2col(const void* src, int dt, const Im2colGeom& g, void* dst, int 
   return BB_OK;
 }
 
-int bb_gemm_tma_launch(TmaGemmArgs& G, int bn, int64_t mtiles, cudaStream_t s) {
-  return bn == 64 ? launch_tma<64>(G, mtiles, s) : launch_tma<128>(G, mtiles, s);
+int bb_gemm_tma_launch(TmaGemmArgs& G, int bn, int64_t mtiles, cudaStream_t s, int batch) {
+  return bn == 64 ? launch_tma<64>(G, mtiles, s, batch) : launch_tma<128>(G, mtiles, s, batch);
 }
 
 int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* A, const TmaView* B, float* out,
                     int64_t ors, int64_t ocs, int beta, const float* bias, int64_t bias_stride, bool out_dense,
-                    cudaStream_t s, int plane_ohw, int min_n) {
-  if (npairs < 1 || npairs > 2 || M < 64 || N < min_n || K < 8) return BB_DECLINED;
-  if (K < 64 && min_n >= 64) return BB_DECLINED;
+                    cudaStream_t s, int plane_ohw, int min_n, int64_t batch, int64_t obs) {
+  if (npairs < 1 || npairs > 2 || batch < 1) return BB_DECLINED;
+  if (batch == 1) {
+    if (M < 64 || N < min_n || K < 8) return BB_DECLINED;
+    if (K < 64 && min_n >= 64) return BB_DECLINED;
+  } else {
+    // batched (attention score / context products): the tiles are mostly padding, but a 128 x 64 tcgen05 tile costs
+    // less than the SIMT kernel's inner loop as soon as the products are not tiny
+    if (M < 32 || N < 32 || K < 32 || batch > 65535 || plane_ohw > 0 || bias != nullptr) return BB_DECLINED;
+  }
   if (M > INT32_MAX / 2 || N > INT32_MAX / 2 || K > INT32_MAX / 2) return BB_DECLINED;
   if (encode_fn() == nullptr || bb_scratch.base == nullptr) return BB_DECLINED;
   // scratch admission: bytes of the operands that need a pack (plan.py sizes the scratch with an upper bound of this)
   {
     size_t need = 1024;
-    for (int p = 0; p < npairs; ++p) need += pack_bytes(A[p], M, K) + pack_bytes(B[p], N, K) + 512;
+    for (int p = 0; p < npairs; ++p) need += pack_bytes(A[p], M, K, batch) + pack_bytes(B[p], N, K, batch) + 512;
     if (bb_scratch.used + need > bb_scratch.bytes) return BB_DECLINED;
   }
   alignas(64) TmaGemmArgs G;
@@ -585,15 +626,13 @@ int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* 
   // 128-wide N tiles unless that leaves most SMs idle; split-K (memset + atomics) only if even 64-wide tiles do
   const int64_t mtiles = (M + BM - 1) / BM;
   int bn = N <= 64 ? 64 : 128;
-  if (bn == 128 && mtiles * ((N + 127) / 128) < BB_SM_COUNT) bn = 64;
+  if (bn == 128 && mtiles * ((N + 127) / 128) * batch < BB_SM_COUNT) bn = 64;
   PackJobs J{};
-  const void* amat[2];
-  const void* bmat[2];
-  int64_t apitch[2], bpitch[2];
+  Prepared pa[2], pb[2];
   for (int p = 0; p < npairs; ++p) {
-    int rc = prepare_operand(J, A[p], M, K, &amat[p], &apitch[p], &G.a_kind[p]);
+    int rc = prepare_operand(J, A[p], M, K, batch, &pa[p]);
     if (rc) return rc;
-    rc = prepare_operand(J, B[p], N, K, &bmat[p], &bpitch[p], &G.b_kind[p]);
+    rc = prepare_operand(J, B[p], N, K, batch, &pb[p]);
     if (rc) return rc;
   }
   {
@@ -601,23 +640,25 @@ int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* 
     if (rc) return rc;
   }
   for (int p = 0; p < npairs; ++p) {
-    int rc = G.a_kind[p] == TMA_KMAJ ? bb_tma_map_2d(&G.a[p], amat[p], M, K, apitch[p], BM)
-                                     : bb_tma_map_2d(&G.a[p], amat[p], K, M, apitch[p], 64);
+    G.a_kind[p] = pa[p].kind;
+    G.b_kind[p] = pb[p].kind;
+    int rc = pa[p].kind == TMA_KMAJ ? bb_tma_map_3d(&G.a[p], pa[p].mat, batch, M, K, pa[p].pitch, pa[p].bstride, BM)
+                                    : bb_tma_map_3d(&G.a[p], pa[p].mat, batch, K, M, pa[p].pitch, pa[p].bstride, 64);
     if (rc) return rc;
-    rc = G.b_kind[p] == TMA_KMAJ ? bb_tma_map_2d(&G.b[p], bmat[p], N, K, bpitch[p], bn)
-                                 : bb_tma_map_2d(&G.b[p], bmat[p], K, N, bpitch[p], 64);
+    rc = pb[p].kind == TMA_KMAJ ? bb_tma_map_3d(&G.b[p], pb[p].mat, batch, N, K, pb[p].pitch, pb[p].bstride, bn)
+                                : bb_tma_map_3d(&G.b[p], pb[p].mat, batch, K, N, pb[p].pitch, pb[p].bstride, 64);
     if (rc) return rc;
   }
   G.M = M; G.N = N; G.K = K; G.npairs = npairs;
   G.a_bytes = A_TILE; G.b_bytes = (uint32_t)bn * BK * 2;
-  G.out = out; G.omode = 0; G.ors = ors; G.ocs = ocs; G.beta = beta; G.bias = bias; G.bias_stride = bias_stride;
+  G.out = out; G.omode = 0; G.ors = ors; G.ocs = ocs; G.obs = obs; G.beta = beta; G.bias = bias; G.bias_stride = bias_stride;
   if (plane_ohw > 0) {
     G.omode = 2; G.OCH = (int)N; G.OHW = plane_ohw;
   }
-  const int64_t tiles = mtiles * ((N + bn - 1) / bn);
+  const int64_t tiles = mtiles * ((N + bn - 1) / bn) * batch;
   const int64_t kblocks = (K + BK - 1) / BK;
   int ksplit = 1;
-  if (2 * tiles < BB_SM_COUNT && kblocks >= 16) {
+  if (batch == 1 && 2 * tiles < BB_SM_COUNT && kblocks >= 16) {
     int64_t want = (BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 8;
     ksplit = (int)(want < maxs ? want : maxs);
     if (ksplit > 2 * BB_SM_COUNT) ksplit = 2 * BB_SM_COUNT;
@@ -633,7 +674,7 @@ int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* 
     }
   }
   G.ksplit = ksplit;
-  return bb_gemm_tma_launch(G, bn, mtiles, s);
+  return bb_gemm_tma_launch(G, bn, mtiles, s, (int)batch);
 }
 
 extern "C" int bb_gemm_bf16_tma(int64_t M, int64_t N, int64_t K, const void* A, int dtA, int64_t ars, int64_t acs,

@@ -31,5 +31,9 @@ inline void* bb_scratch_alloc(size_t bytes) {
 // bf16 row-major matrix [rows][cols], `pitch` elements between rows (multiple of 8, base 16-byte aligned):
 // box = (64 columns, box_rows rows), SWIZZLE_128B.  Returns 0 or an error code.
 int bb_tma_map_2d(CUtensorMap* out, const void* p, int64_t rows, int64_t cols, int64_t pitch, int box_rows);
+// batched form: `batch` such matrices `bstride` elements apart (multiple of 8); box = (64, box_rows, 1).  The kernels
+// always address matrices through this rank-3 form (bb_tma_map_2d is batch = 1).
+int bb_tma_map_3d(CUtensorMap* out, const void* p, int64_t batch, int64_t rows, int64_t cols, int64_t pitch,
+                  int64_t bstride, int box_rows);
 // bf16 NHWC tensor [N][H][W][Cp] (Cp multiple of 64): box = (64 channels, bw, bh, 1), SWIZZLE_128B.
 int bb_tma_map_nhwc(CUtensorMap* out, const void* p, int N, int H, int W, int Cp, int bw, int bh);

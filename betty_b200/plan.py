@@ -183,9 +183,7 @@ class HvpPlan:
             return 0
         if int(r["op"]) == OPS["gemm"]:
             M, Nn, K, batch = (int(x) for x in r["dims"][0:4])
-            if batch != 1:
-                return 0
-            pad = lambda a, b: (a + 8) * (b + 8)
+            pad = lambda a, b: batch * (a + 8) * (b + 8)
             # packs live for the whole node (TB: both adjoints, both weights, both inputs) and the launcher's
             # admission check counts either layout of every operand of the launch at hand
             return 2 * 4 * (pad(M, K) + pad(Nn, K) + pad(M, Nn)) + 16384

@@ -31,6 +31,8 @@ CASES = {
     # 128 tokens x hidden 128: the Linear products are large enough for the tcgen05 tensor-core kernel
     "roberta_bf16_tc": ("bert_data_reweighting", dict(batch=8, seq=16, tiny=True, tiny_hidden=128, precision="bf16"), 4e-2),
     # 64-channel 3x3 convolutions on the tensor-core implicit-GEMM path (forward / data-grad / weight-grad gathers)
+    # 40 tokens x head_dim 64: the batched attention products go through the TMA-fed tensor-core kernel as well
+    "roberta_bf16_attn_tc": ("bert_data_reweighting", dict(batch=4, seq=40, tiny=True, tiny_hidden=256, precision="bf16"), 4e-2),
     "fourconv_bf16_tc": ("implicit_maml", dict(n=6, hidden=64, precision="bf16"), 5e-2),
     "fourconv_mini_bf16_tc": ("implicit_maml", dict(n=2, hidden=32, image="miniimagenet", precision="bf16"), 5e-2),
     "roberta_fp16": ("bert_data_reweighting", dict(batch=3, seq=9, tiny=True, precision="fp16"), 3e-2),
