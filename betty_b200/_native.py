@@ -49,6 +49,7 @@ _SIGS = {
                           C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                           C.c_void_p], None),
     "bb_plan_set_scratch": ([C.c_void_p, C.c_void_p, C.c_int64], 0),
+    "bb_plan_set_persistent": ([C.c_void_p, C.c_void_p, C.c_int64], 0),
     "bb_node_bytes": ([], 0),
     "bb_plan_create": ([C.c_void_p, C.c_int, C.POINTER(C.c_void_p)], 0),
     "bb_plan_destroy": ([C.c_void_p], 0),

@@ -183,6 +183,7 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
   const bool tc = (nd.kind & 1) && unit && !getenv("BB200_NO_TC") && g.O >= 32 && CKK <= 2048 && OKK <= 2048;
   // preferred tensor-core route: NHWC bf16 packs + TMA box loads (conv_tma.cu)
   bool tma_done = false;
+  if (pass == BB_PASS_BASE_BWD && (rc = bb_conv_tma_prepare(nd, s))) return rc;
   if (bb_conv_tma_ok(nd, pass)) {
     rc = bb_conv_tma_run(nd, pass, s);
     if (rc == BB_OK) {

@@ -220,10 +220,17 @@ int run_small_c(const bb_node& nd, int pass, cudaStream_t s) {
   const int kp = (int)((CKK + 7) / 8 * 8), op = (O + 63) / 64 * 64;
   if (small_c_scratch(nd) > bb_scratch.bytes) return BB_DECLINED;
   bb_scratch_reset();
-  void* xcol = bb_scratch_alloc((size_t)P * kp * 2);
+  // the input is data: its im2col matrix is a K-loop constant -> plan-lifetime buffer when one is configured
+  bool fresh = false;
+  void* xcol = bb_persist_get((size_t)P * kp * 2, &fresh);
+  if (!xcol) {
+    xcol = bb_scratch_alloc((size_t)P * kp * 2);
+    fresh = true;
+  }
   if (!xcol) return BB_DECLINED;
-  int rc = bb_pack_im2col(nd.base[0], nd.dt[0], ig, xcol, kp, s);
-  if (rc) return rc;
+  int rc = BB_OK;
+  if (fresh && (rc = bb_pack_im2col(nd.base[0], nd.dt[0], ig, xcol, kp, s))) return rc;
+  if (pass == BB_PASS_BASE_BWD) return BB_OK;   // bb_conv_tma_prepare: only the constant pack
   if (pass == BB_PASS_TAN_FWD) {
     const TmaView a{xcol, BB_BF16, kp, 1};                 // rows = pixels
     const TmaView b{nd.t[1], BB_F32, CKK, 1};              // rows = o
@@ -254,6 +261,13 @@ bool bb_conv_tma_ok(const bb_node& nd, int pass) {
   if (WO > 64 || W > 128 || WO < 4 || HO < 1) return false;
   (void)H;
   return true;
+}
+
+int bb_conv_tma_prepare(const bb_node& nd, cudaStream_t s) {
+  static const bool off = getenv("BB200_NO_TMA") != nullptr || getenv("BB200_NO_TC") != nullptr;
+  if (off || !(nd.kind & 1) || bb_scratch.base == nullptr || !small_c_ok(nd)) return BB_OK;
+  const int rc = run_small_c(nd, BB_PASS_BASE_BWD, s);
+  return rc == BB_DECLINED ? BB_OK : rc;
 }
 
 size_t bb_conv_tma_scratch(const bb_node& nd) {

@@ -7,6 +7,8 @@
 
 // node shape / pass this path handles (stride 1, <= 9 taps, 32..64 channels each way, bf16-autocast graph, scratch set)
 bool bb_conv_tma_ok(const bb_node& nd, int pass);
+// base-backward pass hook: packs the node's K-loop constants into the plan's persistent arena (no-op otherwise)
+int bb_conv_tma_prepare(const bb_node& nd, cudaStream_t s);
 // scratch bytes the node's packs need (plan.py mirrors this bound)
 size_t bb_conv_tma_scratch(const bb_node& nd);
 // TF: writes t_y.  TB: writes at_x and at_W (the bias adjoint stays with the caller).  BB_DECLINED: nothing usable was

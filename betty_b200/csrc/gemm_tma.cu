@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
       row_base = (int64_t)bz * G.obs + row * G.ors;
       col_stride = G.ocs;
     }
-    const bool vec = G.omode == 0 && G.ocs == 1 && G.ksplit == 1 && (G.ors & 3) == 0 && (G.obs & 3) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(G.out) & 15) == 0);
+    const bool row_vec = G.omode == 0 && G.ocs == 1 && (G.ors & 3) == 0 && (G.obs & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(G.out) & 15) == 0);
+    const bool vec = row_vec && G.ksplit == 1, vec_red = row_vec && G.ksplit > 1;
 #pragma unroll 1
     for (int c = 0; c < BN_ / 32; ++c) {
       uint32_t v[32];
@@ -218,6 +219,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
           }
           *q = o;
         }
+      } else if (vec_red && col0 + 32 <= G.N) {
+        // split-K partial sums: 128-bit reductions (red.global.add.v4.f32), a quarter of the atomic traffic
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                       "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                       : "memory");
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -623,10 +631,36 @@ int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* 
   }
   alignas(64) TmaGemmArgs G;
   memset(&G, 0, sizeof(G));
-  // 128-wide N tiles unless that leaves most SMs idle; split-K (memset + atomics) only if even 64-wide tiles do
+  // Tile width and split-K by a cost model.  The kernel is bound by what one SM can pull through the TMA unit
+  // (measured ~43 B/clk/SM = the chip's ~6300 B/clk L2 throughput / 148; a 128 x bn x 64 k-block costs 16 + bn/8 KB),
+  // so the time of a configuration is (waves of CTAs) x (k-blocks per CTA) x (bytes per k-block) / per-SM rate; split-K
+  // adds a memset launch and the reduction traffic of its partial tiles.
   const int64_t mtiles = (M + BM - 1) / BM;
-  int bn = N <= 64 ? 64 : 128;
-  if (bn == 128 && mtiles * ((N + 127) / 128) * batch < BB_SM_COUNT) bn = 64;
+  const int64_t kblocks = (K + BK - 1) / BK;
+  const bool can_split = batch == 1 && plane_ohw == 0 && (beta || out_dense) && kblocks >= 8;
+  int bn = 64, ksplit = 1;
+  {
+    double best = 1e30;
+    const int bn_opts[2] = {128, 64};
+    for (int bi = 0; bi < 2; ++bi) {
+      const int cand = bn_opts[bi];
+      if (cand == 128 && N <= 64) continue;
+      const int64_t tiles = mtiles * ((N + cand - 1) / cand) * batch;
+      for (int sp = 1; sp <= 256; sp = sp < 4 ? sp + 1 : sp * 2) {
+        if (sp > 1 && (!can_split || kblocks / sp < 4)) break;
+        const int64_t ctas = tiles * sp;
+        const int64_t waves = (ctas + BB_SM_COUNT - 1) / BB_SM_COUNT;
+        const int64_t iters = (kblocks + sp - 1) / sp * npairs;
+        double us = (double)waves * (double)iters * (16.0 + cand / 8.0) * 1024.0 / 84e3 + 2.0;   // 84 GB/s per SM
+        if (sp > 1) us += (beta ? 0.0 : 2.5) + (double)M * (double)N * 4.0 * sp / 2.0e6;          // ~2 TB/s of reductions
+        if (us < best) {
+          best = us;
+          bn = cand;
+          ksplit = sp;
+        }
+      }
+    }
+  }
   PackJobs J{};
   Prepared pa[2], pb[2];
   for (int p = 0; p < npairs; ++p) {
@@ -655,23 +689,9 @@ int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* 
   if (plane_ohw > 0) {
     G.omode = 2; G.OCH = (int)N; G.OHW = plane_ohw;
   }
-  const int64_t tiles = mtiles * ((N + bn - 1) / bn) * batch;
-  const int64_t kblocks = (K + BK - 1) / BK;
-  int ksplit = 1;
-  if (batch == 1 && 2 * tiles < BB_SM_COUNT && kblocks >= 16) {
-    int64_t want = (BB_SM_COUNT + tiles - 1) / tiles, maxs = kblocks / 8;
-    ksplit = (int)(want < maxs ? want : maxs);
-    if (ksplit > 2 * BB_SM_COUNT) ksplit = 2 * BB_SM_COUNT;
-    if (ksplit < 1) ksplit = 1;
-  }
-  if (plane_ohw > 0) ksplit = 1;
   if (ksplit > 1 && !beta) {
-    if (!out_dense) {
-      ksplit = 1;
-    } else {
-      BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * M * N, s));
-      bb_launch_tally += 1;
-    }
+    BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * M * N, s));
+    bb_launch_tally += 1;
   }
   G.ksplit = ksplit;
   return bb_gemm_tma_launch(G, bn, mtiles, s, (int)batch);

@@ -16,7 +16,29 @@ struct bb_plan {
   int launches[3] = {0, 0, 0};
   void* scratch = nullptr;      // bf16 operand packs of the TMA-fed tensor-core path (tma.h)
   int64_t scratch_bytes = 0;
+  uint8_t* persist = nullptr;   // plan-lifetime packs of K-loop constants, bump-allocated per node
+  int64_t persist_bytes = 0, persist_used = 0;
+  std::vector<void*> node_persist;
 };
+
+namespace {
+thread_local bb_plan* t_plan = nullptr;
+thread_local int t_node = -1;
+}  // namespace
+
+void* bb_persist_get(size_t bytes, bool* fresh) {
+  *fresh = false;
+  bb_plan* p = t_plan;
+  if (!p || !p->persist || t_node < 0 || t_node >= (int)p->node_persist.size()) return nullptr;
+  void*& slot = p->node_persist[t_node];
+  if (slot) return slot;
+  const int64_t at = (p->persist_used + 255) & ~(int64_t)255;
+  if (at + (int64_t)bytes > p->persist_bytes) return nullptr;
+  slot = p->persist + at;
+  p->persist_used = at + (int64_t)bytes;
+  *fresh = true;
+  return slot;
+}
 
 namespace {
 
@@ -72,17 +94,21 @@ int run_pass(bb_plan* p, int pass, cudaStream_t s) {
     bb_launch_tally += 1;
   }
   const int n = (int)p->nodes.size();
+  t_plan = p;
   if (pass == BB_PASS_TAN_FWD) {
     for (int i = 0; i < n; ++i) {
+      t_node = i;
       const int rc = dispatch(p->nodes[i], pass, s);
       if (rc) return rc;
     }
   } else {
     for (int i = n - 1; i >= 0; --i) {
+      t_node = i;
       const int rc = dispatch(p->nodes[i], pass, s);
       if (rc) return rc;
     }
   }
+  t_node = -1;
   p->launches[pass] = bb_launch_tally - tally0;
   return BB_OK;
 }
@@ -135,6 +161,7 @@ int bb_plan_create(const struct bb_node* nodes, int n_nodes, bb_plan** out) {
   if (!out || n_nodes < 0 || (n_nodes > 0 && !nodes)) return BB_ERR_ARG;
   bb_plan* p = new bb_plan();
   p->nodes.assign(nodes, nodes + n_nodes);
+  p->node_persist.assign((size_t)n_nodes, nullptr);
   *out = p;
   return BB_OK;
 }
@@ -155,6 +182,15 @@ int bb_plan_set_scratch(bb_plan* plan, void* ptr, int64_t bytes) {
   if (!plan || bytes < 0) return BB_ERR_ARG;
   plan->scratch = ptr;
   plan->scratch_bytes = bytes;
+  return BB_OK;
+}
+
+int bb_plan_set_persistent(bb_plan* plan, void* ptr, int64_t bytes) {
+  if (!plan || bytes < 0) return BB_ERR_ARG;
+  plan->persist = reinterpret_cast<uint8_t*>(ptr);
+  plan->persist_bytes = bytes;
+  plan->persist_used = 0;
+  plan->node_persist.assign(plan->nodes.size(), nullptr);
   return BB_OK;
 }
 
@@ -189,6 +225,8 @@ int bb_plan_profile(bb_plan* plan, int pass, float* ms_per_node, void* stream) {
   for (int j = 0; j < n && !rc; ++j) {
     const int i = (pass == BB_PASS_TAN_FWD) ? j : n - 1 - j;
     cudaEventRecord(ev[j], s);
+    t_plan = plan;
+    t_node = i;
     rc = dispatch(plan->nodes[i], pass, s);
     ms_per_node[i] = 0.f;
   }

@@ -28,6 +28,12 @@ inline void* bb_scratch_alloc(size_t bytes) {
   return bb_scratch.base + at;
 }
 
+// Per-node buffer that lives as long as the plan, for packs of operands that are constant across the K-loop (the
+// im2col matrix of a data-input convolution).  Returns nullptr when the plan has no persistent arena (or it is full);
+// *fresh = true means the caller has to fill it.  Filled eagerly in the base-backward pass (plan creation), so the
+// captured K-loop iterations only read it.
+void* bb_persist_get(size_t bytes, bool* fresh);
+
 // bf16 row-major matrix [rows][cols], `pitch` elements between rows (multiple of 8, base 16-byte aligned):
 // box = (64 columns, box_rows rows), SWIZZLE_128B.  Returns 0 or an error code.
 int bb_tma_map_2d(CUtensorMap* out, const void* p, int64_t rows, int64_t cols, int64_t pitch, int box_rows);

@@ -170,11 +170,27 @@ class HvpPlan:
             self.tma_scratch = torch.empty(need, dtype=torch.uint8, device=self.dev)
             N.call("bb_plan_set_scratch", self.handle, self.tma_scratch.data_ptr(), need)
 
+        persist = sum(self._tma_persistent_bytes(r) for r in recs)
+        if persist and need and not self.dry_run:
+            self.tma_persistent = torch.empty(persist, dtype=torch.uint8, device=self.dev)
+            N.call("bb_plan_set_persistent", self.handle, self.tma_persistent.data_ptr(), persist)
+
         zb = [self.A["z"]] if self.zero_bytes else []
         zt = ([self.AT["z"]] if self.zero_bytes else []) + [self.hv_arena]
         for pas, ts in ((PASS_BB, zb), (PASS_TF, []), (PASS_TB, zt)):
             ptrs, nb, cnt = regions(ts)
             N.call("bb_plan_set_zero_regions", self.handle, pas, ptrs, nb, cnt)
+
+    @staticmethod
+    def _tma_persistent_bytes(r) -> int:
+        """Plan-lifetime pack of a data-input convolution's im2col matrix (csrc/conv_tma.cu run_small_c)."""
+        if not (int(r["kind"]) & 1) or int(r["op"]) != OPS["conv2d"]:
+            return 0
+        Nn, Cc, H, W, O, KH, KW, HO, WO = (int(x) for x in r["dims"][0:9])
+        ckk, act = Cc * KH * KW, int(r["active"])
+        if not (act & 1) and (act & 2) and 8 <= ckk <= 64 and 32 <= O <= 128 and Nn * HO * WO >= 128:
+            return 2 * Nn * HO * WO * _align(ckk, 8) + 512
+        return 0
 
     @staticmethod
     def _tma_scratch_bytes(r) -> int:

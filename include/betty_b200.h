@@ -82,6 +82,9 @@ int bb_plan_set_zero_regions(bb_plan* plan, int pass, void* const* ptrs, const i
 /* device scratch for the bf16 operand packs of the TMA-fed tensor-core kernels (caller-owned, >= the largest
  * node's need; without it those nodes use the software-staged kernel) */
 int bb_plan_set_scratch(bb_plan* plan, void* ptr, int64_t bytes);
+/* device buffer that lives as long as the plan, for packs of K-loop constants (im2col matrix of a data-input
+ * convolution): filled once during BB_PASS_BASE_BWD, read by every iteration; optional */
+int bb_plan_set_persistent(bb_plan* plan, void* ptr, int64_t bytes);
 int bb_plan_run(bb_plan* plan, int pass, void* stream);
 int bb_plan_launch_count(const bb_plan* plan, int pass);
 /* eager run of one pass with a CUDA event pair around every node: ms_per_node[n_nodes] */
