@@ -140,9 +140,17 @@ __global__ void __launch_bounds__(256) chansum_kernel(const float* __restrict__ 
   __shared__ float red[32];
   const int ch = blockIdx.x;
   float acc = 0.f;
+  const bool vec = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
   for (int img = blockIdx.y; img < NIMG; img += gridDim.y) {
     const float* src = g + ((int64_t)img * CH + ch) * HW;
-    for (int q = threadIdx.x; q < HW; q += blockDim.x) acc += src[q];
+    if (vec) {
+      for (int q = threadIdx.x * 4; q < HW; q += blockDim.x * 4) {
+        const float4 v = bb::ld4_stream(src + q);
+        acc += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+      for (int q = threadIdx.x; q < HW; q += blockDim.x) acc += src[q];
+    }
   }
   acc = bb::block_sum<float>(acc, red);
   if (threadIdx.x == 0) atomicAdd(out + ch, acc);
