@@ -347,6 +347,18 @@ def main():
                 "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": which}
         del a, b, c, d
 
+    # DRAM traffic of the dominant node from a committed `ncu --set full` capture of the same workload (sum of
+    # dram__bytes_read.sum + dram__bytes_write.sum over the node's kernels, per launch), when one exists
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            tr = json.load(f).get(args.workload, {})
+        for key, rec in tr.items():
+            if roof.get("kernel", "").startswith(key):
+                roof["traffic"] = rec["bytes"]
+                roof["traffic_source"] = rec["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+
     line = {
         "metric": "HVP-iters/sec", "value": value, "unit": "HVP-iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
