@@ -263,11 +263,31 @@ bool bb_conv_tma_ok(const bb_node& nd, int pass) {
   return true;
 }
 
+// NHWC bf16 pack of a K-loop constant (slot 0: the layer input x, slot 1: the base output adjoint a_y) in the plan's
+// persistent arena; nullptr if there is none.  Packed on first use, which bb_conv_tma_prepare makes the eager
+// base-backward pass.
+void* const_nhwc(const void* src, int dt, int N, int C, int HW, int slot, cudaStream_t s, int* rc) {
+  bool fresh = false;
+  void* p = bb_persist_get((size_t)N * HW * 64 * 2, &fresh, slot);
+  *rc = BB_OK;
+  if (p && fresh) *rc = bb_pack_nhwc(src, dt, N, C, HW, p, 64, s);
+  return p;
+}
+
 int bb_conv_tma_prepare(const bb_node& nd, cudaStream_t s) {
   static const bool off = getenv("BB200_NO_TMA") != nullptr || getenv("BB200_NO_TC") != nullptr;
-  if (off || !(nd.kind & 1) || bb_scratch.base == nullptr || !small_c_ok(nd)) return BB_OK;
-  const int rc = run_small_c(nd, BB_PASS_BASE_BWD, s);
-  return rc == BB_DECLINED ? BB_OK : rc;
+  if (off || !(nd.kind & 1) || bb_scratch.base == nullptr) return BB_OK;
+  if (small_c_ok(nd)) {
+    const int rc = run_small_c(nd, BB_PASS_BASE_BWD, s);
+    return rc == BB_DECLINED ? BB_OK : rc;
+  }
+  if (!bb_conv_tma_ok(nd, BB_PASS_TAN_BWD)) return BB_OK;
+  // called at the node's base-backward visit: x is a base value, a_y (nd.a[3]) is final by now
+  int rc = BB_OK;
+  if (nd.active & 2) const_nhwc(nd.base[0], nd.dt[0], (int)nd.dims[0], (int)nd.dims[1], (int)(nd.dims[2] * nd.dims[3]), 0, s, &rc);
+  if (rc) return rc;
+  const_nhwc(nd.a[3], BB_F32, (int)nd.dims[0], (int)nd.dims[4], (int)(nd.dims[7] * nd.dims[8]), 1, s, &rc);
+  return rc;
 }
 
 size_t bb_conv_tma_scratch(const bb_node& nd) {
@@ -303,10 +323,14 @@ int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
       src[np] = a; wm[np] = w; ++np;
     }
     if (actW) {
-      void* a = bb_scratch_alloc(in_bytes);
+      void* a = const_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, 0, s, &rc);
+      if (rc) return rc;
       void* w = bb_scratch_alloc(w_bytes);
+      if (!a) {
+        a = bb_scratch_alloc(in_bytes);
+        if (a && (rc = bb_pack_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, a, 64, s))) return rc;
+      }
       if (!a || !w) return BB_DECLINED;
-      if ((rc = bb_pack_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, a, 64, s))) return rc;
       if ((rc = bb_pack_convw(nd.t[1], BB_F32, g.O, g.C, taps, 0, w, 64, s))) return rc;
       src[np] = a; wm[np] = w; ++np;
     }
@@ -317,11 +341,19 @@ int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
   // ---- tangent backward ----
   const int need = nd.active;
   void* gy = bb_scratch_alloc(out_bytes);     // at_y
-  void* ay = bb_scratch_alloc(out_bytes);     // a_y
-  if (!gy || !ay) return BB_DECLINED;
+  if (!gy) return BB_DECLINED;
   if ((rc = bb_pack_nhwc(nd.at[3], BB_F32, g.N, g.O, g.HO * g.WO, gy, 64, s))) return rc;
   const bool need_ay = ((need & 1) && actW) || ((need & 2) && actX);
-  if (need_ay && (rc = bb_pack_nhwc(nd.a[3], BB_F32, g.N, g.O, g.HO * g.WO, ay, 64, s))) return rc;
+  void* ay = nullptr;                         // a_y: a K-loop constant
+  if (need_ay) {
+    ay = const_nhwc(nd.a[3], BB_F32, g.N, g.O, g.HO * g.WO, 1, s, &rc);
+    if (rc) return rc;
+    if (!ay) {
+      ay = bb_scratch_alloc(out_bytes);
+      if (!ay) return BB_DECLINED;
+      if ((rc = bb_pack_nhwc(nd.a[3], BB_F32, g.N, g.O, g.HO * g.WO, ay, 64, s))) return rc;
+    }
+  }
   if (need & 1) {
     const void* src[2];
     const void* wm[2];
@@ -343,9 +375,13 @@ int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
   if (need & 2) {
     alignas(64) WgradArgs A;
     memset(&A, 0, sizeof(A));
-    void* xs = bb_scratch_alloc(in_bytes);
-    if (!xs) return BB_DECLINED;
-    if ((rc = bb_pack_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, xs, 64, s))) return rc;
+    void* xs = const_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, 0, s, &rc);
+    if (rc) return rc;
+    if (!xs) {
+      xs = bb_scratch_alloc(in_bytes);
+      if (!xs) return BB_DECLINED;
+      if ((rc = bb_pack_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, xs, 64, s))) return rc;
+    }
     const int Hb = g.HO < 64 / g.WO ? g.HO : 64 / g.WO;
     int np = 0;
     if ((rc = bb_tma_map_nhwc(&A.x[np], xs, g.N, g.H, g.W, 64, g.WO, Hb))) return rc;

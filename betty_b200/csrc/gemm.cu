@@ -233,17 +233,31 @@ int bb_launch_gemm(const bb_node& nd, int pass, cudaStream_t s) {
   const Mat gC{base ? nd.a[3] : nd.at[3], BB_F32, sc[0], sc[1], sc[2]};   // adjoint being propagated
   const Mat aC{nd.a[3], BB_F32, sc[0], sc[1], sc[2]};                      // base adjoint (curvature terms)
   const int need = base ? nd.pad0 : nd.active;                              // pad0 = need_a mask
-  if (need & 1) {  // (M x K) = gC (M x N) . B^T (N x K)  [+ aC . tB^T]
-    Mat L[2] = {gC, aC}, R[2] = {T(B), T(tB)};
-    const int np = (!base && actB) ? 2 : 1;
-    rc = run_gemm(M, K, N, batch, np, L, R, reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]), sa[0], sa[1], sa[2],
+  Mat Ld[2] = {gC, aC}, Rd[2] = {T(B), T(tB)};        // (M x K) = gC (M x N) . B^T (N x K)  [+ aC . tB^T]
+  Mat Lw[2] = {T(A), T(tA)}, Rw[2] = {gC, aC};        // (K x N) = A^T (K x M) . gC (M x N)  [+ tA^T . aC]
+  const int npd = (!base && actB) ? 2 : 1, npw = (!base && actA) ? 2 : 1;
+  if (tc && !base && batch == 1 && M >= 64 && N >= 64 && K >= 64 && (need & 3) == 3 && !getenv("BB200_NO_TMA")) {
+    // tensor-core route: pack the operands of BOTH products in one launch (the adjoints are shared between them)
+    TmaPackReq rq[8];
+    int nr = 0;
+    for (int p = 0; p < npd; ++p) {
+      rq[nr++] = TmaPackReq{TmaView{Ld[p].p, Ld[p].dt, Ld[p].rs, Ld[p].cs}, M, N};
+      rq[nr++] = TmaPackReq{TmaView{Rd[p].p, Rd[p].dt, Rd[p].cs, Rd[p].rs}, K, N};
+    }
+    for (int p = 0; p < npw; ++p) {
+      rq[nr++] = TmaPackReq{TmaView{Lw[p].p, Lw[p].dt, Lw[p].rs, Lw[p].cs}, K, M};
+      rq[nr++] = TmaPackReq{TmaView{Rw[p].p, Rw[p].dt, Rw[p].cs, Rw[p].rs}, N, M};
+    }
+    rc = bb_gemm_tma_prepack(rq, nr, 1, s);
+    if (rc) return rc;
+  }
+  if (need & 1) {
+    rc = run_gemm(M, K, N, batch, npd, Ld, Rd, reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]), sa[0], sa[1], sa[2],
                   nd.beta[0], nullptr, 0, s, tc);
     if (rc) return rc;
   }
-  if (need & 2) {  // (K x N) = A^T (K x M) . gC (M x N)  [+ tA^T . aC]
-    Mat L[2] = {T(A), T(tA)}, R[2] = {gC, aC};
-    const int np = (!base && actA) ? 2 : 1;
-    rc = run_gemm(K, N, M, batch, np, L, R, reinterpret_cast<float*>(base ? nd.a[1] : nd.at[1]), sb[0], sb[1], sb[2],
+  if (need & 2) {
+    rc = run_gemm(K, N, M, batch, npw, Lw, Rw, reinterpret_cast<float*>(base ? nd.a[1] : nd.at[1]), sb[0], sb[1], sb[2],
                   nd.beta[1], nullptr, 0, s, tc);
     if (rc) return rc;
   }

@@ -609,6 +609,24 @@ int bb_gemm_tma_launch(TmaGemmArgs& G, int bn, int64_t mtiles, cudaStream_t s, i
   return bn == 64 ? launch_tma<64>(G, mtiles, s, batch) : launch_tma<128>(G, mtiles, s, batch);
 }
 
+int bb_gemm_tma_prepack(const TmaPackReq* reqs, int n, int64_t batch, cudaStream_t s) {
+  if (encode_fn() == nullptr || bb_scratch.base == nullptr) return BB_OK;
+  PackJobs J{};
+  for (int i = 0; i < n; ++i) {
+    const size_t need = pack_bytes(reqs[i].v, reqs[i].rows, reqs[i].k, batch);
+    if (need == 0) continue;
+    if (bb_scratch.used + need + 512 > bb_scratch.bytes) break;   // the products will decline or pack on their own
+    Prepared pr;
+    if (prepare_operand(J, reqs[i].v, reqs[i].rows, reqs[i].k, batch, &pr) != BB_OK) break;
+    if (J.n == 4) {
+      const int rc = flush_packs(J, s);
+      if (rc) return rc;
+      J.n = 0;
+    }
+  }
+  return flush_packs(J, s);
+}
+
 int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* A, const TmaView* B, float* out,
                     int64_t ors, int64_t ocs, int beta, const float* bias, int64_t bias_stride, bool out_dense,
                     cudaStream_t s, int plane_ohw, int min_n, int64_t batch, int64_t obs) {

@@ -23,6 +23,15 @@ int bb_gemm_tma_run(int64_t M, int64_t N, int64_t K, int npairs, const TmaView* 
                     int64_t ors, int64_t ocs, int beta, const float* bias, int64_t bias_stride, bool out_dense,
                     cudaStream_t s, int plane_ohw = 0, int min_n = 64, int64_t batch = 1, int64_t obs = 0);
 
+// Pack, in as few launches as possible (four operands per launch), every listed view that is not TMA-addressable as
+// it stands; the bb_gemm_tma_run calls of the same node then find the packs in the per-node cache.  rows / k as in
+// bb_gemm_tma_run (A: rows = M, B: rows = N).
+struct TmaPackReq {
+  TmaView v;
+  int64_t rows, k;
+};
+int bb_gemm_tma_prepack(const TmaPackReq* reqs, int n, int64_t batch, cudaStream_t s);
+
 enum { TMA_KMAJ = 0, TMA_MNMAJ = 1, TMA_CONV = 2 };
 
 struct alignas(64) TmaGemmArgs {

@@ -26,11 +26,13 @@ thread_local bb_plan* t_plan = nullptr;
 thread_local int t_node = -1;
 }  // namespace
 
-void* bb_persist_get(size_t bytes, bool* fresh) {
+void* bb_persist_get(size_t bytes, bool* fresh, int slot_id) {
   *fresh = false;
   bb_plan* p = t_plan;
-  if (!p || !p->persist || t_node < 0 || t_node >= (int)p->node_persist.size()) return nullptr;
-  void*& slot = p->node_persist[t_node];
+  if (!p || !p->persist || t_node < 0 || slot_id < 0 || slot_id >= BB_PERSIST_SLOTS) return nullptr;
+  const size_t at_slot = (size_t)t_node * BB_PERSIST_SLOTS + slot_id;
+  if (at_slot >= p->node_persist.size()) return nullptr;
+  void*& slot = p->node_persist[at_slot];
   if (slot) return slot;
   const int64_t at = (p->persist_used + 255) & ~(int64_t)255;
   if (at + (int64_t)bytes > p->persist_bytes) return nullptr;
@@ -161,7 +163,7 @@ int bb_plan_create(const struct bb_node* nodes, int n_nodes, bb_plan** out) {
   if (!out || n_nodes < 0 || (n_nodes > 0 && !nodes)) return BB_ERR_ARG;
   bb_plan* p = new bb_plan();
   p->nodes.assign(nodes, nodes + n_nodes);
-  p->node_persist.assign((size_t)n_nodes, nullptr);
+  p->node_persist.assign((size_t)n_nodes * BB_PERSIST_SLOTS, nullptr);
   *out = p;
   return BB_OK;
 }
@@ -190,7 +192,7 @@ int bb_plan_set_persistent(bb_plan* plan, void* ptr, int64_t bytes) {
   plan->persist = reinterpret_cast<uint8_t*>(ptr);
   plan->persist_bytes = bytes;
   plan->persist_used = 0;
-  plan->node_persist.assign(plan->nodes.size(), nullptr);
+  plan->node_persist.assign(plan->nodes.size() * BB_PERSIST_SLOTS, nullptr);
   return BB_OK;
 }
 

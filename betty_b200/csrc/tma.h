@@ -32,7 +32,8 @@ inline void* bb_scratch_alloc(size_t bytes) {
 // im2col matrix of a data-input convolution).  Returns nullptr when the plan has no persistent arena (or it is full);
 // *fresh = true means the caller has to fill it.  Filled eagerly in the base-backward pass (plan creation), so the
 // captured K-loop iterations only read it.
-void* bb_persist_get(size_t bytes, bool* fresh);
+void* bb_persist_get(size_t bytes, bool* fresh, int slot = 0);   // slot: 0..BB_PERSIST_SLOTS-1 per node
+#define BB_PERSIST_SLOTS 4
 
 // bf16 row-major matrix [rows][cols], `pitch` elements between rows (multiple of 8, base 16-byte aligned):
 // box = (64 columns, box_rows rows), SWIZZLE_128B.  Returns 0 or an error code.

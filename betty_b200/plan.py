@@ -190,6 +190,9 @@ class HvpPlan:
         ckk, act = Cc * KH * KW, int(r["active"])
         if not (act & 1) and (act & 2) and 8 <= ckk <= 64 and 32 <= O <= 128 and Nn * HO * WO >= 128:
             return 2 * Nn * HO * WO * _align(ckk, 8) + 512
+        unit = all(int(x) == 1 for x in (r["dims"][9], r["dims"][10], r["dims"][13], r["dims"][14]))
+        if unit and KH * KW <= 9 and 32 <= Cc <= 64 and 32 <= O <= 64 and 4 <= WO <= 64 and W <= 128:
+            return 2 * 64 * Nn * (H * W + HO * WO) + 1024      # NHWC bf16 packs of x and of the base adjoint a_y
         return 0
 
     @staticmethod
