@@ -247,6 +247,205 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant for launches with many more tiles than SMs (convolutions: one tile per 128 pixels).  A CTA
+// walks tiles blockIdx.x, +gridDim.x, ...; the TMA producer and the MMA warp run ahead across tile boundaries on the
+// same stage ring, and the accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i
+// (tcgen05.ld + global stores) overlaps the loads and MMAs of tile i+1.  The one-tile-per-CTA kernel above pays
+// barrier init + TMEM allocation + a cold TMA round trip per tile (~4-8 us for a 1-9 k-block tile).
+//   barriers: full[S] / empty[S] (stage ring), acc_full[2] (MMA -> epilogue), acc_empty[2] (4 epilogue warps -> MMA)
+// No split-K, no batch (conv and plane-output GEMMs only).
+template <int BN_>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_persist_kernel(const __grid_constant__ TmaGemmArgs G, int ntiles_n,
+                                                                       int total_tiles) {
+  using C = Cfg<BN_>;
+  const int STAGES = G.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStage);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t accf0 = smem_u32(bars + 2 * MAX_STAGES), acce0 = smem_u32(bars + 2 * MAX_STAGES + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = (int)((G.K + BK - 1) / BK);
+  const int per_tile = nkb * G.npairs;
+  const bool conv = G.a_kind[0] == TMA_CONV;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf0 + 8 * b, 1);
+      mbar_init(acce0 + 8 * b, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * BN_));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int p = 0; p < G.npairs; ++p) {
+        tma_prefetch_desc(&G.a[p]);
+        tma_prefetch_desc(&G.b[p]);
+      }
+      int git = 0;   // stage-ring position, continues across tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN_;
+        int m0 = 0, img = 0, h0 = 0;
+        if (conv) {
+          img = mt / G.tiles_per_img;
+          h0 = (mt - img * G.tiles_per_img) * G.Hb;
+        } else {
+          m0 = mt * BM;
+        }
+        for (int it = 0; it < per_tile; ++it, ++git) {
+          const int s = git % STAGES;
+          if (git >= STAGES) mbar_wait(empty0 + 8 * s, ((git / STAGES) - 1) & 1);
+          const int pair = it / nkb, kb = it - pair * nkb, k0 = kb * BK;
+          const uint32_t bar = full0 + 8 * s;
+          const uint32_t sa = smem_u32(smem + s * C::kStage), sb = sa + A_TILE;
+          mbar_expect_tx(bar, G.a_bytes + G.b_bytes);
+          const int ak = G.a_kind[pair];
+          if (ak == TMA_KMAJ) {
+            tma_load_3d(sa, &G.a[pair], bar, k0, m0, 0);
+          } else if (ak == TMA_MNMAJ) {
+            tma_load_3d(sa, &G.a[pair], bar, m0, k0, 0);
+            tma_load_3d(sa + 8192, &G.a[pair], bar, m0 + 64, k0, 0);
+          } else {
+            const int tap = kb / G.cblocks, cb = kb - tap * G.cblocks;
+            const int i = tap / G.KW, j = tap - i * G.KW;
+            const int dy = G.flip ? G.ph - i : i - G.ph, dx = G.flip ? G.pw - j : j - G.pw;
+            tma_load_4d(sa, &G.a[pair], bar, cb * 64, dx, h0 + dy, img);
+          }
+          if (G.b_kind[pair] == TMA_KMAJ) {
+            tma_load_3d(sb, &G.b[pair], bar, k0, n0, 0);
+          } else {
+#pragma unroll
+            for (int q = 0; q < BN_ / 64; ++q) tma_load_3d(sb + q * 8192, &G.b[pair], bar, n0 + q * 64, k0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      int git = 0, lt = 0;   // lt = this CTA's tile counter
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        if (lt >= 2) {   // the epilogue must have drained this accumulator (tile lt-2)
+          mbar_wait(acce0 + 8 * buf, ((lt >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN_);
+        for (int it = 0; it < per_tile; ++it, ++git) {
+          const int s = git % STAGES;
+          const int pair = it / nkb;
+          const bool a_mn = G.a_kind[pair] == TMA_MNMAJ, b_mn = G.b_kind[pair] == TMA_MNMAJ;
+          const uint32_t idesc = idesc_bf16(BM, BN_, a_mn, b_mn);
+          mbar_wait(full0 + 8 * s, (git / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * C::kStage), b_addr = a_addr + A_TILE;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = a_mn ? desc_mn(a_addr + k * 2048, 8192) : desc_k(a_addr + k * 32);
+            const uint64_t db = b_mn ? desc_mn(b_addr + k * 2048, 8192) : desc_k(b_addr + k * 32);
+            umma_bf16(tacc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(accf0 + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const bool vec = G.omode == 0 && G.ocs == 1 && (G.ors & 3) == 0 && ((reinterpret_cast<uintptr_t>(G.out) & 15) == 0);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN_;
+      bool row_ok;
+      int64_t row_base, col_stride;
+      if (G.omode == 1) {
+        const int img = mt / G.tiles_per_img, h0 = (mt - img * G.tiles_per_img) * G.Hb;
+        const int64_t q = (int64_t)h0 * G.Wb + r;
+        row_ok = r < G.Wb * G.Hb && q < G.OHW;
+        row_base = (int64_t)img * G.OCH * G.OHW + q;
+        col_stride = G.OHW;
+      } else if (G.omode == 2) {
+        const int64_t row = (int64_t)mt * BM + r;
+        row_ok = row < G.M;
+        const int64_t im = row / G.OHW;
+        row_base = im * G.OCH * G.OHW + (row - im * G.OHW);
+        col_stride = G.OHW;
+      } else {
+        const int64_t row = (int64_t)mt * BM + r;
+        row_ok = row < G.M;
+        row_base = row * G.ors;
+        col_stride = G.ocs;
+      }
+      mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1, 60);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN_ / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN_ + c * 32), v);
+        if (c == BN_ / 32 - 1) {   // last read of this accumulator: hand it back to the MMA warp before storing
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+        }
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= G.N) continue;
+        float* dst = G.out + row_base + (int64_t)col0 * col_stride;
+        if (G.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < G.N) v[j] = __float_as_uint(__uint_as_float(v[j]) + G.bias[(int64_t)(col0 + j) * G.bias_stride]);
+        }
+        if (vec && col0 + 32 <= G.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            float4* q = reinterpret_cast<float4*>(dst + j);
+            if (G.beta) {
+              const float4 old = *q;
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *q = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < G.N) {
+              const float o = __uint_as_float(v[j]);
+              float* q = dst + (int64_t)j * col_stride;
+              *q = G.beta ? *q + o : o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)(2 * BN_));
+  }
+}
+
 template <int BN_>
 int launch_tma(TmaGemmArgs& G, int64_t mtiles, cudaStream_t s, int batch) {
   using C = Cfg<BN_>;
@@ -264,6 +463,20 @@ int launch_tma(TmaGemmArgs& G, int64_t mtiles, cudaStream_t s, int batch) {
   const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
   G.stages = ctas <= BB_SM_COUNT ? C::kStagesDeep : C::kStagesShared;
   if (forced >= 2 && forced <= C::kStagesDeep) G.stages = forced;
+  static const bool no_persist = getenv("BB200_TMA_NO_PERSIST") != nullptr;
+  if (!no_persist && G.ksplit == 1 && batch == 1 && ctas > 4 * BB_SM_COUNT) {
+    static bool configured_p = false;
+    if (!configured_p) {
+      BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tma_persist_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::smem(C::kStagesDeep)));
+      configured_p = true;
+    }
+    G.stages = C::kStagesShared;
+    gemm_tma_persist_kernel<BN_><<<2 * BB_SM_COUNT, NTHREADS, C::smem(G.stages), s>>>(G, (int)grid.x, (int)(grid.x * grid.y));
+    bb_launch_tally += 1;
+    BB_LAUNCH_CHECK();
+    return BB_OK;
+  }
   gemm_tma_kernel<BN_><<<grid, NTHREADS, C::smem(G.stages), s>>>(G);
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();
