@@ -55,6 +55,83 @@ struct Cfg {
   static constexpr size_t smem(int stages) { return (size_t)stages * kStage + 1024 + 256; }
 };
 
+// Epilogue store of one 32-column chunk of a thread's accumulator row.  Written for a low instruction count: the
+// epilogue warps are four single warps per CTA, so their time is (instructions x dependent-issue latency), not
+// bandwidth -- the first version spent ~30 integer instructions per stored value on 64-bit index arithmetic and
+// per-element predicates (ncu source page: 7.7 us per 128x64 tile, see profiles/r01_persist_ncu.md).  Here every mode
+// decision is made once per chunk and addresses advance by pointer increments.
+__device__ __forceinline__ void epi_store(const TmaGemmArgs& G, uint32_t (&v)[32], float* dst, int64_t col_stride, int col0,
+                                          bool add_bias, bool vec, bool vec_red) {
+  const int ncols = (G.N - col0) < 32 ? (int)(G.N - col0) : 32;
+  const bool full = ncols == 32;
+  if (add_bias) {
+    const float* bp = G.bias + (int64_t)col0 * G.bias_stride;
+    if (full && G.bias_stride == 1 && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bp + j);
+        v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
+        v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
+        v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
+        v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] = __float_as_uint(__uint_as_float(v[j]) + bp[(int64_t)j * G.bias_stride]);
+    }
+  }
+  if (full && vec) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                             __uint_as_float(v[j + 3]));
+      float4* q = reinterpret_cast<float4*>(dst + j);
+      if (G.beta) {
+        const float4 old = *q;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *q = o;
+    }
+    return;
+  }
+  if (full && vec_red) {
+    // split-K partial sums: 128-bit reductions (red.global.add.v4.f32), a quarter of the atomic traffic
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                   "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                   : "memory");
+    return;
+  }
+  float* q = dst;
+  if (G.ksplit > 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) atomicAdd(q, __uint_as_float(v[j]));
+      q += col_stride;
+    }
+  } else if (G.beta) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) *q += __uint_as_float(v[j]);
+      q += col_stride;
+    }
+  } else if (full) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      *q = __uint_as_float(v[j]);
+      q += col_stride;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) *q = __uint_as_float(v[j]);
+      q += col_stride;
+    }
+  }
+}
+
 template <int BN_>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_constant__ TmaGemmArgs G) {
   using C = Cfg<BN_>;
@@ -201,42 +278,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
       if (!row_ok) continue;
       const int col0 = n0 + c * 32;
       if (col0 >= G.N) continue;
-      if (G.bias != nullptr && split == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < G.N) v[j] = __float_as_uint(__uint_as_float(v[j]) + G.bias[(int64_t)(col0 + j) * G.bias_stride]);
-      }
-      float* dst = G.out + row_base + (int64_t)col0 * col_stride;
-      if (vec && col0 + 32 <= G.N) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          float4* q = reinterpret_cast<float4*>(dst + j);
-          if (G.beta) {
-            const float4 old = *q;
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          *q = o;
-        }
-      } else if (vec_red && col0 + 32 <= G.N) {
-        // split-K partial sums: 128-bit reductions (red.global.add.v4.f32), a quarter of the atomic traffic
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
-                       "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                       : "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (col0 + j < G.N) {
-            float* q = dst + (int64_t)j * col_stride;
-            const float o = __uint_as_float(v[j]);
-            if (G.ksplit > 1) atomicAdd(q, o);
-            else *q = G.beta ? *q + o : o;
-          }
-        }
-      }
+      epi_store(G, v, G.out + row_base + (int64_t)col0 * col_stride, col_stride, col0, G.bias != nullptr && split == 0, vec,
+                vec_red);
     }
   }
   tc_fence_before();
@@ -407,34 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_persist_kernel(const __g
         }
         const int col0 = n0 + c * 32;
         if (!row_ok || col0 >= G.N) continue;
-        float* dst = G.out + row_base + (int64_t)col0 * col_stride;
-        if (G.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < G.N) v[j] = __float_as_uint(__uint_as_float(v[j]) + G.bias[(int64_t)(col0 + j) * G.bias_stride]);
-        }
-        if (vec && col0 + 32 <= G.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            float4* q = reinterpret_cast<float4*>(dst + j);
-            if (G.beta) {
-              const float4 old = *q;
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            *q = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < G.N) {
-              const float o = __uint_as_float(v[j]);
-              float* q = dst + (int64_t)j * col_stride;
-              *q = G.beta ? *q + o : o;
-            }
-          }
-        }
+        epi_store(G, v, G.out + row_base + (int64_t)col0 * col_stride, col_stride, col0, G.bias != nullptr, vec, false);
       }
     }
   }
