@@ -152,20 +152,42 @@ __global__ void emb_bwd_kernel(float* gw, const int64_t* __restrict__ idx, const
 }
 
 // ---- max-pool: gather / scatter with the base argmax ---------------------------------------------------
+// relu != 0: a ReLU in front of the pool was folded into the node (ir._fuse_relu_maxpool): its derivative at the
+// arg-max position is [pooled base output y > 0]
 __global__ void pool_fwd_kernel(const float* __restrict__ tx, const int64_t* __restrict__ idx, float* ty, int64_t nout,
-                                int hw_in, int hw_out) {
+                                int hw_in, int hw_out, const void* __restrict__ y, int dty, int relu) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nout) return;
   const int64_t plane = i / hw_out;
-  ty[i] = tx[plane * hw_in + idx[i]];
+  float v = tx[plane * hw_in + idx[i]];
+  if (relu && !(bb::ldf(y, i, dty) > 0.f)) v = 0.f;
+  ty[i] = v;
 }
-
 __global__ void pool_bwd_kernel(float* gx, const int64_t* __restrict__ idx, const float* __restrict__ gy, int64_t nout,
-                                int hw_in, int hw_out) {
+                                int hw_in, int hw_out, const void* __restrict__ y, int dty, int relu) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nout) return;
+  if (relu && !(bb::ldf(y, i, dty) > 0.f)) return;
   const int64_t plane = i / hw_out;
   atomicAdd(gx + plane * hw_in + idx[i], gy[i]);  // gx is zeroed at the start of the pass
+}
+// Disjoint windows (kernel == stride, no padding): one thread per INPUT position looks up its window's arg-max and
+// writes its own adjoint -- every position exactly once, so no zero-fill of the buffer and no atomics.
+__global__ void pool_bwd_gather_kernel(float* gx, const int64_t* __restrict__ idx, const float* __restrict__ gy, int64_t nin,
+                                       int H, int W, int HO, int WO, int kh, int kw, const void* __restrict__ y, int dty,
+                                       int relu, int beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nin) return;
+  const int hw = H * W;
+  const int64_t plane = i / hw;
+  const int q = (int)(i - plane * hw), h = q / W, w = q - h * W;
+  const int ho = h / kh, wo = w / kw;
+  float v = 0.f;
+  if (ho < HO && wo < WO) {
+    const int64_t o = plane * ((int64_t)HO * WO) + (int64_t)ho * WO + wo;
+    if (idx[o] == q && !(relu && !(bb::ldf(y, o, dty) > 0.f))) v = gy[o];
+  }
+  gx[i] = beta ? gx[i] + v : v;
 }
 
 // ---- average pooling (linear; count_include_pad, floor mode) ------------------------------------------
@@ -304,14 +326,23 @@ int bb_launch_maxpool2d(const bb_node& nd, int pass, cudaStream_t s) {
   const int64_t nout = planes * hw_out;
   const int64_t* idx = reinterpret_cast<const int64_t*>(nd.aux[0]);
   if (nout <= 0) return BB_OK;
+  const int relu = nd.kind & 1, disjoint = (nd.kind >> 1) & 1;
   if (pass == BB_PASS_TAN_FWD) {
     pool_fwd_kernel<<<blocks(nout, 256), 256, 0, s>>>(reinterpret_cast<const float*>(nd.t[0]), idx,
-                                                      reinterpret_cast<float*>(nd.t[3]), nout, hw_in, hw_out);
+                                                      reinterpret_cast<float*>(nd.t[3]), nout, hw_in, hw_out, nd.base[3],
+                                                      nd.dt[3], relu);
   } else {
     const bool base = pass == BB_PASS_BASE_BWD;
-    pool_bwd_kernel<<<blocks(nout, 256), 256, 0, s>>>(reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]), idx,
-                                                      reinterpret_cast<const float*>(base ? nd.a[3] : nd.at[3]), nout,
-                                                      hw_in, hw_out);
+    float* gx = reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]);
+    const float* gy = reinterpret_cast<const float*>(base ? nd.a[3] : nd.at[3]);
+    if (disjoint) {
+      const int64_t nin = planes * hw_in;
+      pool_bwd_gather_kernel<<<blocks(nin, 256), 256, 0, s>>>(gx, idx, gy, nin, (int)nd.dims[3], (int)nd.dims[4],
+                                                              (int)nd.dims[5], (int)nd.dims[6], (int)nd.dims[7],
+                                                              (int)nd.dims[8], nd.base[3], nd.dt[3], relu, nd.beta[0]);
+    } else {
+      pool_bwd_kernel<<<blocks(nout, 256), 256, 0, s>>>(gx, idx, gy, nout, hw_in, hw_out, nd.base[3], nd.dt[3], relu);
+    }
   }
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();

@@ -225,6 +225,7 @@ class _Lowering:
         g.native_epilogue_ok = self.native_epilogue_ok
         if fold_quadratic:
             _fold_quadratic_regularisers(g)
+        _fuse_relu_maxpool(g)
         _analyse(g)
         return g
 
@@ -297,7 +298,16 @@ class _Lowering:
             out, idx = op.out
             if not out.is_contiguous():
                 raise UnsupportedGraph("max_pool2d: non-contiguous output")
-            self.emit("maxpool2d", [x], out, name, indices=idx)
+            pair = lambda v, d: tuple(int(q) for q in (v if isinstance(v, (list, tuple)) and len(v) else d)) * (
+                2 if isinstance(v, (list, tuple)) and len(v) == 1 else 1)
+            kernel = pair(a[1], (1, 1))
+            stride = pair(a[2] if len(a) > 2 else [], kernel)
+            padding = pair(a[3] if len(a) > 3 else [], (0, 0))
+            dilation = pair(a[4] if len(a) > 4 else [], (1, 1))
+            # disjoint windows (kernel == stride, no padding / dilation): every input position belongs to at most
+            # one window, so the adjoint is a gather that writes each position exactly once (no zero-fill, no atomics)
+            disjoint = stride == kernel and padding == (0, 0) and dilation == (1, 1)
+            self.emit("maxpool2d", [x], out, name, indices=idx, kernel=kernel, disjoint=disjoint, relu=False)
             return
         if name in _BN_OPS:
             return self._batchnorm(op)
@@ -709,8 +719,8 @@ def _analyse(g: Graph):
             # slices (H.d arena) always accumulate into the arena zeroed at the start of the pass -- several
             # of their kernels are split-K / scatter kernels with atomics -- and so do max-pool / embedding
             # scatters.
-            single = (r.writers == 1 and v.chain_full_cover() and r.param_index is None
-                      and n.op not in ("embedding", "maxpool2d"))
+            scatter = n.op == "embedding" or (n.op == "maxpool2d" and not n.attrs.get("disjoint"))
+            single = r.writers == 1 and v.chain_full_cover() and r.param_index is None and not scatter
             if single:
                 n.beta.append(0)
             else:
@@ -723,6 +733,37 @@ def _analyse(g: Graph):
             b.zero_init = True    # read only by the epilogue; may have no node writer (folded proximal terms)
     g.stats = {**g.stats, "nodes": len(g.nodes), "values": sum(1 for v in g.values if v.parent is None and v.needed),
                "aliases": sum(1 for v in g.values if v.parent is not None)}
+
+
+def _fuse_relu_maxpool(g: Graph):
+    """ReLU feeding only a max-pool is folded into the pool node: the arg-max of relu(x) sits where x is largest,
+    so relu'(x[argmax]) = [pooled output > 0] and the pool rules become
+        TF  t_y = [y > 0] * t_x[argmax]        BB/TB  a_x[argmax] += [y > 0] * a_y
+    (relu'' = 0: no curvature term).  Removes a full-size element-wise pass over the pre-pool activation in each
+    direction -- the pool output is a quarter of it."""
+    consumers: Dict[int, int] = {}
+    for n in g.nodes:
+        for v in n.ins:
+            if v is not None:
+                consumers[id(v.root)] = consumers.get(id(v.root), 0) + 1
+    producer = {id(n.out): n for n in g.nodes if n.out is not None}
+    drop = set()
+    for p in g.nodes:
+        if p.op != "maxpool2d" or p.ins[0] is None or p.ins[0].parent is not None:
+            continue
+        x = p.ins[0]
+        r = producer.get(id(x))
+        if r is None or r.op != "unary" or r.attrs.get("kind") != "relu" or consumers.get(id(x), 0) != 1:
+            continue
+        src = r.ins[0]
+        if x is g.loss or x.boundary or src is None or tuple(src.shape) != tuple(x.shape) or not src.base.is_contiguous():
+            continue
+        p.ins[0] = src
+        p.attrs["relu"] = True
+        drop.add(id(r))
+    if drop:
+        g.nodes = [n for n in g.nodes if id(n) not in drop]
+        g.stats = {**g.stats, "relu_pool_fused": len(drop)}
 
 
 def lower_tape(tape, fold_quadratic: bool = True) -> Graph:

@@ -374,10 +374,13 @@ class HvpPlan:
         idx = n.attrs["indices"]
         Nn, Cc, H, W = x.base.shape
         _, _, HO, WO = n.out.base.shape
-        r["dims"][0:3] = (Nn * Cc, H * W, HO * WO)
+        kh, kw = n.attrs.get("kernel", (1, 1))
+        r["dims"][0:9] = (Nn * Cc, H * W, HO * WO, H, W, HO, WO, kh, kw)
+        # kind bit 0: ReLU folded in (mask = pooled base output > 0); bit 1: disjoint windows -> gather-form adjoint
+        r["kind"] = int(bool(n.attrs.get("relu"))) | (int(bool(n.attrs.get("disjoint"))) << 1)
         r["aux"][0] = self._const(idx, torch.int64).data_ptr()
         self._slot(r, 0, x, x.base)
-        self._slot(r, 3, n.out, None)
+        self._slot(r, 3, n.out, n.out.base)
 
     def _n_avgpool2d(self, n: Node, r):
         x = n.ins[0]

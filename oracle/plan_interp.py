@@ -322,12 +322,17 @@ class Interp:
         idx = n.attrs["indices"]
         t = self.buf(x, "t")
         N, C = t.shape[:2]
-        self.buf(n.out, "t").copy_(t.reshape(N, C, -1).gather(2, idx.reshape(N, C, -1)).reshape(idx.shape))
+        ty = t.reshape(N, C, -1).gather(2, idx.reshape(N, C, -1)).reshape(idx.shape)
+        if n.attrs.get("relu"):      # fused ReLU (ir._fuse_relu_maxpool): relu'(x[argmax]) = [pooled output > 0]
+            ty = ty * (n.out.base > 0).to(ty.dtype)
+        self.buf(n.out, "t").copy_(ty)
 
     def _bw_pool(self, n, kind):
         x = n.ins[0]
         idx = n.attrs["indices"]
         g = self.buf(n.out, kind)
+        if n.attrs.get("relu"):
+            g = g * (n.out.base > 0).to(g.dtype)
         N, C = g.shape[:2]
         z = torch.zeros(x.shape, dtype=self.dtype, device=g.device).reshape(N, C, -1)
         z.scatter_add_(2, idx.reshape(N, C, -1), g.reshape(N, C, -1))
