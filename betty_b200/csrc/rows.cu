@@ -171,23 +171,46 @@ __global__ void pool_bwd_kernel(float* gx, const int64_t* __restrict__ idx, cons
   const int64_t plane = i / hw_out;
   atomicAdd(gx + plane * hw_in + idx[i], gy[i]);  // gx is zeroed at the start of the pass
 }
-// Disjoint windows (kernel == stride, no padding): one thread per INPUT position looks up its window's arg-max and
-// writes its own adjoint -- every position exactly once, so no zero-fill of the buffer and no atomics.
-__global__ void pool_bwd_gather_kernel(float* gx, const int64_t* __restrict__ idx, const float* __restrict__ gy, int64_t nin,
-                                       int H, int W, int HO, int WO, int kh, int kw, const void* __restrict__ y, int dty,
-                                       int relu, int beta) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nin) return;
-  const int hw = H * W;
-  const int64_t plane = i / hw;
-  const int q = (int)(i - plane * hw), h = q / W, w = q - h * W;
-  const int ho = h / kh, wo = w / kw;
-  float v = 0.f;
-  if (ho < HO && wo < WO) {
-    const int64_t o = plane * ((int64_t)HO * WO) + (int64_t)ho * WO + wo;
-    if (idx[o] == q && !(relu && !(bb::ldf(y, o, dty) > 0.f))) v = gy[o];
+// Disjoint windows (kernel == stride, no padding): every input position belongs to at most one window, so the
+// adjoint needs no zero-fill of the buffer and no atomics.  One thread per WINDOW writes its kh x kw input positions
+// (the arg-max gets the adjoint, the others 0; 64-bit stores for 2-wide windows); the threads of the last window
+// column / row also clear the positions no window covers (odd H or W in floor mode).
+template <int KW>
+__global__ void __launch_bounds__(256) pool_bwd_window_kernel(float* gx, const int64_t* __restrict__ idx,
+                                                              const float* __restrict__ gy, int64_t nout, int H, int W, int HO,
+                                                              int WO, int kh, int kw_rt, const void* __restrict__ y, int dty,
+                                                              int relu, int beta) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nout) return;
+  const int kw = KW > 0 ? KW : kw_rt;
+  const int hwo = HO * WO;
+  const int64_t plane = o / hwo;
+  const int r = (int)(o - plane * hwo), ho = r / WO, wo = r - ho * WO;
+  const int am = (int)idx[o];                       // arg-max position inside the plane
+  float g = gy[o];
+  if (relu && !(bb::ldf(y, o, dty) > 0.f)) g = 0.f;
+  float* base = gx + plane * ((int64_t)H * W);
+  const int h0 = ho * kh, w0 = wo * kw;
+  const int wend = (wo == WO - 1) ? W : w0 + kw;    // last window column also covers the uncovered tail columns
+  const int hend = (ho == HO - 1) ? H : h0 + kh;
+  for (int h = h0; h < hend; ++h) {
+    float* row = base + (int64_t)h * W;
+    if (KW == 2 && wend == w0 + 2 && (W & 1) == 0) {
+      const int p = h * W + w0;
+      float2 v = make_float2(p == am ? g : 0.f, p + 1 == am ? g : 0.f);
+      float2* q = reinterpret_cast<float2*>(row + w0);
+      if (beta) {
+        const float2 old = *q;
+        v.x += old.x; v.y += old.y;
+      }
+      *q = v;
+    } else {
+      for (int w = w0; w < wend; ++w) {
+        const float v = (h * W + w == am) ? g : 0.f;
+        row[w] = beta ? row[w] + v : v;
+      }
+    }
   }
-  gx[i] = beta ? gx[i] + v : v;
 }
 
 // ---- average pooling (linear; count_include_pad, floor mode) ------------------------------------------
@@ -336,10 +359,14 @@ int bb_launch_maxpool2d(const bb_node& nd, int pass, cudaStream_t s) {
     float* gx = reinterpret_cast<float*>(base ? nd.a[0] : nd.at[0]);
     const float* gy = reinterpret_cast<const float*>(base ? nd.a[3] : nd.at[3]);
     if (disjoint) {
-      const int64_t nin = planes * hw_in;
-      pool_bwd_gather_kernel<<<blocks(nin, 256), 256, 0, s>>>(gx, idx, gy, nin, (int)nd.dims[3], (int)nd.dims[4],
-                                                              (int)nd.dims[5], (int)nd.dims[6], (int)nd.dims[7],
-                                                              (int)nd.dims[8], nd.base[3], nd.dt[3], relu, nd.beta[0]);
+      const int H = (int)nd.dims[3], W = (int)nd.dims[4], HO = (int)nd.dims[5], WO = (int)nd.dims[6];
+      const int kh = (int)nd.dims[7], kw = (int)nd.dims[8];
+      if (kw == 2)
+        pool_bwd_window_kernel<2><<<blocks(nout, 256), 256, 0, s>>>(gx, idx, gy, nout, H, W, HO, WO, kh, kw, nd.base[3],
+                                                                    nd.dt[3], relu, nd.beta[0]);
+      else
+        pool_bwd_window_kernel<0><<<blocks(nout, 256), 256, 0, s>>>(gx, idx, gy, nout, H, W, HO, WO, kh, kw, nd.base[3],
+                                                                    nd.dt[3], relu, nd.beta[0]);
     } else {
       pool_bwd_kernel<<<blocks(nout, 256), 256, 0, s>>>(gx, idx, gy, nout, hw_in, hw_out, nd.base[3], nd.dt[3], relu);
     }
