@@ -741,6 +741,10 @@ def _fuse_relu_maxpool(g: Graph):
         TF  t_y = [y > 0] * t_x[argmax]        BB/TB  a_x[argmax] += [y > 0] * a_y
     (relu'' = 0: no curvature term).  Removes a full-size element-wise pass over the pre-pool activation in each
     direction -- the pool output is a quarter of it."""
+    import os
+
+    if os.environ.get("BB200_NO_RELU_POOL"):
+        return
     consumers: Dict[int, int] = {}
     for n in g.nodes:
         for v in n.ins:

@@ -40,10 +40,16 @@ def _tolerance(rec, case):
     reference's fp32-vs-fp64 gap on the same input -- the SURVEY.md 8(c) protocol (CG on small un-shifted
     problems and the finite-difference method sit at 2e-5...5e-4 in the reference itself)."""
     if case not in _FLOOR:
-        w32 = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
         w64 = to_double(W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"]))
         fn = ref_port.METHODS[rec["method"]]
-        _FLOOR[case] = rel_l2(fn(w32.vector, w32.lower, w32.upper, False), fn(w64.vector, w64.lower, w64.upper, False))
+        want64 = fn(w64.vector, w64.lower, w64.upper, False)
+        # the fp32 reference is itself not run-to-run reproducible on a GPU (atomics in cuDNN / index_add backward):
+        # on the ill-conditioned cases one sample of its fp32-vs-fp64 gap ranges over 2e-5 ... 1e-3, so take three
+        gaps = []
+        for _ in range(3):
+            w32 = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
+            gaps.append(rel_l2(fn(w32.vector, w32.lower, w32.upper, False), want64))
+        _FLOOR[case] = max(gaps)
     return max(1e-4, 5 * _FLOOR[case])
 
 
