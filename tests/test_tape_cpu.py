@@ -146,3 +146,58 @@ def test_uncaptured_upper_dependence_disables_the_native_epilogue():
     wl.lower._training_step = step
     _, tape, _ = trace(wl)
     assert lower_tape(tape).native_epilogue_ok is False
+
+
+class _PoolNet(torch.nn.Module):
+    """conv -> relu -> max-pool variants for the ReLU->pool fold: `share` feeds the ReLU output to a second consumer
+    (the fold must not fire), `kernel`/`stride` choose disjoint (2,2), overlapping (3,2) or odd-size windows."""
+
+    def __init__(self, kernel, stride, share, size):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(2, 3, 3, padding=1)
+        self.kernel, self.stride, self.share = kernel, stride, share
+        ho = (size - kernel) // stride + 1
+        self.fc = torch.nn.Linear(3 * ho * ho, 4)
+        self.fc2 = torch.nn.Linear(3, 4)
+        self.size = size
+
+    def forward(self, x):
+        h = torch.relu(self.conv(x))
+        p = torch.nn.functional.max_pool2d(h, self.kernel, self.stride)
+        out = self.fc(p.flatten(1))
+        if self.share:   # second consumer of the ReLU output
+            out = out + self.fc2(torch.nn.functional.avg_pool2d(h, self.size).flatten(1))
+        return out
+
+
+@pytest.mark.parametrize("kernel,stride,share,size,fused", [(2, 2, False, 8, True), (2, 2, False, 7, True),
+                                                            (3, 2, False, 9, True), (2, 2, True, 8, False),
+                                                            (3, 3, False, 10, True)])
+def test_relu_maxpool_fold(kernel, stride, share, size, fused):
+    """ir._fuse_relu_maxpool: same H.v as autograd (fp64) whether or not the fold fires; disjoint windows get the
+    overwrite (beta = 0) window-form adjoint, overlapping ones keep the accumulate/scatter form."""
+    torch.manual_seed(0)
+    wl = to_double(W.mlp_reweight(device="cpu", batch=5))
+    net = _PoolNet(kernel, stride, share, size).double()
+    wl.lower.module = net
+    x = torch.randn(5, 2, size, size, dtype=torch.float64)
+    y = torch.randint(0, 4, (5,))
+    wl.lower.cur_batch = (x, y)
+    wl.lower._training_step = lambda p, batch: torch.nn.functional.cross_entropy(p.module(batch[0]), batch[1])
+    params = [p for p in net.parameters() if share or p is not net.fc2.weight and p is not net.fc2.bias]
+    loss, tape = record_tape(lambda: wl.lower.training_step_exec(wl.lower.cur_batch), params)
+    g = lower_tape(tape)
+    pools = [n for n in g.nodes if n.op == "maxpool2d"]
+    assert len(pools) == 1
+    assert bool(pools[0].attrs.get("relu")) == fused
+    assert bool(pools[0].attrs.get("disjoint")) == (kernel == stride)
+    if fused:
+        assert not any(n.op == "unary" and n.attrs.get("kind") == "relu" for n in g.nodes)
+        assert pools[0].beta[0] == (0 if kernel == stride else 1)
+    it = Interp(g, torch.float64)
+    it.base_backward()
+    in_grad = torch.autograd.grad(loss, params, create_graph=True)
+    assert rel_l2([p.a for p in g.params], in_grad) < 1e-10
+    vec = [torch.randn_like(p) for p in params]
+    want = torch.autograd.grad(in_grad, params, grad_outputs=vec, retain_graph=True)
+    assert rel_l2(it.hvp(vec), want) < 1e-9
