@@ -605,6 +605,40 @@ def _fold_quadratic_regularisers(g: Graph):
                 return pp, uv, float(su)
         return None
 
+    # d loss / d value along an affine single-consumer path (None if the path is not of that form).  Memoised:
+    # weight decay written as ``sum(p.pow(2).sum() for p in params)`` is a chain of ~200 adds, and walking it from
+    # every term is quadratic (35 ms of a RoBERTa call's prologue).
+    to_loss: Dict[int, Optional[float]] = {id(loss_root): 1.0}
+
+    def factor_to_loss(v: Val) -> Optional[float]:
+        path: List[Tuple[int, float]] = []
+        cur, res = v, None
+        while True:
+            rid = id(cur.root)
+            if rid in to_loss:
+                res = to_loss[rid]
+                break
+            cons = consumers.get(rid, [])
+            if len({id(n) for n, _ in cons}) != 1:
+                break
+            n = cons[0][0]
+            if n.op == "unary" and n.attrs.get("kind") in ("scale", "neg"):
+                step = -1.0 if n.attrs["kind"] == "neg" else float(n.attrs["scalar"])
+            elif n.op == "add2":
+                step = float(sum((n.attrs["sa"] if k == 0 else n.attrs["sb"]) for _, k in cons))
+            else:
+                break
+            path.append((rid, step))
+            cur = n.out
+        else:
+            res = None
+        if res is None and id(cur.root) not in to_loss:
+            to_loss[id(cur.root)] = None
+        for rid, step in reversed(path):
+            res = None if res is None else res * step
+            to_loss[rid] = res
+        return res
+
     folds: List[Tuple[Val, float, Val, Optional[Val], float]] = []   # (param, coef, x, theta, s_theta)
     removed = set()
     quad_only = set()
@@ -621,24 +655,10 @@ def _fold_quadratic_regularisers(g: Graph):
         if got is None or tuple(x.base.shape) != tuple(got[0].base.shape):
             continue
         param, theta, s_theta = got
-        c, cur, ok = float(s_node.attrs["scale"]), s_node.out, True
-        while cur.root is not loss_root:
-            cons = consumers.get(id(cur.root), [])
-            nodes_ = {id(n) for n, _ in cons}
-            if len(nodes_) != 1:
-                ok = False
-                break
-            n = cons[0][0]
-            if n.op == "unary" and n.attrs.get("kind") in ("scale", "neg"):
-                c *= -1.0 if n.attrs["kind"] == "neg" else float(n.attrs["scalar"])
-            elif n.op == "add2":
-                c *= sum((n.attrs["sa"] if k == 0 else n.attrs["sb"]) for _, k in cons)
-            else:
-                ok = False
-                break
-            cur = n.out
-        if not ok:
+        f = factor_to_loss(s_node.out)
+        if f is None:
             continue
+        c = float(s_node.attrs["scale"]) * f
         folds.append((param, 2.0 * c, x, theta, s_theta))
         removed.update((id(pw), id(s_node)))
         quad_only.add(id(s_node.out))
