@@ -38,6 +38,15 @@ CASES = {
 }
 
 
+# Extra model families, used by the CPU oracle test only (tests/golden_cpu/): the GPU parity suite globs tests/golden/.
+CPU_ONLY_CASES = {
+    "resnet_cg": ("learning_to_reweight_resnet", dict(method="cg", batch=4, n=1, width=4, K=4)),
+    "resnet_neumann": ("learning_to_reweight_resnet", dict(method="neumann", batch=4, n=1, width=4, K=5, alpha=0.05)),
+    "fourconv_mini_neumann": ("implicit_maml", dict(method="neumann", n=2, K=4, alpha=0.01, hidden=4, image="miniimagenet")),
+    "mlp_cg_long": ("mlp_reweight", dict(method="cg", K=12)),
+}
+
+
 def input_checksum(wl):
     s = 0.0
     for t in list(wl.lower.module.parameters()) + list(wl.upper.module.parameters()) + list(wl.vector):
@@ -52,10 +61,14 @@ def main():
     import betty.hypergradient as ref  # the real thing, read-only
     from betty.hypergradient.neumann import approx_inverse_hvp
 
-    out_dir = os.path.join(ROOT, "tests", "golden")
-    os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(1)  # deterministic reductions
-    for case, (factory, kw) in CASES.items():
+    todo = [(os.path.join(ROOT, "tests", "golden"), c, f, k) for c, (f, k) in CASES.items()]
+    todo += [(os.path.join(ROOT, "tests", "golden_cpu"), c, f, k) for c, (f, k) in CPU_ONLY_CASES.items()]
+    only = set(sys.argv[1:])
+    for out_dir, case, factory, kw in todo:
+        if only and case not in only:
+            continue
+        os.makedirs(out_dir, exist_ok=True)
         wl = W.FACTORIES[factory](device="cpu", **kw)
         method = wl.lower.config.type
         rec = {"factory": factory, "kwargs": kw, "method": method, "checksum": input_checksum(wl),

@@ -12,6 +12,10 @@ from oracle import dense, ref_port
 from tests.helpers import GOLDEN, assert_close, checksum, flat, load_golden
 
 CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")))
+# more model families (ResNet, mini-ImageNet 4-conv, a longer CG) pinned for the oracle only: the GPU parity suite
+# globs tests/golden/, these live in tests/golden_cpu/
+GOLDEN_CPU = os.path.join(os.path.dirname(GOLDEN), "golden_cpu")
+CPU_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_CPU, "*.pt")))
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -25,6 +29,18 @@ def test_port_matches_reference_golden(case):
     if "ihvp" in rec:
         x = ref_port.k_loop_only(rec["method"], wl.vector, wl.lower)
         assert_close(x, rec["ihvp"], 1e-5, case + " ihvp")
+
+
+@pytest.mark.parametrize("case", CPU_CASES)
+def test_port_matches_reference_golden_more_families(case):
+    rec = torch.load(os.path.join(GOLDEN_CPU, case + ".pt"), weights_only=False)
+    torch.set_num_threads(1)
+    wl = W.FACTORIES[rec["factory"]](device="cpu", **rec["kwargs"])
+    assert abs(checksum(wl) - rec["checksum"]) <= 1e-6 * max(1.0, abs(rec["checksum"])), "seeded inputs drifted"
+    hg = ref_port.METHODS[rec["method"]](wl.vector, wl.lower, wl.upper, False)
+    assert_close(hg, rec["hypergrad"], 1e-5, case)
+    if "ihvp" in rec:
+        assert_close(ref_port.k_loop_only(rec["method"], wl.vector, wl.lower), rec["ihvp"], 1e-5, case + " ihvp")
 
 
 def test_port_sync_accumulates_into_upper_grads():
