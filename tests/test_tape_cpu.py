@@ -201,3 +201,46 @@ def test_relu_maxpool_fold(kernel, stride, share, size, fused):
     vec = [torch.randn_like(p) for p in params]
     want = torch.autograd.grad(in_grad, params, grad_outputs=vec, retain_graph=True)
     assert rel_l2(it.hvp(vec), want) < 1e-9
+
+
+def _golden_records():
+    import glob
+    import os
+
+    from tests.helpers import GOLDEN
+
+    recs = {}
+    for d in (GOLDEN, os.path.join(os.path.dirname(GOLDEN), "golden_cpu")):
+        for p in sorted(glob.glob(os.path.join(d, "*.pt"))):
+            recs[os.path.basename(p)[:-3]] = p
+    return recs
+
+
+@pytest.mark.parametrize("case", sorted(c for c in _golden_records() if "darts" not in c))
+def test_interpreted_engine_matches_the_real_reference(case):
+    """Whole algorithm, no CUDA: tape -> IR (folds included) -> second-order rules (fp64 interpreter) -> the
+    reference's Neumann / CG recurrence -> native epilogue seeds, against the hypergradient the REAL
+    betty.hypergradient function returned for the same seeded inputs (oracle/make_golden.py).  The golden vectors
+    are fp32, so the bar is the reference's own rounding: 1e-4 for the Neumann series, 2e-3 for CG (its fp32
+    recurrence amplifies rounding on the small un-shifted problems, cf. tools/parity_margin.py)."""
+    from betty_b200.engine import chain_boundary_seeds
+    from oracle import ref_port
+
+    rec = torch.load(_golden_records()[case], weights_only=False)
+    wl = to_double(W.FACTORIES[rec["factory"]](device="cpu", **rec["kwargs"]))
+    loss, tape, params = trace(wl)
+    g = lower_tape(tape)
+    it = Interp(g, torch.float64)
+    it.base_backward()
+    cfg = wl.lower.config
+    vec = [v.double() for v in wl.vector]
+    if rec["method"] == "neumann":
+        x = ref_port.neumann_series(vec, it.hvp, cfg.neumann_iterations, cfg.neumann_alpha)
+    else:
+        x = ref_port.cg_solve(vec, it.hvp, cfg.cg_iterations, cfg.cg_alpha)
+    if "ihvp" in rec:
+        assert rel_l2(x, rec["ihvp"]) < 1e-4, case
+    assert g.native_epilogue_ok
+    got = chain_boundary_seeds(it.mixed_seeds(x), wl.upper, False)
+    tol = 2e-3 if rec["method"] == "cg" else 1e-4
+    assert rel_l2(got, rec["hypergrad"]) < tol, (case, rel_l2(got, rec["hypergrad"]))
