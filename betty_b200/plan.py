@@ -61,6 +61,7 @@ class HvpPlan:
         self.dry_run = dry_run
         self.g: Graph = lower_tape(tape)
         self._keep: List[torch.Tensor] = []   # constants / scratch referenced by raw pointer
+        self._views: dict = {}                # (id(alias value), kind) -> torch view of its root buffer
         self._alloc_buffers()
         self._build_nodes()
         self.launches_per_iter = 0
@@ -108,8 +109,14 @@ class HvpPlan:
             return None
         if v.parent is None:
             return getattr(v, kind)
+        key = (id(v), kind)             # alias views are asked for several times per consuming node: build them once
+        hit = self._views.get(key, self)
+        if hit is not self:
+            return hit
         b = self.buf(v.parent, kind)
-        return None if b is None else v.viewfn(b)
+        out = None if b is None else v.viewfn(b)
+        self._views[key] = out
+        return out
 
     # ------------------------------------------------------------------------------------------
     def _ptr(self, t: Optional[torch.Tensor]) -> int:
