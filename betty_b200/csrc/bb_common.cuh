@@ -28,6 +28,20 @@
 #define BB_BF16 1
 #define BB_F16 2
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: a launcher remembers it per device,
+// so a process driving several GPUs opts in on each of them.
+struct BbOncePerDevice {
+  unsigned long long done = 0;
+  bool need() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+
 namespace bb {
 
 __device__ __forceinline__ float ldf(const void* p, int64_t i, int dt) {

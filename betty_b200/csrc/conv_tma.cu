@@ -408,10 +408,9 @@ int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
     if (stages < 2) return BB_DECLINED;
     A.stages = stages;
     const size_t smem = stages * stage + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static BbOncePerDevice configured;
+    if (configured.need()) {
       BB_CUDA_TRY(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-      configured = true;
     }
     if (!nd.beta[1]) {
       BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * g.O * g.C * taps, s));

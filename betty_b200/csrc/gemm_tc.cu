@@ -603,11 +603,10 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const __grid_co
 
 template <int BN_, int MINB>
 int launch_tc(const TcGemmArgs& G, int ksplit, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static BbOncePerDevice configured;
+  if (configured.need()) {
     BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<BN_, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(Cfg<BN_>::kSmem + 2 * sizeof(int2) * kMaxLutK)));
-    configured = true;
   }
   dim3 grid((unsigned)((G.N + BN_ - 1) / BN_), (unsigned)((G.M + BM - 1) / BM), (unsigned)ksplit);
   gemm_tc_kernel<BN_, MINB><<<grid, NTHREADS, Cfg<BN_>::kSmem + 2 * sizeof(int2) * G.lut_k, s>>>(G);

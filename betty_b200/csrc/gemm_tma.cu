@@ -465,11 +465,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_persist_kernel(const __g
 template <int BN_>
 int launch_tma(TmaGemmArgs& G, int64_t mtiles, cudaStream_t s, int batch) {
   using C = Cfg<BN_>;
-  static bool configured = false;
-  if (!configured) {
+  static BbOncePerDevice configured;
+  if (configured.need()) {
     BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tma_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C::smem(C::kStagesDeep)));
-    configured = true;
   }
   dim3 grid((unsigned)((G.N + BN_ - 1) / BN_), (unsigned)mtiles, (unsigned)(G.ksplit * batch));
   // A grid that does not fill the machine is latency-bound on its k-loop (each TMA round trip is ~1.5 us): give the
@@ -481,11 +480,10 @@ int launch_tma(TmaGemmArgs& G, int64_t mtiles, cudaStream_t s, int batch) {
   if (forced >= 2 && forced <= C::kStagesDeep) G.stages = forced;
   static const bool no_persist = getenv("BB200_TMA_NO_PERSIST") != nullptr;
   if (!no_persist && G.ksplit == 1 && batch == 1 && ctas > 4 * BB_SM_COUNT) {
-    static bool configured_p = false;
-    if (!configured_p) {
+    static BbOncePerDevice configured_p;
+    if (configured_p.need()) {
       BB_CUDA_TRY(cudaFuncSetAttribute(gemm_tma_persist_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)C::smem(C::kStagesDeep)));
-      configured_p = true;
     }
     G.stages = C::kStagesShared;
     gemm_tma_persist_kernel<BN_><<<2 * BB_SM_COUNT, NTHREADS, C::smem(G.stages), s>>>(G, (int)grid.x, (int)(grid.x * grid.y));

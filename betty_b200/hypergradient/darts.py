@@ -21,7 +21,11 @@ def _table(a_list, b_list, device):
 def _grad_lambda(loss, lam):
     g = torch.autograd.grad(loss, lam, allow_unused=True)
     # reference betty/utils.py:132-137
-    return [torch.zeros_like(p) if gi is None else gi.contiguous() for gi, p in zip(g, lam)]
+    out = [torch.zeros_like(p) if gi is None else gi.contiguous() for gi, p in zip(g, lam)]
+    for gi in out:
+        if gi.dtype != torch.float32:
+            raise N.NativeError("betty_b200.darts: upper gradient of dtype %s (fp32 expected)" % gi.dtype)
+    return out
 
 
 def darts(vector, curr, prev, sync):
@@ -35,6 +39,10 @@ def darts(vector, curr, prev, sync):
     for p in w:
         if p.dtype != torch.float32 or not p.is_contiguous():
             raise N.NativeError("betty_b200.darts needs contiguous fp32 lower parameters")
+    for p in lam:
+        # the K4 chunk tables address the upper gradients as fp32 words
+        if p.dtype != torch.float32:
+            raise N.NativeError("betty_b200.darts needs fp32 upper parameters (got %s)" % p.dtype)
     v = as_f32_contig(vector)
     ws = Workspace.get(dev)
     s = stream_ptr()

@@ -132,6 +132,14 @@ def _narrow_interior(t: torch.Tensor, pads, nd: int, shape) -> torch.Tensor:
     return t
 
 
+def _float_outputs(out) -> List[torch.Tensor]:
+    if isinstance(out, torch.Tensor):
+        return [out] if out.is_floating_point() else []
+    if isinstance(out, (list, tuple)):
+        return [o for o in out if isinstance(o, torch.Tensor) and o.is_floating_point()]
+    return []
+
+
 def _is_dense(t: torch.Tensor) -> bool:
     """non-overlapping and dense: some permutation of the dims is contiguous"""
     if t.numel() <= 1:
@@ -207,9 +215,27 @@ class _Lowering:
                     tensors += [x for x in a if isinstance(x, torch.Tensor)]
             if not any(id(t) in self.vals and not self.vals[id(t)].boundary for t in tensors):
                 continue  # constant w.r.t. the lower parameters (data prep, upper module forward, ...)
+            outs = _float_outputs(op.out)
+            if not outs:
+                continue  # .item(), argmax, comparisons ...: nothing differentiable comes out (metrics, masks)
+            if not any(o.requires_grad for o in outs):
+                # computed under torch.no_grad() (or detached): autograd -- hence the reference -- treats the
+                # result as a constant, and so must the second-order rules.  An in-place op would have kept
+                # requires_grad, so the tensor object is a fresh one and nothing recorded refers to it.
+                continue
             self._pending_upper = {id(t) for t in tensors
                                    if t.requires_grad and t.is_floating_point() and id(t) not in self.vals}
-            self.lower_op(op)
+            n_nodes, n_vals = len(self.nodes), len(self.all_vals)
+            try:
+                self.lower_op(op)
+            except UnsupportedGraph as e:
+                # Not fatal yet: side computations (logging, accuracy) routinely use ops without a rule.  The
+                # outputs become *poison* values; the call is refused only if one of them reaches the loss
+                # (checked after dead-code elimination in _analyse).
+                del self.nodes[n_nodes:]
+                ins = [self.vals[id(t)] for t in tensors if id(t) in self.vals]
+                for o in outs:
+                    self.emit("poison", ins, o, op.name, error=str(e))
             if self._pending_upper and op.name not in ("aten.detach.default", "aten.detach_.default"):
                 # an upper-dependent tensor entered an op in a slot this lowering treats as a plain constant:
                 # the K-loop is still exact, but the mixed second derivative must then come from autograd
@@ -721,6 +747,13 @@ def _analyse(g: Graph):
                 v.root.needed = True
     live.reverse()
     g.nodes = live
+    for n in live:
+        if n.op == "poison":
+            raise UnsupportedGraph(f"{n.attrs['error']} [{n.src} feeds the lower loss]")
+    if not loss.chain_full_cover():
+        # e.g. ``per_sample[0]``: the scalar is one element of a larger root buffer; the executor seeds only that
+        # element (plan.py) and the root's other elements must stay zero
+        loss.root.zero_init = False
     # count adjoint writers per root (parameters: writers of the H.d slice)
     for v in g.values:
         v.writers = 0

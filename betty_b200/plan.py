@@ -101,7 +101,10 @@ class HvpPlan:
             if not p.base.is_contiguous() or p.base.dtype != torch.float32:
                 raise UnsupportedGraph("lower parameters must be contiguous fp32 tensors")
             p.t, p.at, p.a = dviews[p.param_index], hviews[p.param_index], None
-        g.loss.root.a.fill_(1.0)   # seed dL/dL; its adjoint tangent stays 0
+        # seed dL/dL = 1 through the loss's own alias chain: when the scalar is one element of a larger tensor
+        # (``per_sample[0]``) the root's other elements must stay 0; its adjoint tangent stays 0
+        g.loss.root.a.zero_()
+        self.buf(g.loss, "a").fill_(1.0)
         self.bytes_buffers = 4 * (self.T.numel() + 2 * (self.A["z"].numel() + self.A["nz"].numel()))
 
     def buf(self, v: Optional[Val], kind: str) -> Optional[torch.Tensor]:

@@ -56,7 +56,8 @@ class Interp:
 
     def base_backward(self):
         self.zero("a")
-        self.g.loss.root.a.fill_(1.0)
+        self.g.loss.root.a.zero_()
+        self.buf(self.g.loss, "a").fill_(1.0)   # only the loss's own element of a larger root
         for n in reversed(self.g.nodes):
             getattr(self, "bb_" + n.op)(n)
 
