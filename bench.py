@@ -35,7 +35,8 @@ WORKLOADS = {
     "logistic_regression_hpo": ("logistic_regression_hpo", dict(method="neumann", K=5), "20-dim logistic HPO, Neumann K=5, fp32"),
     "neural_architecture_search": ("neural_architecture_search", dict(batch=64, c=16, cells=4), "DARTS-style supernet c16 x 4 cells B=64, finite-difference hypergradient (1 call = 1 iter-equivalent), fp32"),
 }
-DEFAULT = "learning_to_reweight"
+DEFAULT = "implicit_maml"      # the config BASELINE.json's ">=60 % HBM roofline on the Neumann K=20 path" is quoted on
+EXTRA = ("learning_to_reweight", "bert_data_reweighting")   # sub-records of the default run
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -112,124 +113,104 @@ def build_workload(name, device, seed=0):
     return wl, kw, desc
 
 
+def reference_kloop_rate(workload, budget_s, max_iters=None, calibrate=True):
+    """HVP-iters/s of the reference's CPU autograd path on this host (bounded sample of `workload`).
+
+    With ``oracle/_ref`` present (the unmodified reference, mirrored by oracle/fetch_ref.sh) the K-loop that is timed
+    is the reference's own code -- ``betty.hypergradient.neumann.approx_inverse_hvp``, the loop inside
+    ``betty.hypergradient.cg.cg`` (timed by difference, see oracle/reference.py), ``betty.hypergradient.darts.darts``
+    -- driven through the duck-typed problems of betty_b200.shim (``kind: "reference"``); otherwise the oracle port
+    (``kind: "port"``)."""
+    from oracle import ref_port
+    from oracle import reference as R
+
+    wl, kw, desc = build_workload(workload, "cpu")
+    method = wl.lower.config.type
+    K = kw.get("K", 1)
+    cores = min(os.cpu_count() or 1, 32)
+    kind = "reference" if R.available() else "port"
+    t_all = time.perf_counter()
+    if method == "darts":
+        torch.set_num_threads(cores)
+        fn = (lambda: R.kloop_seconds(wl, "darts", 1)["kloop_s"]) if kind == "reference" else None
+        if fn is None:
+            def fn():
+                t0 = time.perf_counter()
+                ref_port.darts(wl.vector, wl.lower, wl.upper, False)
+                return time.perf_counter() - t0
+        fn()                                                   # warm-up
+        n, spent = 0, 0.0
+        while (n < 1 or spent < budget_s) and n < 20:
+            spent += fn()
+            n += 1
+        return {"value": n / spent, "unit": "HVP-iters/s", "cores": cores, "kind": kind, "iters": n, "K": 1,
+                "seconds": spent, "desc": desc,
+                "sample": f"{n} finite-difference call(s) of the full-size workload ({spent:.1f} s), fp32, torch {torch.__version__} CPU autograd"}
+    if calibrate:
+        in_grad = ref_port.lower_gradient(wl.lower)
+        hvp = ref_port.make_hvp(in_grad, wl.lower.trainable_parameters())
+        cores = best_thread_count(hvp, list(wl.vector), budget_s=min(40.0, budget_s))
+        del in_grad, hvp
+    else:
+        torch.set_num_threads(min(cores, 16))
+        cores = min(cores, 16)
+    cap = K if max_iters is None else min(K, max_iters)
+
+    def run(k):
+        if kind == "reference":
+            return R.kloop_seconds(wl, method, k)["kloop_s"]
+        ig = ref_port.lower_gradient(wl.lower)
+        h = ref_port.make_hvp(ig, wl.lower.trainable_parameters())
+        t0 = time.perf_counter()
+        if method == "neumann":
+            ref_port.neumann_series(list(wl.vector), h, k, wl.lower.config.neumann_alpha)
+        else:
+            ref_port.cg_solve(list(wl.vector), h, k, wl.lower.config.cg_alpha)
+        return time.perf_counter() - t0
+
+    t1 = run(1)                                                # also the warm-up
+    k = int(max(1, min(cap, round(0.5 * budget_s / max(t1, 1e-6)))))
+    iters, spent = 0, 0.0
+    while iters == 0 or (spent + k * t1 < budget_s and iters < 4 * cap):
+        spent += run(k)
+        iters += k
+    return {"value": iters / spent, "unit": "HVP-iters/s", "cores": cores, "kind": kind, "iters": iters, "K": K,
+            "seconds": spent, "desc": desc, "k_per_step": k,
+            "sample": f"{iters} K-loop iteration(s) ({spent:.1f} s; {k} per step of K={K}) of the full-size workload, fp32, torch {torch.__version__} CPU autograd, total {time.perf_counter() - t_all:.0f} s incl. prologue"}
+
+
 def run_reference(args):
-    """--impl reference: the oracle port of the reference's CPU autograd path on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import ref_port
-
-    wl, kw, desc = build_workload(args.workload, "cpu")
-    method = wl.lower.config.type
-    K = kw.get("K", 1)
-    if method == "darts":
-        return run_reference_fd(args, wl, desc)
-    # bounded sample: cap K so that one step stays within a few seconds-to-tens-of-seconds of CPU work
-    k_sample = min(K, args.ref_iters)
-    if method == "neumann":
-        wl.lower.config.neumann_iterations = k_sample
-    else:
-        wl.lower.config.cg_iterations = k_sample
-    in_grad = ref_port.lower_gradient(wl.lower)
-    hvp = ref_port.make_hvp(in_grad, wl.lower.trainable_parameters())
-    cores = best_thread_count(hvp, list(wl.vector))
-
-    def step():
-        if method == "neumann":
-            return ref_port.neumann_series(list(wl.vector), hvp, k_sample, wl.lower.config.neumann_alpha)
-        return ref_port.cg_solve(list(wl.vector), hvp, k_sample, wl.lower.config.cg_alpha)
-
-    for _ in range(min(args.warmup, 1)):
-        step()
     t0 = time.perf_counter()
-    n = 0
-    for _ in range(args.steps):
-        step()
-        n += 1
-        if time.perf_counter() - t0 > args.ref_budget_s:
-            break
-    dt = time.perf_counter() - t0
-    value = n * k_sample / dt
+    rec = reference_kloop_rate(args.workload, budget_s=args.ref_budget_s)
+    wall = time.perf_counter() - t0
+    steps = max(1, rec["iters"] // max(1, rec.get("k_per_step", 1)))
     line = {
-        "impl": "reference", "metric": "HVP-iters/sec", "value": value, "unit": "HVP-iters/s", "n_gpus": args.gpus,
-        "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / n, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "describe": desc, "K": K},
-        "cpu_baseline": {"value": value, "unit": "HVP-iters/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} step(s) x {k_sample} of K={K} iterations, full batch, torch {torch.__version__} CPU autograd double backward"},
-        "e2e": {"value": value, "unit": "HVP-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "HVP-iters/sec", "value": rec["value"], "unit": "HVP-iters/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * rec["seconds"] / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "describe": rec["desc"], "K": rec["K"], "wall_s": wall},
+        "cpu_baseline": {"value": rec["value"], "unit": "HVP-iters/s", "cores": rec["cores"], "kind": rec["kind"],
+                         "sample": rec["sample"]},
+        "e2e": {"value": rec["value"], "unit": "HVP-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
-def run_reference_fd(args, wl, desc):
-    from oracle import ref_port
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(min(cores, 32))
-    ref_port.darts(wl.vector, wl.lower, wl.upper, False)
-    t0 = time.perf_counter()
-    n = 0
-    for _ in range(args.steps):
-        ref_port.darts(wl.vector, wl.lower, wl.upper, False)
-        n += 1
-        if time.perf_counter() - t0 > args.ref_budget_s:
-            break
-    dt = time.perf_counter() - t0
-    value = n / dt
-    print(json.dumps({
-        "impl": "reference", "metric": "HVP-iters/sec", "value": value, "unit": "HVP-iters/s", "n_gpus": args.gpus,
-        "steps": n, "warmup": 1, "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "describe": desc, "K": 1},
-        "cpu_baseline": {"value": value, "unit": "HVP-iters/s", "cores": min(cores, 32), "kind": "port",
-                         "sample": f"{n} finite-difference call(s), torch CPU autograd"},
-        "e2e": {"value": value, "unit": "HVP-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-    return 0
-
-
 # -------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--hvp", default="native", choices=["native", "autograd"])
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-iters", type=int, default=4, help="K-loop iterations per reference step (bounded sample)")
-    ap.add_argument("--ref-budget-s", type=float, default=60.0)
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-
-    if args.impl == "reference":
-        return run_reference(args)
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+def measure(name, args, dev, dist, world, rank, local, steps, e2e_steps, with_cpu):
+    """One workload: K-loop rate (inputs resident), e2e through the plugin call from pinned host buffers, roofline."""
+    import gc
 
     from betty_b200 import _native as N
     from betty_b200 import engine as E
     from betty_b200 import hypergradient as H
 
-    E.settings.hvp = args.hvp
-    E.settings.cuda_graph = not args.no_graph
-    wl, kw, desc = build_workload(args.workload, dev, seed=rank)
+    wl, kw, desc = build_workload(name, dev, seed=rank)
     kw = dict(kw)
     method = wl.lower.config.type
     K = kw.get("K", 1)
@@ -263,10 +244,10 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = N.launch_counter
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         ev[i][0].record()
         call.solve(wl.vector)
         ev[i][1].record()
@@ -278,13 +259,42 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = sum(step_ms)  # device time of the K steps, L2 flushes excluded
     launches = N.launch_counter - launches0
-    plan_launches = getattr(call.hvp, "launches_per_iter", 0) * K * args.steps
     t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
-    ms_per_step = dev_ms_max / args.steps
-    value = world * K * args.steps / (dev_ms_max / 1e3)
+    ms_per_step = dev_ms_max / steps
+    value = world * K * steps / (dev_ms_max / 1e3)
+
+    # ---- roofline (before e2e: the plan of `call` is still alive) -------------------------------
+    hbm, tf, which = measured_peaks()
+    roof = None
+    if call.hvp is not None and hasattr(call.hvp, "roofline"):
+        roof = call.hvp.roofline(hbm_gbs=hbm, which=which)
+        from betty_b200.roofline import survey_bytes
+
+        sb = survey_bytes(call.hvp.g, method)
+        per_gpu = value / world
+        roof["plan"] = roof.pop("iteration")                       # the executed plan's own byte count / node times
+        roof["iteration"] = {"alg_bytes": sb["bytes"], "formula": sb["formula"], "A_in": sb["A_in"], "A_out": sb["A_out"],
+                             "P": sb["P"], "s_a": sb["s_a"], "iters_per_s_per_gpu": per_gpu,
+                             "achieved_GBps": sb["bytes"] * per_gpu / 1e9, "frac": sb["bytes"] * per_gpu / 1e9 / hbm,
+                             "hbm_ceiling_iters_per_s": hbm * 1e9 / sb["bytes"],
+                             "note": "SURVEY 8(d) bytes x measured K-loop rate (vector kernels K1-K3 included in the time)"}
+    elif method == "darts":
+        roof = fd_kernel_roofline(wl, dev, hbm, which)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f).get(name, {})
+        for key, rec in tr.items():
+            if roof and roof.get("kernel", "").startswith(key):
+                roof["traffic"] = rec["bytes"]
+                roof["traffic_source"] = rec["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    n_params = call.layout.n_logical
+    del call
+    gc.collect()
 
     # ---- e2e: whole plugin call from pinned host buffers -------------------------------------
     host_batch = [b.cpu().pin_memory() if torch.is_tensor(b) else b for b in wl.lower.cur_batch]
@@ -306,76 +316,135 @@ def main():
         d2h = sum(o.numel() * o.element_size() for o in out)
         return out
 
-    import gc
-
-    for _ in range(2):      # warm-up: allocator pools, cuBLAS/cuDNN handles of the lower forward, graph instantiation
+    for _ in range(2):      # warm-up: allocator pools, cuBLAS/cuDNN handles of the lower forward, plan cache
         e2e_step()
     gc.collect()
     barrier()
+    launches1 = N.launch_counter
     t1 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         e2e_step()
     barrier()
     e2e_wall = time.perf_counter() - t1
     t = torch.tensor([e2e_wall], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * K * args.e2e_steps / float(t.item())
+    e2e_value = world * K * e2e_steps / float(t.item())
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------
-    hbm, tf, which = measured_peaks()
-    roof = None
-    if call.hvp is not None and hasattr(call.hvp, "roofline"):
-        roof = call.hvp.roofline(hbm_gbs=hbm, which=which)
-    if roof is None:
-        # development mode: the only kernels of ours in the loop are the flat-arena updates
-        n = 128 * 1024 * 1024
-        a, b, c, d = (torch.randn(n, device=dev) for _ in range(4))
-        ws = E.Workspace.get(dev)
-        s = torch.cuda.current_stream().cuda_stream
-        N.call("bb_cg_dots", b.data_ptr(), d.data_ptr(), c.data_ptr(), 1.0, 1, n, ws.ptr, s)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            N.call("bb_cg_update_xr", a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), n, ws.ptr, s)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        ach = 24.0 * n / (ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "cg_update_xr_kernel (128Mi-element arena, isolated)", "achieved": ach,
-                "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": which}
-        del a, b, c, d
-
-    # DRAM traffic of the dominant node from a committed `ncu --set full` capture of the same workload (sum of
-    # dram__bytes_read.sum + dram__bytes_write.sum over the node's kernels, per launch), when one exists
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
-            tr = json.load(f).get(args.workload, {})
-        for key, rec in tr.items():
-            if roof.get("kernel", "").startswith(key):
-                roof["traffic"] = rec["bytes"]
-                roof["traffic_source"] = rec["source"]
-    except (OSError, ValueError, KeyError):
-        pass
-
-    line = {
-        "metric": "HVP-iters/sec", "value": value, "unit": "HVP-iters/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if wl.lower.config.precision == "fp32" else "bf16+f32",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "describe": desc, "K": K, "method": method, "hvp": args.hvp,
+    rec = {
+        "value": value, "unit": "HVP-iters/s", "ms_per_step": ms_per_step, "steps": steps,
+        "dtype": "f32" if wl.lower.config.precision == "fp32" else "bf16+f32",
+        "config": {"workload": name, "describe": desc, "K": K, "method": method, "hvp": args.hvp,
                    "cuda_graph": E.settings.cuda_graph, "l2": "252 MB buffer rewritten between timed steps",
                    "parallelism": f"replicas x{world} (local solve per rank, SURVEY 8e)",
-                   "n_params": call.layout.n_logical, "wall_s": wall},
+                   "n_params": n_params, "wall_s": wall},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "HVP-iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": args.e2e_steps, "includes": "H2D batch+v, prologue, K-loop, epilogue, D2H hypergradient"},
-        "gpu_launches": launches + plan_launches,
+                "steps": e2e_steps, "includes": "H2D batch+v, prologue, K-loop, epilogue, D2H hypergradient",
+                "gpu_launches": N.launch_counter - launches1},
+        "gpu_launches": launches,
         "roofline": roof,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, kw)
+    del wl, flush, host_batch, host_vec
+    gc.collect()
+    torch.cuda.empty_cache()
+    if with_cpu:
+        r = reference_kloop_rate(name, budget_s=args.cpu_budget_s, max_iters=args.ref_iters)
+        rec["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    return rec
+
+
+def fd_kernel_roofline(wl, dev, hbm, which):
+    """Finite difference: the only kernels of ours are K4 (norm, three parameter sweeps, combine); report the
+    parameter sweep `w += eps v` over this workload's own parameter tensors (12 B per element)."""
+    from betty_b200 import _native as N
+    from betty_b200 import engine as E
+    from betty_b200.arena import ChunkTable
+
+    ps = [p.data for p in wl.lower.parameters()]
+    vs = [torch.randn_like(p) for p in ps]
+    tab = ChunkTable([v.data_ptr() for v in vs], [p.data_ptr() for p in ps], [p.numel() for p in ps], dev, keep=(vs, ps))
+    ws = E.Workspace.get(dev)
+    s = torch.cuda.current_stream().cuda_stream
+    zero = torch.zeros(1, device=dev)
+    reps = 20
+    for _ in range(3):
+        N.call("bb_mt_axpby", tab.ptr, tab.n, 1.0, zero.data_ptr(), 1.0, s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        N.call("bb_mt_axpby", tab.ptr, tab.n, 1.0, zero.data_ptr(), 1.0, s)   # w += 0 * v: values unchanged
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    n = sum(p.numel() for p in ps)
+    ach = 12.0 * n / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": f"mt_axpby (K4 parameter sweep w += eps v over {len(ps)} tensors, {n} elements; "
+            "L2-resident at this size)", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "traffic": None, "peak_source": which, "kernel_ms": ms, "kernel_alg_bytes": 12 * n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hvp", default="native", choices=["native", "autograd"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sub-records of the other headline configs")
+    ap.add_argument("--ref-iters", type=int, default=4, help="cap on K-loop iterations per CPU-baseline step")
+    ap.add_argument("--ref-budget-s", type=float, default=60.0, help="--impl reference: CPU seconds of timed K-loop")
+    ap.add_argument("--cpu-budget-s", type=float, default=12.0, help="cpu_baseline leg: CPU seconds of timed K-loop")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    extras = [] if (args.workload is not None or args.no_extra) else list(EXTRA)
+    args.workload = args.workload or DEFAULT
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    from betty_b200 import engine as E
+
+    E.settings.hvp = args.hvp
+    E.settings.cuda_graph = not args.no_graph
+    with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    main_rec = measure(args.workload, args, dev, dist, world, rank, local, args.steps, args.e2e_steps, with_cpu)
+    line = {
+        "metric": "HVP-iters/sec", "value": main_rec["value"], "unit": "HVP-iters/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": main_rec["dtype"], "data": "synthetic",
+        "config": main_rec["config"], "clocks": main_rec["clocks"], "e2e": main_rec["e2e"],
+        "gpu_launches": main_rec["gpu_launches"] + main_rec["e2e"]["gpu_launches"], "roofline": main_rec["roofline"],
+    }
+    if "cpu_baseline" in main_rec:
+        line["cpu_baseline"] = main_rec["cpu_baseline"]
+    if extras:
+        # the other two headline configs of BASELINE.json (LeNet CG K=20 fp32; RoBERTa-base CG K=10 bf16) as
+        # sub-records of the same line: same timing rules, fewer steps
+        line["extra"] = {}
+        for name in extras:
+            r = measure(name, args, dev, dist, world, rank, local, max(3, args.steps // 2), 3, with_cpu)
+            line["extra"][name] = r
+            line["gpu_launches"] += r["gpu_launches"] + r["e2e"]["gpu_launches"]
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -406,41 +475,6 @@ def best_thread_count(hvp, v, budget_s: float = 40.0):
             break
     torch.set_num_threads(best)
     return best
-
-
-def cpu_baseline(args, kw):
-    """Oracle port (reference algorithm, torch CPU autograd) on this box's host cores, bounded sample."""
-    from oracle import ref_port
-
-    wl, kw, desc = build_workload(args.workload, "cpu")
-    method = wl.lower.config.type
-    if method == "darts":
-        cores = min(os.cpu_count() or 1, 32)
-        torch.set_num_threads(cores)
-        ref_port.darts(wl.vector, wl.lower, wl.upper, False)
-        t0 = time.perf_counter()
-        n = 0
-        while n < 3 and time.perf_counter() - t0 < 12.0:
-            ref_port.darts(wl.vector, wl.lower, wl.upper, False)
-            n += 1
-        dt = time.perf_counter() - t0
-        return {"value": n / dt, "unit": "HVP-iters/s", "cores": cores, "kind": "port",
-                "sample": f"{n} finite-difference call(s) ({dt:.1f} s), fp32, torch CPU autograd"}
-    in_grad = ref_port.lower_gradient(wl.lower)
-    hvp = ref_port.make_hvp(in_grad, wl.lower.trainable_parameters())
-    v = list(wl.vector)
-    cores = best_thread_count(hvp, v)
-    iters = 0
-    t0 = time.perf_counter()
-    while iters < kw.get("K", 1) and (time.perf_counter() - t0 < 12.0 or iters < 1):
-        if method == "neumann":
-            ref_port.neumann_series(v, hvp, 1, wl.lower.config.neumann_alpha)
-        else:
-            ref_port.cg_solve(v, hvp, 1, wl.lower.config.cg_alpha)
-        iters += 1
-    dt = time.perf_counter() - t0
-    return {"value": iters / dt, "unit": "HVP-iters/s", "cores": cores, "kind": "port",
-            "sample": f"{iters} K-loop iteration(s) of the full-size workload ({dt:.1f} s), fp32, torch CPU autograd"}
 
 
 if __name__ == "__main__":

@@ -58,6 +58,10 @@ _SIGS = {
     "bb_plan_launch_count": ([C.c_void_p, C.c_int], 0),
     "bb_plan_profile": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
     "bb_plan_hvp": ([C.c_void_p, C.c_void_p], None),
+    "bb_plan_hvp_replay": ([C.c_void_p, C.c_void_p], None),
+    "bb_plan_invalidate_constants": ([C.c_void_p], 0),
+    "bb_plan_graph_captures": ([C.c_void_p], 0),
+    "bb_plan_node_route": ([C.c_void_p, C.c_int, C.c_int], 0),
     "bb_plan_neumann_loop": ([C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_int, C.c_void_p], None),
     "bb_plan_cg_loop": ([C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -8,6 +8,7 @@
 #include "bb_common.cuh"
 #include "plan.h"
 #include "tma.h"
+#include "conv_tma.h"
 
 struct bb_plan {
   std::vector<bb_node> nodes;
@@ -19,6 +20,29 @@ struct bb_plan {
   uint8_t* persist = nullptr;   // plan-lifetime packs of K-loop constants, bump-allocated per node
   int64_t persist_bytes = 0, persist_used = 0;
   std::vector<void*> node_persist;
+  // One captured iteration per loop kind (0 Neumann, 1 CG, 2 bare H.d), kept for the plan's lifetime and relaunched
+  // by every later K-loop on the same arenas: capture + instantiate (0.5 ms ... 15 ms for ~1000 nodes) is paid
+  // once per plan, not once per solve.  The key holds everything the captured kernels have baked in.
+  struct LoopKey {
+    const void* ptr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t n = 0;
+    float alpha = 0.f;
+    bool operator==(const LoopKey& o) const {
+      for (int i = 0; i < 5; ++i)
+        if (ptr[i] != o.ptr[i]) return false;
+      return n == o.n && alpha == o.alpha;
+    }
+  };
+  cudaGraphExec_t exec[3] = {nullptr, nullptr, nullptr};
+  LoopKey key[3];
+  int graph_captures = 0;
+  void drop_graphs() {
+    for (auto& e : exec) {
+      if (e) cudaGraphExecDestroy(e);
+      e = nullptr;
+    }
+  }
+  ~bb_plan() { drop_graphs(); }
 };
 
 namespace {
@@ -116,41 +140,41 @@ int run_pass(bb_plan* p, int pass, cudaStream_t s) {
 }
 
 template <class Body>
-int loop_with_graph(int iterations, int use_graph, cudaStream_t s, Body body) {
+int loop_with_graph(bb_plan* plan, int kind, const bb_plan::LoopKey& key, int iterations, int use_graph, cudaStream_t s,
+                    Body body) {
   if (iterations <= 0) return BB_OK;
-  if (!use_graph || iterations == 1) {
+  if (!use_graph) {
     for (int k = 0; k < iterations; ++k) {
       const int rc = body();
       if (rc) return rc;
     }
     return BB_OK;
   }
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
-  BB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-  const int rc = body();
-  cudaError_t e = cudaStreamEndCapture(s, &graph);
-  if (rc) {
-    if (graph) cudaGraphDestroy(graph);
-    return rc;
+  if (plan->exec[kind] && !(plan->key[kind] == key)) {
+    cudaGraphExecDestroy(plan->exec[kind]);
+    plan->exec[kind] = nullptr;
   }
-  if (e != cudaSuccess) return (int)e;
-  e = cudaGraphInstantiate(&exec, graph, 0);
-  if (e != cudaSuccess) {
-    cudaGraphDestroy(graph);
-    return (int)e;
-  }
-  int out = BB_OK;
-  for (int k = 0; k < iterations; ++k) {
-    e = cudaGraphLaunch(exec, s);
-    if (e != cudaSuccess) {
-      out = (int)e;
-      break;
+  if (!plan->exec[kind]) {
+    cudaGraph_t graph = nullptr;
+    BB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+    const int rc = body();
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
     }
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGraphInstantiate(&plan->exec[kind], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      plan->exec[kind] = nullptr;
+      return (int)e;
+    }
+    plan->key[kind] = key;
+    plan->graph_captures += 1;
   }
-  cudaGraphExecDestroy(exec);
-  cudaGraphDestroy(graph);
-  return out;
+  for (int k = 0; k < iterations; ++k) BB_CUDA_TRY(cudaGraphLaunch(plan->exec[kind], s));
+  return BB_OK;
 }
 
 }  // namespace
@@ -193,7 +217,28 @@ int bb_plan_set_persistent(bb_plan* plan, void* ptr, int64_t bytes) {
   plan->persist_bytes = bytes;
   plan->persist_used = 0;
   plan->node_persist.assign(plan->nodes.size() * BB_PERSIST_SLOTS, nullptr);
+  plan->drop_graphs();
   return BB_OK;
+}
+
+int bb_plan_invalidate_constants(bb_plan* plan) {
+  // the base values behind the plan's pointers were refreshed in place (a cached plan serving a new batch): packs of
+  // K-loop constants must be rebuilt by the next base-backward pass.  Addresses are unchanged, so captured graphs stay.
+  if (!plan) return BB_ERR_ARG;
+  plan->persist_used = 0;
+  plan->node_persist.assign(plan->nodes.size() * BB_PERSIST_SLOTS, nullptr);
+  return BB_OK;
+}
+
+int bb_plan_graph_captures(const bb_plan* plan) { return plan ? plan->graph_captures : BB_ERR_ARG; }
+
+int bb_plan_node_route(bb_plan* plan, int node, int pass) {
+  // introspection for the unit tests: 2 = TMA-fed tensor-core convolution path takes (node, pass), 0 = another path
+  if (!plan || node < 0 || node >= (int)plan->nodes.size()) return BB_ERR_ARG;
+  bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(plan->scratch), (size_t)plan->scratch_bytes, 0};
+  const bb_node& nd = plan->nodes[node];
+  if (nd.op == BB_OP_CONV2D && bb_conv_tma_ok(nd, pass)) return 2;
+  return 0;
 }
 
 int bb_plan_run(bb_plan* plan, int pass, void* stream) {
@@ -211,6 +256,14 @@ int bb_plan_hvp(bb_plan* plan, void* stream) {
   int rc = run_pass(plan, BB_PASS_TAN_FWD, (cudaStream_t)stream);
   if (rc) return rc;
   return run_pass(plan, BB_PASS_TAN_BWD, (cudaStream_t)stream);
+}
+
+int bb_plan_hvp_replay(bb_plan* plan, void* stream) {
+  // H.d as one graph launch (epilogue pass along x, benchmarks of the bare product)
+  if (!plan) return BB_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  bb_plan::LoopKey key;
+  return loop_with_graph(plan, 2, key, 1, 1, s, [&]() -> int { return bb_plan_hvp(plan, s); });
 }
 
 int bb_plan_profile(bb_plan* plan, int pass, float* ms_per_node, void* stream) {
@@ -248,7 +301,9 @@ int bb_plan_neumann_loop(bb_plan* plan, int iterations, float alpha, float* v, f
                          int use_graph, void* stream) {
   if (!plan) return BB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  return loop_with_graph(iterations, use_graph, s, [&]() -> int {
+  bb_plan::LoopKey key;
+  key.ptr[0] = v; key.ptr[1] = p; key.ptr[2] = hv; key.n = n; key.alpha = alpha;
+  return loop_with_graph(plan, 0, key, iterations, use_graph, s, [&]() -> int {
     int rc = bb_plan_hvp(plan, s);                            // hv <- H v        (neumann.py:62)
     if (rc) return rc;
     return bb_neumann_update(v, p, hv, alpha, 0.f, n, s);     // v, p updates     (neumann.py:63-64)
@@ -261,7 +316,9 @@ int bb_plan_cg_loop(bb_plan* plan, int iterations, float cg_alpha, float* x, flo
   cudaStream_t s = (cudaStream_t)stream;
   int rc = bb_cg_init(r, n, ws, s);                           // rr = r.r         (cg.py:45, first iteration)
   if (rc) return rc;
-  return loop_with_graph(iterations, use_graph, s, [&]() -> int {
+  bb_plan::LoopKey key;
+  key.ptr[0] = x; key.ptr[1] = r; key.ptr[2] = p; key.ptr[3] = hp; key.ptr[4] = ws; key.n = n; key.alpha = cg_alpha;
+  return loop_with_graph(plan, 1, key, iterations, use_graph, s, [&]() -> int {
     int rc2 = bb_plan_hvp(plan, s);                           // hp <- H p        (cg.py:39-41)
     if (rc2) return rc2;
     rc2 = bb_cg_dots(r, hp, p, cg_alpha, 0, n, ws, s);        // alpha            (cg.py:42-47)

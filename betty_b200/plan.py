@@ -65,6 +65,7 @@ class HvpPlan:
         self._alloc_buffers()
         self._build_nodes()
         self.launches_per_iter = 0
+        self.serves = 1                       # hypergradient calls this plan has served (plan cache, engine.py)
         if dry_run:
             return
         self.side = torch.cuda.Stream(device=self.dev)
@@ -512,7 +513,7 @@ class HvpPlan:
         (neumann.py:44-54, cg.py:58-68)."""
         if x_arena.data_ptr() != self.d_arena.data_ptr():
             self.d_arena.copy_(x_arena)
-        self._on_side(lambda s: N.call("bb_plan_hvp", self.handle, s))
+        self._on_side(lambda s: N.call("bb_plan_hvp_replay" if (self.use_graph and self.serves > 1) else "bb_plan_hvp", self.handle, s))
         self._count_iter(1, 0)
         return [(b.base, b.at) for b in self.g.boundaries if b.parent is None and b.at is not None]
 

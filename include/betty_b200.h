@@ -91,7 +91,15 @@ int bb_plan_launch_count(const bb_plan* plan, int pass);
 int bb_plan_profile(bb_plan* plan, int pass, float* ms_per_node, void* stream);
 /* one H.d product: zero regions, tangent forward, tangent backward */
 int bb_plan_hvp(bb_plan* plan, void* stream);
-/* whole K-loops, captured once into a CUDA graph and replayed (direction arena `d`, result `hv`) */
+/* the same product as ONE graph launch (captured at the first call, kept for the plan's lifetime) */
+int bb_plan_hvp_replay(bb_plan* plan, void* stream);
+/* a cached plan is about to serve new base values written in place behind the same pointers: rebuild the packs of
+ * K-loop constants at the next BB_PASS_BASE_BWD (captured graphs stay valid, addresses do not change) */
+int bb_plan_invalidate_constants(bb_plan* plan);
+int bb_plan_graph_captures(const bb_plan* plan); /* how many times a K-loop iteration was captured (tests) */
+int bb_plan_node_route(bb_plan* plan, int node, int pass); /* tests: 2 = TMA tensor-core convolution path */
+/* whole K-loops: one iteration is captured into a CUDA graph at the first call and relaunched by every later
+ * call with the same arenas / alpha (direction arena `d`, result `hv`) */
 int bb_plan_neumann_loop(bb_plan* plan, int iterations, float alpha, float* v /*direction*/, float* p,
                          const float* hv, int64_t n, int use_graph, void* stream);
 int bb_plan_cg_loop(bb_plan* plan, int iterations, float cg_alpha, float* x, float* r, float* p /*direction*/,

@@ -35,22 +35,34 @@ def hvp_mode(request):
 _FLOOR = {}
 
 
-def _tolerance(rec, case):
-    """1e-4 (fp32 bar of BASELINE.json) or, where the reference's own arithmetic is noisier than that, 5x the
-    reference's fp32-vs-fp64 gap on the same input -- the SURVEY.md 8(c) protocol (CG on small un-shifted
-    problems and the finite-difference method sit at 2e-5...5e-4 in the reference itself)."""
+def _reference_floor(rec, case):
+    """The reference's own fp32-vs-fp64 gap on the same input (max of three samples: its fp32 result is not
+    run-to-run reproducible on a GPU -- atomics in cuDNN / index_add backward)."""
     if case not in _FLOOR:
         w64 = to_double(W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"]))
         fn = ref_port.METHODS[rec["method"]]
         want64 = fn(w64.vector, w64.lower, w64.upper, False)
-        # the fp32 reference is itself not run-to-run reproducible on a GPU (atomics in cuDNN / index_add backward):
-        # on the ill-conditioned cases one sample of its fp32-vs-fp64 gap ranges over 2e-5 ... 1e-3, so take three
         gaps = []
         for _ in range(3):
             w32 = W.FACTORIES[rec["factory"]](device="cuda", **rec["kwargs"])
             gaps.append(rel_l2(fn(w32.vector, w32.lower, w32.upper, False), want64))
         _FLOOR[case] = max(gaps)
-    return max(1e-4, 5 * _FLOOR[case])
+    return _FLOOR[case]
+
+
+def _tolerance(rec, case):
+    """BASELINE.json's fp32 bar, 1e-4, HARD for every Neumann / CG case: each golden workload carries an explicit
+    regulariser (SPD-shifted Hessian), so nothing excuses a larger error.  The reference's own
+    fp32-vs-fp64 gap is printed next to it as the noise floor, never multiplied in.
+
+    The finite-difference method is the one exception SURVEY.md 8(c) provides for: `(g- - g+)/(2 eps)` amplifies fp32
+    rounding of the two gradients by 1/eps whatever the conditioning, and the *reference itself* sits at 1e-4...5e-4
+    of its fp64 value there; those cases use max(1e-4, 5 x that gap)."""
+    floor = _reference_floor(rec, case)
+    tol = 1e-4 if rec["method"] in ("neumann", "cg") else max(1e-4, 5 * floor)
+    print(f"[parity] {case}: reference fp32-vs-fp64 floor {floor:.3e}, tolerance {tol:.1e}"
+          + (" (> 1e-4: finite-difference noise floor)" if tol > 1e-4 else ""))
+    return tol
 
 
 @pytest.mark.parametrize("case", CASES)

@@ -89,10 +89,13 @@ def test_plan_matches_interpreter_and_autograd(case):
         assert rel_l2(got, want_i) < tol * 5, f"{case}: H.v vs fp64 interpreter {rel_l2(got, want_i):.3e}"
         want_a = torch.autograd.grad(in_grad, params, grad_outputs=vec, retain_graph=True)
         e = rel_l2(got, want_a)
-        assert e < max(1e-4, tol * 5), f"{case}: H.v vs autograd double backward {e:.3e}"
+        reduced = tol >= 1e-2      # bf16 / fp16 autocast graph: the reference's own double backward runs in bf16
+        # fp32: 1e-4 (BASELINE.json north_star).  Reduced precision: 2e-2 = two independently bf16-rounded evaluations
+        # of the same product, each within the north_star's 1e-2 of the exact value
+        assert e < (2e-2 if reduced else max(1e-4, tol * 5)), f"{case}: H.v vs autograd double backward {e:.3e}"
         for g_, w_ in zip(got, want_a):   # per-tensor, so a wrong small tensor is not hidden by a big one
             if float(w_.norm()) > 0:
-                assert rel_l2([g_], [w_]) < max(3e-4, tol * 20), f"{case}: tensor {tuple(g_.shape)}"
+                assert rel_l2([g_], [w_]) < (6e-2 if reduced else max(3e-4, tol * 20)), f"{case}: tensor {tuple(g_.shape)}"
 
 
 def test_generic_conv_path_on_small_channels(monkeypatch):
