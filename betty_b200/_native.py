@@ -62,6 +62,7 @@ _SIGS = {
     "bb_plan_invalidate_constants": ([C.c_void_p], 0),
     "bb_plan_graph_captures": ([C.c_void_p], 0),
     "bb_plan_node_route": ([C.c_void_p, C.c_int, C.c_int], 0),
+    "bb_convblock_ws_bytes": ([C.c_int] * 9, 0),
     "bb_plan_neumann_loop": ([C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_int, C.c_void_p], None),
     "bb_plan_cg_loop": ([C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -121,7 +122,7 @@ def lib() -> C.CDLL:
             for name, (argtypes, _) in _SIGS.items():
                 fn = getattr(l, name)
                 fn.argtypes = argtypes
-                fn.restype = C.c_int
+                fn.restype = C.c_int64 if name.endswith("_bytes") and name != "bb_node_bytes" and name != "bb_kloop_ws_bytes" else C.c_int
             l.bb_version.restype = C.c_char_p
             _lib = l
     return _lib

@@ -131,6 +131,57 @@ def _events():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
+class _PlanEntry:
+    """What one traced computation needs on the device: the native plan and the K-loop arenas its descriptors and
+    captured graphs point into."""
+
+    def __init__(self, plan, layout, d, hd, acc, out):
+        self.plan, self.layout, self.d, self.hd, self.acc, self.out = plan, layout, d, hd, acc, out
+        self.r = None
+        self.in_use = False
+
+
+class PlanCache:
+    """Plans keyed by tape signature (trace.tape_signature).  A training loop calls the plugin every few steps with
+    the same model and batch shape: tracing the forward is unavoidable (the reference runs it too, neumann.py:31),
+    but lowering, descriptor building, buffer allocation, tensor-map encoding and CUDA-graph capture are paid once --
+    a hit copies the new forward's values behind the pointers the plan already holds (HvpPlan.rebind)."""
+
+    def __init__(self):
+        import collections
+
+        self.entries = collections.OrderedDict()
+        self.hits = self.misses = 0
+
+    @property
+    def capacity(self) -> int:
+        return int(os.environ.get("BB200_PLAN_CACHE", "4"))
+
+    def get(self, key):
+        e = self.entries.get(key)
+        if e is not None and not e.in_use:
+            self.entries.move_to_end(key)
+            return e
+        return None
+
+    def put(self, key, entry):
+        if self.capacity <= 0:
+            return
+        self.entries[key] = entry
+        self.entries.move_to_end(key)
+        while len(self.entries) > self.capacity:
+            k, old = next(iter(self.entries.items()))
+            if old.in_use and len(self.entries) <= self.capacity + 2:
+                break
+            del self.entries[k]
+
+    def clear(self):
+        self.entries.clear()
+
+
+plan_cache = PlanCache()
+
+
 class HypergradientCall:
     """One ``fn(vector, curr, prev, sync)`` invocation split into its three phases so that
     ``bench.py`` can time the K-loop alone: ``__init__`` = prologue (+ arenas, + native plan),
@@ -148,30 +199,83 @@ class HypergradientCall:
             raise ValueError(method)
         params = curr.trainable_parameters()
         self.dev = params[0].device
-        lay = self.layout = ArenaLayout.like(params)
-        # d = direction the HVP is taken along (v for Neumann, p for CG); hd = H.d
-        self.d, self.hd, self.acc, self.out = lay.new(self.dev), lay.new(self.dev), lay.new(self.dev), lay.new(self.dev)
-        self.r = lay.new(self.dev) if method == "cg" else None
-        self.ws = Workspace.get(self.dev)
+        self.entry = None
         self.in_grad = None
-        if settings.hvp == "native":
-            # prologue = the lower forward only (reference neumann.py:31 / cg.py:27), recorded as a tape; the
-            # gradient-with-graph of neumann.py:34 is needed only if the epilogue has to fall back to autograd
-            from .plan import HvpPlan
-            from .trace import record_tape
+        with torch.cuda.device(self.dev):
+            self.ws = Workspace.get(self.dev)
+            if settings.hvp == "native":
+                self._init_native(curr, params)
+            else:
+                lay = self.layout = ArenaLayout.like(params)
+                # d = direction the HVP is taken along (v for Neumann, p for CG); hd = H.d
+                self.d, self.hd, self.acc, self.out = (lay.new(self.dev) for _ in range(4))
+                self.in_loss, self.in_grad = lower_gradient(curr)
+                self.tape = None
+                self.hvp = AutogradHvp(self.in_grad, params, lay, self.d, self.hd)
+                self.native_epilogue = False
+            self.r = None
+            if method == "cg":
+                if self.entry is not None:
+                    if self.entry.r is None:
+                        self.entry.r = self.layout.new(self.dev)
+                    self.r = self.entry.r
+                else:
+                    self.r = self.layout.new(self.dev)
 
-            with _nvtx("betty_b200:prologue:trace"):
-                self.in_loss, self.tape = record_tape(lambda: curr.training_step_exec(curr.cur_batch), params)
-            with _nvtx("betty_b200:prologue:plan"):
-                self.hvp = HvpPlan(self.tape, params, lay, self.d, self.hd)
-            self.native_epilogue = settings.native_epilogue and self.hvp.g.native_epilogue_ok
+    def _init_native(self, curr, params):
+        # prologue = the lower forward only (reference neumann.py:31 / cg.py:27), recorded as a tape; the
+        # gradient-with-graph of neumann.py:34 is needed only if the epilogue has to fall back to autograd
+        from .plan import HvpPlan
+        from .trace import record_tape, tape_signature
+
+        with _nvtx("betty_b200:prologue:trace"):
+            self.in_loss, tape = record_tape(lambda: curr.training_step_exec(curr.cur_batch), params)
+        entry = None
+        key = None
+        if plan_cache.capacity > 0:
+            with _nvtx("betty_b200:prologue:signature"):
+                key = tape_signature(tape, extra=(bool(settings.cuda_graph), self.dev.index))
+            entry = plan_cache.get(key)
+        if entry is not None:
+            with _nvtx("betty_b200:prologue:rebind"):
+                if not entry.plan.rebind(tape):
+                    entry = None
+        if entry is not None:
+            plan_cache.hits += 1
+            self.tape = entry.plan.tape
         else:
-            self.in_loss, self.in_grad = lower_gradient(curr)
-            self.tape = None
-            self.hvp = AutogradHvp(self.in_grad, params, lay, self.d, self.hd)
-            self.native_epilogue = False
+            plan_cache.misses += 1
+            lay = ArenaLayout.like(params)
+            d, hd, acc, out = (lay.new(self.dev) for _ in range(4))
+            with _nvtx("betty_b200:prologue:plan"):
+                plan = HvpPlan(tape, params, lay, d, hd)
+            entry = _PlanEntry(plan, lay, d, hd, acc, out)
+            if key is not None:
+                plan_cache.put(key, entry)
+            self.tape = tape
+        entry.in_use = True
+        self.entry = entry
+        self.hvp, self.layout = entry.plan, entry.layout
+        self.d, self.hd, self.acc, self.out = entry.d, entry.hd, entry.acc, entry.out
+        self.native_epilogue = settings.native_epilogue and self.hvp.g.native_epilogue_ok
+
+    def release(self):
+        """Hand the cached plan back (end of the call)."""
+        if self.entry is not None:
+            self.entry.in_use = False
+            self.entry = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
     def solve(self, vector: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        with torch.cuda.device(self.dev):
+            return self._solve(vector)
+
+    def _solve(self, vector: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         global last_stats
         lay, s, n = self.layout, stream_ptr(), self.layout.total
         K, alpha, hvp = self.K, self.alpha, self.hvp
@@ -216,14 +320,19 @@ class HypergradientCall:
         return lay.views(self.out)
 
     def finish(self, prev, x, sync):
-        if self.native_epilogue:
-            with _nvtx("betty_b200:epilogue:native"):
-                return chain_boundary_seeds(self.hvp.mixed_seeds(self.out), prev, sync)
-        if self.in_grad is None:
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                self.in_grad = torch.autograd.grad(self.in_loss, self.curr.trainable_parameters(), create_graph=True)
-        return mixed_product(self.in_grad, prev, x, sync)
+        try:
+            with torch.cuda.device(self.dev):
+                if self.native_epilogue:
+                    with _nvtx("betty_b200:epilogue:native"):
+                        return chain_boundary_seeds(self.hvp.mixed_seeds(self.out), prev, sync)
+                if self.in_grad is None:
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        self.in_grad = torch.autograd.grad(self.in_loss, self.curr.trainable_parameters(),
+                                                           create_graph=True)
+                return mixed_product(self.in_grad, prev, x, sync)
+        finally:
+            self.release()
 
 
 def chain_boundary_seeds(seeds, prev, sync: bool):

@@ -35,7 +35,7 @@ class Val:
     """A lower-active tensor value."""
 
     __slots__ = ("vid", "base", "param_index", "parent", "viewfn", "full_cover", "name", "t", "a", "at",
-                 "writers", "needed", "zero_init", "ident", "boundary")
+                 "writers", "needed", "zero_init", "ident", "boundary", "interp_only")
 
     def __init__(self, vid, base, param_index=None, parent=None, viewfn=None, full_cover=True, name="", ident=False):
         self.vid = vid
@@ -51,6 +51,7 @@ class Val:
         self.zero_init = False              # root adjoint buffers must be zeroed before BB / TB
         self.ident = ident                  # alias whose buffers are *exactly* the parent's (cast, x + const)
         self.boundary = False               # upper-dependent constant (requires_grad, not from the lower params)
+        self.interp_only = False            # internal value of a fused node: only the torch interpreter gives it buffers
 
     @property
     def root(self) -> "Val":
@@ -100,6 +101,7 @@ class Graph:
     stats: Dict[str, int] = field(default_factory=dict)
     boundaries: List[Val] = field(default_factory=list)   # upper-dependent tensors entering the lower tape
     native_epilogue_ok: bool = True                        # every such tensor was captured as a boundary value
+    validators: List[Any] = field(default_factory=list)    # (check() -> bool, message): data-dependent refusals
 
 
 # --------------------------------------------------------------------------------------------------
@@ -162,6 +164,7 @@ class _Lowering:
         self.params: List[Val] = []
         self.boundaries: List[Val] = []
         self.native_epilogue_ok = True
+        self.validators: List[Tuple[Callable[[], bool], str]] = []   # value-dependent refusals, re-checked per call
         self._pending_upper: set = set()
         for i, p in enumerate(tape.params):
             v = self._new(p, param_index=i, name=f"param{i}")
@@ -249,9 +252,11 @@ class _Lowering:
         g = Graph(self.nodes, self.all_vals, self.params, loss)
         g.boundaries = self.boundaries
         g.native_epilogue_ok = self.native_epilogue_ok
+        g.validators = self.validators
         if fold_quadratic:
             _fold_quadratic_regularisers(g)
         _fuse_relu_maxpool(g)
+        _fuse_data_conv_block(g)
         _analyse(g)
         return g
 
@@ -355,8 +360,10 @@ class _Lowering:
             if a[0].dim() != 2:
                 raise UnsupportedGraph("nll_loss on non-2D input")
             self.need_contig(x, name)
-            if bool((target == ignore_index).any()):
+            check = lambda target=target, ii=ignore_index: bool((target == ii).any())
+            if check():
                 raise UnsupportedGraph("nll_loss with ignored targets")
+            self.validators.append((check, "nll_loss with ignored targets"))   # re-run when a cached plan is reused
             out = op.out[0]
             scale = {0: 1.0, 1: 1.0 / a[0].shape[0], 2: 1.0}[reduction]
             self.emit("nll", [x], out, name, target=target, reduction=reduction, scale=scale)
@@ -418,7 +425,8 @@ class _Lowering:
             x = A(a[0])
             out, mask = op.out
             p = float(a[1])
-            self.emit("mulc", [x], out, name, const=mask.to(a[0].dtype if a[0].dtype == torch.float64 else torch.float32) * (1.0 / (1.0 - p)), scalar=None)
+            fn = lambda mask=mask, dt=(a[0].dtype if a[0].dtype == torch.float64 else torch.float32), p=p: mask.to(dt) * (1.0 / (1.0 - p))
+            self.emit("mulc", [x], out, name, const=fn(), const_fn=fn, const_srcs=[mask], scalar=None)
             return
         raise UnsupportedGraph(f"no second-order rule for {name}")
 
@@ -445,16 +453,20 @@ class _Lowering:
             self.emit("mul2", [x, u] if c is a[1] else [u, x], op.out, name)
             return
         if isinstance(c, torch.Tensor):
-            cc = c.detach()
-            cc = cc if cc.dtype == torch.float64 else cc.to(torch.float32)  # fp64 only in the CPU rule tests
-            if is_div:
-                cc = 1.0 / cc
-            if tuple(cc.shape) != tuple(op.out.shape):
-                cc = cc.expand(op.out.shape)
             if tuple(x.base.shape) != tuple(op.out.shape):
                 raise UnsupportedGraph("broadcast of the parameter-dependent factor")
-            self.emit("mulc", [x], op.out, name, const=cc.contiguous(),
-                      scalar=None)
+
+            def fn(c=c, is_div=is_div, shape=tuple(op.out.shape)):
+                cc = c.detach()
+                cc = cc if cc.dtype == torch.float64 else cc.to(torch.float32)  # fp64 only in the CPU rule tests
+                if is_div:
+                    cc = 1.0 / cc
+                if tuple(cc.shape) != shape:
+                    cc = cc.expand(shape)
+                return cc.contiguous()
+
+            # const_fn / const_srcs: how to rebuild the constant when a cached plan serves new values (plan.rebind)
+            self.emit("mulc", [x], op.out, name, const=fn(), const_fn=fn, const_srcs=[c], scalar=None)
         else:
             s = float(c)
             self.emit("unary", [x], op.out, name, kind="scale", scalar=(1.0 / s if is_div else s))
@@ -821,6 +833,88 @@ def _fuse_relu_maxpool(g: Graph):
     if drop:
         g.nodes = [n for n in g.nodes if id(n) not in drop]
         g.stats = {**g.stats, "relu_pool_fused": len(drop)}
+
+
+def _fuse_data_conv_block(g: Graph):
+    """conv3x3(data) -> BatchNorm2d(batch stats) -> [ReLU] -> MaxPool2d(2) of a DATA input becomes one ``convblock`` node
+    (csrc/convblock.cu): with a constant input the conv tangent is linear in the direction, so the BatchNorm
+    statistics of every pass are products with per-call Gram matrices and only pooled-size arrays are streamed per
+    iteration -- the conv-output-sized tangent / adjoint buffers (y, z) are never allocated.
+    (First block of reference examples/implicit_maml/models.py:9-24.)  The member nodes stay in ``attrs['members']``:
+    the torch interpreter executes them one by one, and the SURVEY 8(d) byte count still sees three layers."""
+    import os
+
+    if os.environ.get("BB200_NO_CONVBLOCK"):
+        return
+    consumers: Dict[int, List[Node]] = {}
+    for n in g.nodes:
+        for v in n.ins:
+            if v is not None:
+                consumers.setdefault(id(v.root), []).append(n)
+    out_nodes = []
+    dropped = set()
+    fused = 0
+    for n in g.nodes:
+        if id(n) in dropped:
+            continue
+        blk = _match_data_conv_block(g, n, consumers)
+        if blk is None:
+            out_nodes.append(n)
+            continue
+        conv, bn, pool = blk
+        w, b = conv.ins[1], conv.ins[2]
+        gam, bet = bn.ins[1], bn.ins[2]
+        conv.beta, bn.beta, pool.beta = [0, 1, 1], [0, 1, 1], [0]   # what _analyse would give the members
+        node = Node("convblock", [w, b, gam, bet], pool.out,
+                    dict(members=[conv, bn, pool], X=conv.attrs["X"], W=conv.attrs["W"], Y=conv.out.base,
+                         padding=conv.attrs["padding"], eps=bn.attrs["eps"], gamma=bn.attrs["gamma"],
+                         indices=pool.attrs["indices"], relu=bool(pool.attrs.get("relu"))),
+                    src="conv3x3(data)+batch_norm+relu+max_pool2d" if pool.attrs.get("relu") else "conv3x3(data)+batch_norm+max_pool2d")
+        conv.out.interp_only = bn.out.interp_only = True
+        out_nodes.append(node)
+        dropped.update((id(bn), id(pool)))
+        fused += 1
+    if fused:
+        g.nodes = out_nodes
+        g.stats = {**g.stats, "conv_blocks_fused": fused}
+
+
+def _match_data_conv_block(g: Graph, conv: Node, consumers) -> Optional[Tuple[Node, Node, Node]]:
+    if conv.op != "conv2d" or conv.ins[0] is not None or conv.ins[1] is None:
+        return None
+    at = conv.attrs
+    W = at["W"]
+    if (at["groups"] != 1 or tuple(at["stride"]) != (1, 1) or tuple(at["dilation"]) != (1, 1)
+            or tuple(W.shape[2:]) != (3, 3) or W.shape[1] not in (1, 3) or W.shape[0] > 64):
+        return None
+    def is_param(v):
+        # the parameter itself, or its autocast copy (an identity alias: same tangent / adjoint-tangent slices)
+        while v is not None and v.parent is not None and v.ident:
+            v = v.parent
+        return v is not None and v.parent is None and v.param_index is not None
+
+    if not is_param(conv.ins[1]) or (conv.ins[2] is not None and not is_param(conv.ins[2])):
+        return None
+    y = conv.out
+    cons = consumers.get(id(y), [])
+    if len(cons) != 1 or cons[0].op != "batchnorm" or cons[0].ins[0] is not y or y is g.loss:
+        return None
+    bn = cons[0]
+    for v in bn.ins[1:]:
+        if v is not None and not is_param(v):
+            return None
+    if bn.attrs["gamma"] is not None and bn.attrs["gamma"].dtype != torch.float32:
+        return None
+    z = bn.out
+    cons = consumers.get(id(z), [])
+    if len(cons) != 1 or cons[0].op != "maxpool2d" or cons[0].ins[0] is not z or z is g.loss:
+        return None
+    pool = cons[0]
+    if tuple(pool.attrs.get("kernel", ())) != (2, 2) or not pool.attrs.get("disjoint"):
+        return None
+    if not (y.base.is_contiguous() and z.base.is_contiguous() and pool.out.base.is_contiguous()):
+        return None
+    return conv, bn, pool
 
 
 def lower_tape(tape, fold_quadratic: bool = True) -> Graph:

@@ -18,7 +18,7 @@ from .ir import Graph, Node, UnsupportedGraph, Val, _is_dense, lower_tape
 BB_MAX_DIMS = 6
 OPS = {"unary": 1, "copy": 2, "add2": 3, "mulc": 4, "mul2": 5, "sumall": 6, "gemm": 7, "conv2d": 8,
        "maxpool2d": 9, "batchnorm": 10, "layernorm": 11, "softmax": 12, "logsoftmax": 13, "nll": 14,
-       "bce_logits": 15, "embedding": 16, "diagshift": 17, "avgpool2d": 18}
+       "bce_logits": 15, "embedding": 16, "diagshift": 17, "avgpool2d": 18, "convblock": 19}
 UNARY = {"relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4, "pow": 5, "scale": 6, "neg": 6}
 PASS_BB, PASS_TF, PASS_TB = 0, 1, 2
 
@@ -61,11 +61,14 @@ class HvpPlan:
         self.dry_run = dry_run
         self.g: Graph = lower_tape(tape)
         self._keep: List[torch.Tensor] = []   # constants / scratch referenced by raw pointer
+        self._derived: list = []              # (constant, thunk recomputing it from the tape's tensors) -- see rebind()
         self._views: dict = {}                # (id(alias value), kind) -> torch view of its root buffer
         self._alloc_buffers()
         self._build_nodes()
         self.launches_per_iter = 0
         self.serves = 1                       # hypergradient calls this plan has served (plan cache, engine.py)
+        self.boundary_bases = None            # vid -> upper-dependent tensor of the CURRENT call's forward (after rebind)
+        self._locator = None
         if dry_run:
             return
         self.side = torch.cuda.Stream(device=self.dev)
@@ -126,13 +129,22 @@ class HvpPlan:
     def _ptr(self, t: Optional[torch.Tensor]) -> int:
         return 0 if t is None else t.data_ptr()
 
-    def _const(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
-        t = t.detach()
-        if dtype is not None and t.dtype != dtype:
-            t = t.to(dtype)
-        t = t.to(self.dev).contiguous()
-        self._keep.append(t)
-        return t
+    def _const(self, t: torch.Tensor, dtype=None, recipe=None) -> torch.Tensor:
+        """A constant the descriptors point at.  ``recipe`` (or, for a converted copy of a tape tensor, the conversion
+        itself) is remembered so that ``rebind`` can refresh the values in place when the plan is reused."""
+        def make(src=t):
+            o = src.detach()
+            if dtype is not None and o.dtype != dtype:
+                o = o.to(dtype)
+            return o.to(self.dev).contiguous()
+
+        out = make()
+        self._keep.append(out)
+        if recipe is not None:
+            self._derived.append((out, lambda: make(recipe())))
+        elif out.data_ptr() != t.data_ptr():
+            self._derived.append((out, make))
+        return out
 
     def _scratch(self, nbytes: int) -> torch.Tensor:
         t = torch.zeros(_align(nbytes, 8) // 8, dtype=torch.float64, device=self.dev)
@@ -302,7 +314,7 @@ class HvpPlan:
 
     def _n_mulc(self, n: Node, r):
         x = n.ins[0]
-        c = self._const(n.attrs["const"], torch.float32)
+        c = self._const(n.attrs["const"], torch.float32, recipe=n.attrs.get("const_fn"))
         r["aux"][0] = c.data_ptr()
         self._slot(r, 0, x, x.base)
         self._slot(r, 3, n.out, None)
@@ -392,6 +404,35 @@ class HvpPlan:
         r["aux"][0] = self._const(idx, torch.int64).data_ptr()
         self._slot(r, 0, x, x.base)
         self._slot(r, 3, n.out, n.out.base)
+
+    def _n_convblock(self, n: Node, r):
+        """Fused data-input conv3x3 -> BatchNorm -> [ReLU] -> MaxPool2d(2) (csrc/convblock.cu; slot map there)."""
+        w, b, gam, bet = n.ins
+        X, W, Y = n.attrs["X"], n.attrs["W"], n.attrs["Y"]
+        Nn, Cc, H, Wd = X.shape
+        O = W.shape[0]
+        _, _, HO, WO = Y.shape
+        _, _, HP, WP = n.out.base.shape
+        ph, pw = n.attrs["padding"]
+        r["dims"][0:16] = (Nn, Cc, H, Wd, O, 3, 3, HO, WO, 1, 1, ph, pw, HP, WP, int(n.attrs["relu"]))
+        r["f"][0] = n.attrs["eps"]
+        r["kind"] = int(X.dtype in (torch.bfloat16, torch.float16))
+        if not (X.is_contiguous() and Y.is_contiguous()):
+            raise UnsupportedGraph("convblock operands must be NCHW-contiguous")
+        self._slot(r, 0, w, None)
+        self._slot(r, 1, b, None)
+        g_t = n.attrs["gamma"]
+        self._slot(r, 2, gam, g_t)                       # base[2] = gamma values (fp32 parameter)
+        self._slot(r, 3, n.out, n.out.base)
+        r["base"][0], r["dt"][0] = X.data_ptr(), _dt(X)
+        r["base"][1], r["dt"][1] = Y.data_ptr(), _dt(Y)
+        nbytes = int(N.lib().bb_convblock_ws_bytes(Nn, Cc, H, Wd, O, HO, WO, HP, WP))
+        ws = torch.zeros(nbytes // 8 + 1, dtype=torch.float64, device=self.dev)
+        self._keep.append(ws)
+        r["aux"][0] = ws.data_ptr()
+        r["aux"][1] = self._ptr(self.buf(bet, "t"))
+        r["aux"][2] = self._ptr(self.buf(bet, "at"))
+        r["aux"][3] = self._const(n.attrs["indices"], torch.int64).data_ptr()
 
     def _n_avgpool2d(self, n: Node, r):
         x = n.ins[0]
@@ -515,7 +556,102 @@ class HvpPlan:
             self.d_arena.copy_(x_arena)
         self._on_side(lambda s: N.call("bb_plan_hvp_replay" if (self.use_graph and self.serves > 1) else "bb_plan_hvp", self.handle, s))
         self._count_iter(1, 0)
-        return [(b.base, b.at) for b in self.g.boundaries if b.parent is None and b.at is not None]
+        bases = self.boundary_bases or {}
+        return [(bases.get(b.vid, b.base), b.at) for b in self.g.boundaries if b.parent is None and b.at is not None]
+
+    # ---- reuse across calls (engine.py plan cache) ------------------------------------------------------------
+    def tape_tensors(self) -> List[torch.Tensor]:
+        """Every tape tensor this plan reads through a raw pointer or a recipe: bases of live values, the tensors the
+        node descriptors were built from, sources of derived constants."""
+        seen, out = set(), []
+
+        def add(t):
+            if isinstance(t, torch.Tensor) and id(t) not in seen:
+                seen.add(id(t))
+                out.append(t)
+
+        for v in self.g.values:
+            if (v.needed or v.boundary) and v.param_index is None:
+                add(v.base)
+
+        def visit(n):
+            for key, val in n.attrs.items():
+                if key == "members":
+                    for m in val:
+                        visit(m)
+                elif key == "const_srcs":
+                    for t in val:
+                        add(t)
+                elif key != "const":
+                    add(val)
+            if n.out is not None:
+                add(n.out.base)
+
+        for n in self.g.nodes:
+            visit(n)
+        return out
+
+    def rebind(self, new_tape) -> bool:
+        """Serve a new call whose tape has the same signature (trace.tape_signature): the new forward's values are
+        copied INTO the tensors this plan already points at (every descriptor, tensor map and captured graph stays
+        valid), derived constants are recomputed, value-dependent refusals re-checked, the packs of K-loop constants
+        invalidated and the base-backward pass re-run.  Returns False if some tensor cannot be located (caller then
+        builds a fresh plan)."""
+        from .trace import op_tensors, tensor_locator
+
+        if self._locator is None:
+            self._locator = tensor_locator(self.tape)
+        cache: dict = {}
+
+        def new_of(t_old):
+            loc = self._locator.get(id(t_old))
+            if loc is None:
+                return None
+            i, k = loc
+            lst = cache.get(i)
+            if lst is None:
+                lst = cache[i] = op_tensors(new_tape.ops[i])
+            return lst[k]
+
+        param_ids = {id(p) for p in self.tape.params}
+        dsts, srcs = [], []
+        done = set()
+        for t_old in self.tape_tensors():
+            if id(t_old) in param_ids:
+                continue
+            t_new = new_of(t_old)
+            if t_new is None:
+                return False
+            if t_new.data_ptr() == t_old.data_ptr():
+                continue                      # same storage both times (views of parameters, upper parameters)
+            key = (t_old.data_ptr(), tuple(t_old.shape), t_old.stride())
+            if key in done:
+                continue
+            done.add(key)
+            dsts.append(t_old.detach())
+            srcs.append(t_new.detach())
+        bases = {}
+        for b in self.g.boundaries:
+            if b.parent is None:
+                t_new = new_of(b.base)
+                if t_new is None:
+                    return False
+                bases[b.vid] = t_new          # the NEW upper graph is what the epilogue must differentiate through
+        with torch.no_grad():
+            if dsts:
+                torch._foreach_copy_(dsts, srcs)
+            for const, thunk in self._derived:
+                const.copy_(thunk())
+        for check, msg in getattr(self.g, "validators", ()):
+            if check():
+                raise UnsupportedGraph(msg)
+        self.boundary_bases = bases
+        N.call("bb_plan_invalidate_constants", self.handle)
+        self.g.loss.root.a.zero_()
+        self.buf(self.g.loss, "a").fill_(1.0)
+        self.run_pass(PASS_BB)
+        self.serves += 1
+        return True
 
     def profile(self, pas: int) -> np.ndarray:
         ms = np.zeros(len(self.recs), dtype=np.float32)
@@ -530,6 +666,12 @@ class HvpPlan:
         n = self.g.nodes[i]
         if n.op == "diagshift":
             return 12 * sum(p.base.numel() for p in n.ins) if pas == PASS_TB else 0
+        if n.op == "convblock":
+            # what the fused rule streams: x once, then pooled-size arrays (arg-max code 1 B, xhat* 4 B, dxhat* 4 B,
+            # pooled tangent / adjoint-tangent 4 B, masked base adjoint 4 B)
+            X, q = n.attrs["X"], n.out.base.numel()
+            xb = X.numel() * X.element_size()
+            return int(xb + q * {PASS_TF: 13, PASS_TB: 17}.get(pas, 17))
         out_n = n.out.base.numel()
         total = 0
         uses_base = {"unary": (0,), "mul2": (0, 1), "gemm": (0, 1), "conv2d": (0, 1), "batchnorm": (0,),

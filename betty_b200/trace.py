@@ -63,3 +63,69 @@ def record_tape(fn: Callable[[], Any], params: Sequence[torch.Tensor]) -> Tuple[
     loss = out["loss"] if isinstance(out, dict) else (out[0] if isinstance(out, (tuple, list)) else out)
     tape.loss = loss
     return loss, tape
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# tape signatures (plan cache, engine.py): two tapes with equal signatures are the same computation on different values
+# --------------------------------------------------------------------------------------------------------------------
+def op_tensors(op: TapeOp) -> List[torch.Tensor]:
+    """Every tensor an op touches, in a fixed order (args, kwargs by key, outputs; nested lists flattened).  The
+    position in this list identifies "the same tensor" across two tapes of equal signature."""
+    out: List[torch.Tensor] = []
+
+    def walk(x):
+        if isinstance(x, torch.Tensor):
+            out.append(x)
+        elif isinstance(x, (list, tuple)):
+            for y in x:
+                walk(y)
+
+    walk(op.args)
+    if op.kwargs:
+        for k in sorted(op.kwargs):
+            walk(op.kwargs[k])
+    walk(op.out)
+    return out
+
+
+def _plain(x):
+    if isinstance(x, torch.Tensor):
+        return None
+    if isinstance(x, (list, tuple)):
+        return tuple(_plain(y) for y in x)
+    if isinstance(x, (int, float, bool, str, type(None), torch.dtype, torch.device, torch.layout, torch.memory_format)):
+        return x
+    return repr(x)
+
+
+def tape_signature(tape: Tape, extra=()) -> tuple:
+    """Hashable description of the recorded computation: op sequence, non-tensor arguments, and for every tensor slot
+    either (shape, stride, dtype, requires_grad) at its first appearance or the index of that first appearance
+    (the dataflow).  Parameter storage addresses are part of it: a cached plan points at them."""
+    seen: dict = {}
+    parts = [tuple(extra), tuple((p.data_ptr(), tuple(p.shape), p.dtype) for p in tape.params)]
+    for p in tape.params:
+        seen[id(p)] = len(seen)
+    for op in tape.ops:
+        items = [op.func, _plain(op.args), _plain(tuple(sorted(op.kwargs.items()))) if op.kwargs else None]
+        for t in op_tensors(op):
+            j = seen.get(id(t))
+            if j is None:
+                seen[id(t)] = len(seen)
+                items.append((tuple(t.shape), t.stride(), t.dtype, t.requires_grad, t.device.index))
+            else:
+                items.append(j)
+        parts.append(tuple(items))
+    loss = tape.loss
+    parts.append(seen.get(id(loss), -1))
+    return tuple(parts)
+
+
+def tensor_locator(tape: Tape) -> dict:
+    """id(tensor) -> (op index, position in op_tensors) of its first appearance."""
+    loc: dict = {}
+    for i, op in enumerate(tape.ops):
+        for k, t in enumerate(op_tensors(op)):
+            if id(t) not in loc:
+                loc[id(t)] = (i, k)
+    return loc

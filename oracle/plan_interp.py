@@ -20,7 +20,7 @@ class Interp:
     def __init__(self, graph: Graph, dtype=torch.float64):
         self.g, self.dtype = graph, dtype
         for v in graph.values:
-            if v.parent is None and (v.needed or v.param_index is not None or v.boundary):
+            if v.parent is None and (v.needed or v.param_index is not None or v.boundary or getattr(v, "interp_only", False)):
                 shape, stride = v.base.shape, v.base.stride()
                 mk = lambda: torch.zeros_like(v.base, dtype=dtype)  # preserves dense strides
                 v.t, v.a, v.at = mk(), mk(), mk()
@@ -76,6 +76,20 @@ class Interp:
         self.tangent_forward()
         self.tangent_backward()
         return [p.at.clone() for p in self.g.params]
+
+    # ---- convblock: fused conv3x3(data) -> batch_norm -> [relu] -> max_pool2d (ir._fuse_data_conv_block) -------------
+    # The executable specification of the fused CUDA node is the composition of its three member rules.
+    def tf_convblock(self, n):
+        for m in n.attrs["members"]:
+            getattr(self, "tf_" + m.op)(m)
+
+    def bb_convblock(self, n):
+        for m in reversed(n.attrs["members"]):
+            getattr(self, "bb_" + m.op)(m)
+
+    def tb_convblock(self, n):
+        for m in reversed(n.attrs["members"]):
+            getattr(self, "tb_" + m.op)(m)
 
     # ---- diagshift: folded c*sum((w-const)^2) terms (ir._fold_quadratic_regularisers) -----------------
     def tf_diagshift(self, n):
