@@ -34,15 +34,16 @@ _SIGS = {
     "bb_kloop_ws_bytes": ([], 0),
     "bb_neumann_update": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p], 1),
     "bb_scale": ([C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p], 1),
-    "bb_cg_dots": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_void_p, C.c_void_p], 1),
+    "bb_cg_dots": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int64, C.c_void_p, C.c_void_p], 1),
     "bb_cg_init": ([C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p], 1),
-    "bb_cg_update_xr": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p], 1),
+    "bb_cg_update_xr": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p], 1),
     "bb_cg_update_p": ([C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p], 1),
     "bb_mt_copy": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p], 1),
     "bb_mt_axpby": ([C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_float, C.c_void_p], 1),
     "bb_mt_sumsq": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], 1),
     "bb_fd_eps": ([C.c_void_p, C.c_double, C.c_void_p], 1),
     "bb_mt_fd_combine": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], 1),
+    "bb_mt_adam_precondition": ([C.c_void_p, C.c_int, C.c_void_p], 1),
     "bb_gemm_bf16_tc": ([C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                          C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p], 1),
     "bb_gemm_bf16_tma": ([C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
@@ -59,6 +60,7 @@ _SIGS = {
     "bb_plan_profile": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], None),
     "bb_plan_hvp": ([C.c_void_p, C.c_void_p], None),
     "bb_plan_hvp_replay": ([C.c_void_p, C.c_void_p], None),
+    "bb_plan_set_uniform_shift": ([C.c_void_p, C.c_int, C.c_double], 0),
     "bb_plan_invalidate_constants": ([C.c_void_p], 0),
     "bb_plan_graph_captures": ([C.c_void_p], 0),
     "bb_plan_node_route": ([C.c_void_p, C.c_int, C.c_int], 0),

@@ -36,10 +36,12 @@ __global__ void __launch_bounds__(kThreads) neumann_update_kernel(float* __restr
     const float4 h = bb::ld4_stream(hv + 4 * i);
     float4 q = bb::ld4(p + 4 * i);
     // v - alpha*(hv + shift*v): `shift` folds a declared c*I curvature term into the update
-    a.x = a.x - alpha * (h.x + shift * a.x);
-    a.y = a.y - alpha * (h.y + shift * a.y);
-    a.z = a.z - alpha * (h.z + shift * a.z);
-    a.w = a.w - alpha * (h.w + shift * a.w);
+    if (shift != 0.f) {
+      a.x = a.x - alpha * fmaf(shift, a.x, h.x); a.y = a.y - alpha * fmaf(shift, a.y, h.y);
+      a.z = a.z - alpha * fmaf(shift, a.z, h.z); a.w = a.w - alpha * fmaf(shift, a.w, h.w);
+    } else {
+      a.x = a.x - alpha * h.x; a.y = a.y - alpha * h.y; a.z = a.z - alpha * h.z; a.w = a.w - alpha * h.w;
+    }
     q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
     bb::st4(v + 4 * i, a);
     bb::st4(p + 4 * i, q);
@@ -76,14 +78,17 @@ __device__ __forceinline__ Ws ws_view(void* ws) {
 
 __global__ void __launch_bounds__(kThreads) cg_dots_kernel(const float* __restrict__ r, const float* __restrict__ hp,
                                                            const float* __restrict__ p, float cg_alpha,
-                                                           int first, int64_t n4, void* wsraw) {
+                                                           float shift, int first, int64_t n4, void* wsraw) {
   __shared__ double red[32];
   Ws w = ws_view(wsraw);
   float acc_php = 0.f, acc_rr = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 h = bb::ld4(hp + 4 * i);
+    float4 h = bb::ld4(hp + 4 * i);
     const float4 q = bb::ld4(p + 4 * i);
+    if (shift != 0.f) {   // H p = hp + shift p: a declared c*I curvature term folded into the vector pass
+      h.x = fmaf(shift, q.x, h.x); h.y = fmaf(shift, q.y, h.y); h.z = fmaf(shift, q.z, h.z); h.w = fmaf(shift, q.w, h.w);
+    }
     acc_php += (cg_alpha * h.x) * q.x + (cg_alpha * h.y) * q.y + (cg_alpha * h.z) * q.z + (cg_alpha * h.w) * q.w;
     if (first) {
       const float4 a = bb::ld4(r + 4 * i);
@@ -124,8 +129,8 @@ __global__ void __launch_bounds__(kThreads) cg_init_kernel(const float* __restri
 // ---- K3 -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) cg_update_xr_kernel(float* __restrict__ x, float* __restrict__ r,
                                                                 const float* __restrict__ p,
-                                                                const float* __restrict__ hp, int64_t n4,
-                                                                void* wsraw) {
+                                                                const float* __restrict__ hp, float shift,
+                                                                int64_t n4, void* wsraw) {
   __shared__ double red[32];
   Ws w = ws_view(wsraw);
   const float alpha = (float)w.s->alpha;
@@ -135,7 +140,10 @@ __global__ void __launch_bounds__(kThreads) cg_update_xr_kernel(float* __restric
     float4 xx = bb::ld4(x + 4 * i);
     float4 rr = bb::ld4(r + 4 * i);
     const float4 q = bb::ld4(p + 4 * i);
-    const float4 h = bb::ld4_stream(hp + 4 * i);
+    float4 h = bb::ld4_stream(hp + 4 * i);
+    if (shift != 0.f) {
+      h.x = fmaf(shift, q.x, h.x); h.y = fmaf(shift, q.y, h.y); h.z = fmaf(shift, q.z, h.z); h.w = fmaf(shift, q.w, h.w);
+    }
     xx.x += alpha * q.x; xx.y += alpha * q.y; xx.z += alpha * q.z; xx.w += alpha * q.w;
     rr.x -= alpha * h.x; rr.y -= alpha * h.y; rr.z -= alpha * h.z; rr.w -= alpha * h.w;
     acc += rr.x * rr.x + rr.y * rr.y + rr.z * rr.z + rr.w * rr.w;
@@ -171,7 +179,10 @@ __global__ void __launch_bounds__(kMtThreads) mt_copy_kernel(const bb_mt_chunk* 
   const bb_mt_chunk c = tab[blockIdx.x];
   const float* src = reinterpret_cast<const float*>(dir == 0 ? c.a : c.b);
   float* dst = reinterpret_cast<float*>(dir == 0 ? c.b : c.a);
-  for (int i = threadIdx.x; i < c.n; i += kMtThreads) dst[i] = src[i];
+  const bool vec = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+  const int n4 = vec ? c.n >> 2 : 0;
+  for (int i = threadIdx.x; i < n4; i += kMtThreads) bb::st4(dst + 4 * i, bb::ld4(src + 4 * i));
+  for (int i = 4 * n4 + threadIdx.x; i < c.n; i += kMtThreads) dst[i] = src[i];
 }
 
 // b <- coef_a * scale_dev * a + coef_b * b   (scale_dev may be null => 1; a may alias b)
@@ -181,10 +192,26 @@ __global__ void __launch_bounds__(kMtThreads) mt_axpby_kernel(const bb_mt_chunk*
   const float s = coef_a * (scale_dev ? (float)(*scale_dev) : 1.f);
   const float* a = reinterpret_cast<const float*>(c.a);
   float* b = reinterpret_cast<float*>(c.b);
+  // 128-bit body when both chunk pointers are 16-byte aligned (chunks start at tensor base + k*BB_MT_CHUNK floats,
+  // so this is the case for every chunk of an allocator-aligned tensor), scalar tail / fallback otherwise
+  const bool vec = (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+  const int n4 = vec ? c.n >> 2 : 0;
+  for (int i = threadIdx.x; i < n4; i += kMtThreads) {
+    const float4 va = bb::ld4(a + 4 * i);
+    float4 vb;
+    if (coef_b == 0.f) {
+      vb = make_float4(s * va.x, s * va.y, s * va.z, s * va.w);
+    } else {
+      vb = bb::ld4(b + 4 * i);
+      vb.x = s * va.x + coef_b * vb.x; vb.y = s * va.y + coef_b * vb.y;
+      vb.z = s * va.z + coef_b * vb.z; vb.w = s * va.w + coef_b * vb.w;
+    }
+    bb::st4(b + 4 * i, vb);
+  }
   if (coef_b == 0.f) {
-    for (int i = threadIdx.x; i < c.n; i += kMtThreads) b[i] = s * a[i];
+    for (int i = 4 * n4 + threadIdx.x; i < c.n; i += kMtThreads) b[i] = s * a[i];
   } else {
-    for (int i = threadIdx.x; i < c.n; i += kMtThreads) b[i] = s * a[i] + coef_b * b[i];
+    for (int i = 4 * n4 + threadIdx.x; i < c.n; i += kMtThreads) b[i] = s * a[i] + coef_b * b[i];
   }
 }
 
@@ -194,7 +221,12 @@ __global__ void __launch_bounds__(kMtThreads) mt_sumsq_kernel(const bb_mt_chunk*
   const bb_mt_chunk c = tab[blockIdx.x];
   const float* a = reinterpret_cast<const float*>(c.a);
   float acc = 0.f;
-  for (int i = threadIdx.x; i < c.n; i += kMtThreads) acc += a[i] * a[i];
+  const int n4 = (((uintptr_t)a) & 15) == 0 ? c.n >> 2 : 0;
+  for (int i = threadIdx.x; i < n4; i += kMtThreads) {
+    const float4 v = bb::ld4(a + 4 * i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int i = 4 * n4 + threadIdx.x; i < c.n; i += kMtThreads) acc += a[i] * a[i];
   double b = bb::block_sum<double>((double)acc, red);
   // chunk count can exceed kMaxGrid: accumulate with a fixed-order scheme per slot
   if (threadIdx.x == 0) atomicAdd(&w.slots[blockIdx.x % kMaxGrid], b);
@@ -231,13 +263,50 @@ __global__ void __launch_bounds__(kMtThreads) mt_fd_combine_kernel(const bb_mt_c
   const bb_mt_chunk c = tab[blockIdx.x];
   float* a = reinterpret_cast<float*>(c.a);
   const float* b = reinterpret_cast<const float*>(c.b);
-  for (int i = threadIdx.x; i < c.n; i += kMtThreads) a[i] = (a[i] - b[i]) * s;
+  const bool vec = (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+  const int n4 = vec ? c.n >> 2 : 0;
+  for (int i = threadIdx.x; i < n4; i += kMtThreads) {
+    float4 va = bb::ld4(a + 4 * i);
+    const float4 vb = bb::ld4(b + 4 * i);
+    va.x = (va.x - vb.x) * s; va.y = (va.y - vb.y) * s; va.z = (va.z - vb.z) * s; va.w = (va.w - vb.w) * s;
+    bb::st4(a + 4 * i, va);
+  }
+  for (int i = 4 * n4 + threadIdx.x; i < c.n; i += kMtThreads) a[i] = (a[i] - b[i]) * s;
+}
+
+// SAMA's Adam preconditioner (reference hypergradient/utils.py:37-63), one chunk row per <= BB_MT_CHUNK floats:
+//   m_old = (m - (1-b1) g)/b1 (0 if b1 == 0);  s_old = (s - (1-b2) g^2)/b2
+//   out = v * lr * ((1-b1) b2 s_old - b1 (1-b2) g m_old) / (sqrt(s) + eps)^3        missing state tensors read as 0
+__global__ void __launch_bounds__(kMtThreads) mt_adam_precondition_kernel(const bb_mt_adam_chunk* __restrict__ tab) {
+  const bb_mt_adam_chunk c = tab[blockIdx.x];
+  const float* v = reinterpret_cast<const float*>(c.v);
+  const float* g = reinterpret_cast<const float*>(c.g);
+  const float* m = reinterpret_cast<const float*>(c.m);
+  const float* q = reinterpret_cast<const float*>(c.s);
+  float* out = reinterpret_cast<float*>(c.out);
+  const float b1 = c.beta1, b2 = c.beta2;
+  for (int i = threadIdx.x; i < c.n; i += kMtThreads) {
+    const float gi = g ? g[i] : 0.f, mi = m ? m[i] : 0.f, si = q ? q[i] : 0.f;
+    const float m_old = b1 != 0.f ? (mi - (1.f - b1) * gi) / b1 : 0.f;
+    const float s_old = (si - (1.f - b2) * gi * gi) / b2;
+    float scale = (1.f - b1) * b2 * s_old - b1 * (1.f - b2) * gi * m_old;
+    const float d = sqrtf(si) + c.eps;
+    scale /= d * d * d;
+    out[i] = v[i] * scale * c.lr;
+  }
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
 extern "C" {
+
+int bb_mt_adam_precondition(const bb_mt_adam_chunk* table_dev, int nchunks, void* stream) {
+  if (nchunks <= 0) return BB_OK;
+  mt_adam_precondition_kernel<<<nchunks, kMtThreads, 0, (cudaStream_t)stream>>>(table_dev);
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
 
 int bb_kloop_ws_bytes(void) { return 512 + 3 * kMaxGrid * (int)sizeof(double); }
 
@@ -259,11 +328,11 @@ int bb_scale(float* out, const float* in, float c, int64_t n, void* stream) {
   return BB_OK;
 }
 
-int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, int first, int64_t n, void* ws,
-               void* stream) {
+int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, float shift, int first, int64_t n,
+               void* ws, void* stream) {
   if ((n & 3) != 0) return BB_ERR_ARG;
   const int64_t n4 = n >> 2;
-  cg_dots_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(r, hp, p, cg_alpha, first, n4, ws);
+  cg_dots_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(r, hp, p, cg_alpha, shift, first, n4, ws);
   BB_LAUNCH_CHECK();
   return BB_OK;
 }
@@ -276,10 +345,11 @@ int bb_cg_init(const float* r, int64_t n, void* ws, void* stream) {
   return BB_OK;
 }
 
-int bb_cg_update_xr(float* x, float* r, const float* p, const float* hp, int64_t n, void* ws, void* stream) {
+int bb_cg_update_xr(float* x, float* r, const float* p, const float* hp, float shift, int64_t n, void* ws,
+                    void* stream) {
   if ((n & 3) != 0) return BB_ERR_ARG;
   const int64_t n4 = n >> 2;
-  cg_update_xr_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(x, r, p, hp, n4, ws);
+  cg_update_xr_kernel<<<grid_for(n4), kThreads, 0, (cudaStream_t)stream>>>(x, r, p, hp, shift, n4, ws);
   BB_LAUNCH_CHECK();
   return BB_OK;
 }

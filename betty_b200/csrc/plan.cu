@@ -33,6 +33,8 @@ struct bb_plan {
       return n == o.n && alpha == o.alpha;
     }
   };
+  int shift_node = -1;          // BB_OP_DIAGSHIFT covering every parameter: applied by K1-K3 inside the K-loops
+  float shift = 0.f;
   cudaGraphExec_t exec[3] = {nullptr, nullptr, nullptr};
   LoopKey key[3];
   int graph_captures = 0;
@@ -112,8 +114,9 @@ int dispatch(const bb_node& nd, int pass, cudaStream_t s) {
   }
 }
 
-int run_pass(bb_plan* p, int pass, cudaStream_t s) {
+int run_pass(bb_plan* p, int pass, cudaStream_t s, bool in_loop = false) {
   if (pass < 0 || pass > 2) return BB_ERR_ARG;
+  const int skip = in_loop ? p->shift_node : -1;
   bb_scratch = BbScratch{reinterpret_cast<uint8_t*>(p->scratch), (size_t)p->scratch_bytes, 0};
   bb_scratch_reset();
   const int tally0 = bb_launch_tally;
@@ -131,13 +134,14 @@ int run_pass(bb_plan* p, int pass, cudaStream_t s) {
     }
   } else {
     for (int i = n - 1; i >= 0; --i) {
+      if (i == skip) continue;
       t_node = i;
       const int rc = dispatch(p->nodes[i], pass, s);
       if (rc) return rc;
     }
   }
   t_node = -1;
-  p->launches[pass] = bb_launch_tally - tally0;
+  if (!in_loop) p->launches[pass] = bb_launch_tally - tally0;
   return BB_OK;
 }
 
@@ -260,6 +264,22 @@ int bb_plan_hvp(bb_plan* plan, void* stream) {
   return run_pass(plan, BB_PASS_TAN_BWD, (cudaStream_t)stream);
 }
 
+// H.d without the uniform c*I term (the K-loop kernels apply it as their `shift`)
+static int hvp_in_loop(bb_plan* plan, cudaStream_t s) {
+  int rc = run_pass(plan, BB_PASS_TAN_FWD, s, true);
+  if (rc) return rc;
+  return run_pass(plan, BB_PASS_TAN_BWD, s, true);
+}
+
+int bb_plan_set_uniform_shift(bb_plan* plan, int node, double coef) {
+  if (!plan || node >= (int)plan->nodes.size()) return BB_ERR_ARG;
+  if (node >= 0 && plan->nodes[node].op != BB_OP_DIAGSHIFT) return BB_ERR_ARG;
+  plan->shift_node = node;
+  plan->shift = node >= 0 ? (float)coef : 0.f;
+  plan->drop_graphs();
+  return BB_OK;
+}
+
 int bb_plan_hvp_replay(bb_plan* plan, void* stream) {
   // H.d as one graph launch (epilogue pass along x, benchmarks of the bare product)
   if (!plan) return BB_ERR_ARG;
@@ -306,9 +326,9 @@ int bb_plan_neumann_loop(bb_plan* plan, int iterations, float alpha, float* v, f
   bb_plan::LoopKey key;
   key.ptr[0] = v; key.ptr[1] = p; key.ptr[2] = hv; key.n = n; key.alpha = alpha;
   return loop_with_graph(plan, 0, key, iterations, use_graph, s, [&]() -> int {
-    int rc = bb_plan_hvp(plan, s);                            // hv <- H v        (neumann.py:62)
+    int rc = hvp_in_loop(plan, s);                                    // hv <- H v        (neumann.py:62)
     if (rc) return rc;
-    return bb_neumann_update(v, p, hv, alpha, 0.f, n, s);     // v, p updates     (neumann.py:63-64)
+    return bb_neumann_update(v, p, hv, alpha, plan->shift, n, s);     // v, p updates     (neumann.py:63-64)
   });
 }
 
@@ -321,11 +341,11 @@ int bb_plan_cg_loop(bb_plan* plan, int iterations, float cg_alpha, float* x, flo
   bb_plan::LoopKey key;
   key.ptr[0] = x; key.ptr[1] = r; key.ptr[2] = p; key.ptr[3] = hp; key.ptr[4] = ws; key.n = n; key.alpha = cg_alpha;
   return loop_with_graph(plan, 1, key, iterations, use_graph, s, [&]() -> int {
-    int rc2 = bb_plan_hvp(plan, s);                           // hp <- H p        (cg.py:39-41)
+    int rc2 = hvp_in_loop(plan, s);                                   // hp <- H p        (cg.py:39-41)
     if (rc2) return rc2;
-    rc2 = bb_cg_dots(r, hp, p, cg_alpha, 0, n, ws, s);        // alpha            (cg.py:42-47)
+    rc2 = bb_cg_dots(r, hp, p, cg_alpha, plan->shift, 0, n, ws, s);   // alpha            (cg.py:42-47)
     if (rc2) return rc2;
-    rc2 = bb_cg_update_xr(x, r, p, hp, n, ws, s);             // x, r, beta       (cg.py:49-52)
+    rc2 = bb_cg_update_xr(x, r, p, hp, plan->shift, n, ws, s);        // x, r, beta       (cg.py:49-52)
     if (rc2) return rc2;
     return bb_cg_update_p(p, r, n, ws, s);                    // p                (cg.py:53)
   });

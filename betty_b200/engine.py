@@ -244,7 +244,7 @@ class HypergradientCall:
             plan_cache.hits += 1
             self.tape = entry.plan.tape
         else:
-            plan_cache.misses += 1
+            plan_cache.misses += key is not None
             lay = ArenaLayout.like(params)
             d, hd, acc, out = (lay.new(self.dev) for _ in range(4))
             with _nvtx("betty_b200:prologue:plan"):
@@ -309,8 +309,8 @@ class HypergradientCall:
             else:
                 for k in range(K):
                     hvp()
-                    N.call("bb_cg_dots", r.data_ptr(), hd.data_ptr(), d.data_ptr(), alpha, int(k == 0), n, ws.ptr, s)
-                    N.call("bb_cg_update_xr", acc.data_ptr(), r.data_ptr(), d.data_ptr(), hd.data_ptr(), n, ws.ptr, s)
+                    N.call("bb_cg_dots", r.data_ptr(), hd.data_ptr(), d.data_ptr(), alpha, 0.0, int(k == 0), n, ws.ptr, s)
+                    N.call("bb_cg_update_xr", acc.data_ptr(), r.data_ptr(), d.data_ptr(), hd.data_ptr(), 0.0, n, ws.ptr, s)
                     N.call("bb_cg_update_p", d.data_ptr(), r.data_ptr(), n, ws.ptr, s)
             if e1 is not None:
                 e1.record()

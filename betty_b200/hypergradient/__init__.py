@@ -1,4 +1,4 @@
-"""Drop-in replacements for ``betty.hypergradient.{neumann, cg, darts}`` (+ the ``finite_diff`` alias
+"""Drop-in replacements for ``betty.hypergradient.{neumann, cg, darts, sama}`` (+ the ``finite_diff`` alias
 named by BASELINE.json; the reference calls the same algorithm ``darts``).
 
 ``install()`` rebinds the reference's plugin table in place, so ``Engine`` / ``ImplicitProblem`` and
@@ -7,10 +7,11 @@ the ``Config(type=...)`` selector are used unchanged (reference betty/hypergradi
 from .cg import cg
 from .darts import darts
 from .neumann import neumann
+from .sama import sama
 
 finite_diff = darts
 
-jvp_fn_mapping = {"darts": darts, "finite_diff": darts, "neumann": neumann, "cg": cg}
+jvp_fn_mapping = {"darts": darts, "finite_diff": darts, "sama": sama, "neumann": neumann, "cg": cg}
 
 
 def get_grads(loss, path, retain_graph, do_sync):

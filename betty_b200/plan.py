@@ -198,6 +198,20 @@ class HvpPlan:
             self.tma_persistent = torch.empty(persist, dtype=torch.uint8, device=self.dev)
             N.call("bb_plan_set_persistent", self.handle, self.tma_persistent.data_ptr(), persist)
 
+        # a folded c*I term over EVERY parameter is applied by the K-loop vector kernels (their `shift`) instead of a
+        # 12 B/parameter sweep per iteration; the bare H.d product (tests, epilogue) still runs the node
+        self.uniform_shift = None
+        all_params = {id(p) for p in g.params}
+        for i, n in enumerate(g.nodes):
+            if n.op == "diagshift" and not any(t.boundary for t in n.attrs["targets"]):
+                tg = [id(t) for t in n.attrs["targets"]]
+                if len(tg) == len(set(tg)) == len(all_params) and set(tg) == all_params and all(
+                        s_ is t_ for s_, t_ in zip(n.ins, n.attrs["targets"])):
+                    if not self.dry_run:
+                        N.call("bb_plan_set_uniform_shift", self.handle, i, float(n.attrs["coef"]))
+                    self.uniform_shift = (i, float(n.attrs["coef"]))
+                    break
+
         zb = [self.A["z"]] if self.zero_bytes else []
         zt = ([self.AT["z"]] if self.zero_bytes else []) + [self.hv_arena]
         for pas, ts in ((PASS_BB, zb), (PASS_TF, []), (PASS_TB, zt)):
@@ -532,6 +546,8 @@ class HvpPlan:
 
     def _count_iter(self, iters: int, extra_per_iter: int):
         per = N.lib().bb_plan_launch_count(self.handle, PASS_TF) + N.lib().bb_plan_launch_count(self.handle, PASS_TB)
+        if extra_per_iter and self.uniform_shift is not None:
+            per -= 1            # the K-loops skip the folded c*I node
         self.launches_per_iter = per + extra_per_iter
         N.launch_counter += iters * self.launches_per_iter
 

@@ -33,6 +33,8 @@ class ShimConfig:
     precision: str = "fp32"
     darts_alpha: float = 0.01
     darts_multitask: bool = False
+    sama_adam_alpha: float = 1.0
+    sama_multitask: bool = False
     neumann_iterations: int = 1
     neumann_alpha: float = 1.0
     cg_iterations: int = 1
@@ -65,6 +67,7 @@ class ShimProblem:
         self.paths: List[Any] = []
         self._strategy = "default"
         self.peers: dict = {}
+        self.optimizer = None           # `sama` reads the lower optimizer's state (reference utils.py:37-63)
 
     # -- reference problem.py:320-332 -------------------------------------------------------
     def training_step(self, batch):
@@ -96,6 +99,20 @@ class ShimProblem:
             if g is None:
                 continue
             p.grad = g if p.grad is None else p.grad + g
+
+    # -- reference problem.py:697-723 (used by the SAMA preconditioner) ----------------------
+    def get_opt_param_group_for_param(self, param):
+        for group in self.optimizer.param_groups:
+            for p in group["params"]:
+                if param is p:
+                    return group
+
+    def get_opt_state_for_param(self, param):
+        return self.optimizer.state[param]
+
+    def synchronize_params(self, params, all_reduce=False):
+        # reference problem.py:599-610: a no-op on one process
+        return None
 
     def zero_grad(self):
         for p in self.trainable_parameters():

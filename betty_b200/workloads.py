@@ -235,7 +235,12 @@ def _pair(name, lower_mod, lower_step, upper_mod, cfg, batch, device, seed_v=1, 
     lower.cur_batch = tuple(b.to(device) if torch.is_tensor(b) else b for b in batch)
     g = torch.Generator().manual_seed(seed_v)
     vec = tuple(torch.randn(p.shape, generator=g).to(device) for p in lower_mod.parameters())
-    return Workload(name, lower, upper, vec, describe or {})
+    wl = Workload(name, lower, upper, vec, describe or {})
+    if cfg.type == "sama":
+        # sama preconditions the direction with the lower optimizer's Adam state: make it part of the seeded workload
+        with torch.random.fork_rng(devices=[]):
+            attach_adam_state(wl)
+    return wl
 
 
 def logistic_hpo(device="cpu", method="neumann", n=500, dim=20, K=5, alpha=1.0, seed=0):
@@ -410,6 +415,167 @@ def darts_search(device="cpu", batch=16, c=8, cells=2, darts_alpha=0.01, seed=0)
                  describe=dict(batch=batch, c=c, cells=cells, method="darts"))
 
 
+
+# -- config 4 at full size: the DARTS search network Network(16, 10, 8) + Architecture(4) -------------------------
+# Restated from reference ``examples/neural_architecture_search/model_search.py:129-317`` and ``operations.py:5-196``
+# (1,930,618 parameters in 1,399 tensors; tests/test_workloads_cpu.py pins the restatement to the reference's own
+# classes: same parameter list, same logits).  Only the finite-difference K4 kernels are ours on this config; the
+# two lower forward/backward passes stay on PyTorch.
+DARTS_PRIMITIVES = ("none", "max_pool_3x3", "avg_pool_3x3", "skip_connect", "sep_conv_3x3", "sep_conv_5x5",
+                    "dil_conv_3x3", "dil_conv_5x5")
+
+
+def _bn(c, affine=False):
+    return nn.BatchNorm2d(c, affine=affine)
+
+
+def _depthwise_then_pointwise(cin, cout, k, stride, pad, dilation=1):
+    return [nn.Conv2d(cin, cin, k, stride=stride, padding=pad, dilation=dilation, groups=cin, bias=False),
+            nn.Conv2d(cin, cout, 1, padding=0, bias=False), _bn(cout)]
+
+
+class _ZeroOp(nn.Module):
+    def __init__(self, stride):
+        super().__init__()
+        self.stride = stride
+
+    def forward(self, x):
+        return (x if self.stride == 1 else x[:, :, ::self.stride, ::self.stride]).mul(0.0)
+
+
+class _HalveResolution(nn.Module):
+    """Two stride-2 1x1 convolutions on the even / odd pixel grids, concatenated (operations.py:173-196)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.relu = nn.ReLU()
+        self.even = nn.Conv2d(cin, cout // 2, 1, stride=2, bias=False)
+        self.odd = nn.Conv2d(cin, cout // 2, 1, stride=2, bias=False)
+        self.bn = _bn(cout)
+
+    def forward(self, x):
+        x = self.relu(x)
+        return self.bn(torch.cat([self.even(x), self.odd(x[:, :, 1:, 1:])], dim=1))
+
+
+def _darts_op(name, c, stride):
+    if name == "none":
+        return _ZeroOp(stride)
+    if name == "max_pool_3x3":
+        return nn.Sequential(nn.MaxPool2d(3, stride=stride, padding=1), _bn(c))
+    if name == "avg_pool_3x3":
+        return nn.Sequential(nn.AvgPool2d(3, stride=stride, padding=1, count_include_pad=False), _bn(c))
+    if name == "skip_connect":
+        return nn.Identity() if stride == 1 else _HalveResolution(c, c)
+    kind, _, size = name.split("_")
+    k = int(size[0])
+    if kind == "sep":
+        pad = k // 2
+        return nn.Sequential(nn.ReLU(), *_depthwise_then_pointwise(c, c, k, stride, pad),
+                             nn.ReLU(), *_depthwise_then_pointwise(c, c, k, 1, pad))
+    pad = k - 1                                       # dilation 2: "same" padding is (k-1)
+    return nn.Sequential(nn.ReLU(), *_depthwise_then_pointwise(c, c, k, stride, pad, dilation=2))
+
+
+class _MixedEdge(nn.Module):
+    def __init__(self, c, stride):
+        super().__init__()
+        self.ops = nn.ModuleList([_darts_op(name, c, stride) for name in DARTS_PRIMITIVES])
+
+    def forward(self, x, w):
+        return sum(wi * op(x) for wi, op in zip(w, self.ops))
+
+
+class _SearchCell(nn.Module):
+    def __init__(self, steps, multiplier, cpp, cp, c, reduction, reduction_prev):
+        super().__init__()
+        self.reduction, self.steps, self.multiplier = reduction, steps, multiplier
+        relu_conv_bn = lambda cin: nn.Sequential(nn.ReLU(), nn.Conv2d(cin, c, 1, bias=False), _bn(c))
+        self.pre0 = _HalveResolution(cpp, c) if reduction_prev else relu_conv_bn(cpp)
+        self.pre1 = relu_conv_bn(cp)
+        self.edges = nn.ModuleList([_MixedEdge(c, 2 if reduction and j < 2 else 1)
+                                    for i in range(steps) for j in range(2 + i)])
+
+    def forward(self, s0, s1, weights):
+        states = [self.pre0(s0), self.pre1(s1)]
+        e = 0
+        for _ in range(self.steps):
+            states.append(sum(self.edges[e + j](h, weights[e + j]) for j, h in enumerate(states)))
+            e += len(states) - 1
+        return torch.cat(states[-self.multiplier:], dim=1)
+
+
+class DartsSearchNetwork(nn.Module):
+    """Network(c, classes, layers): stem, `layers` search cells (reduction cells at 1/3 and 2/3), pooled classifier."""
+
+    def __init__(self, c=16, classes=10, layers=8, steps=4, multiplier=4, stem_multiplier=3):
+        super().__init__()
+        cur = stem_multiplier * c
+        self.stem = nn.Sequential(nn.Conv2d(3, cur, 3, padding=1, bias=False), nn.BatchNorm2d(cur))
+        cpp, cp, cur = cur, cur, c
+        self.cells = nn.ModuleList()
+        prev_reduced = False
+        for i in range(layers):
+            reduced = i in (layers // 3, 2 * layers // 3)
+            if reduced:
+                cur *= 2
+            self.cells.append(_SearchCell(steps, multiplier, cpp, cp, cur, reduced, prev_reduced))
+            prev_reduced = reduced
+            cpp, cp = cp, multiplier * cur
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.classifier = nn.Linear(cp, classes)
+
+    def forward(self, x, alphas):
+        alpha_reduce, alpha_normal = alphas
+        s0 = s1 = self.stem(x)
+        for cell in self.cells:
+            w = F.softmax(alpha_reduce if cell.reduction else alpha_normal, dim=-1)
+            s0, s1 = s1, cell(s0, s1, w)
+        return self.classifier(self.pool(s1).flatten(1))
+
+
+class DartsArchitecture(nn.Module):
+    """Architecture(steps): alpha_normal / alpha_reduce, one row of 8 op logits per edge (model_search.py:300-317)."""
+
+    def __init__(self, steps=4):
+        super().__init__()
+        k = sum(2 + i for i in range(steps))
+        self.alpha_normal = nn.Parameter(1e-3 * torch.randn(k, len(DARTS_PRIMITIVES)))
+        self.alpha_reduce = nn.Parameter(1e-3 * torch.randn(k, len(DARTS_PRIMITIVES)))
+
+    def forward(self):
+        return self.alpha_reduce, self.alpha_normal
+
+
+def darts_search_full(device="cpu", batch=64, c=16, layers=8, darts_alpha=0.01, method="darts", seed=0):
+    """Config 4 as SURVEY.md 8(d) states it: Network(16,10,8) + Architecture(4), x 64x3x32x32 (train_search.py:24)."""
+    torch.manual_seed(seed)
+    x = torch.randn(batch, 3, 32, 32)
+    y = torch.randint(0, 10, (batch,))
+    lower = DartsSearchNetwork(c, 10, layers)
+    upper = DartsArchitecture(4)
+    cfg = ShimConfig(type=method, darts_alpha=darts_alpha)
+    return _pair("neural_architecture_search", lower, _darts_lower_step, upper, cfg, (x, y), device,
+                 describe=dict(batch=batch, c=c, layers=layers, method=method))
+
+
+def attach_adam_state(wl: Workload, steps: int = 3, lr: float = 1e-2) -> Workload:
+    """Give the lower problem an Adam optimizer whose state (exp_avg, exp_avg_sq and the ``last_grad`` the reference's
+    ImplicitProblem records, implicit_problem.py:50-66) comes from ``steps`` real Adam steps on the lower loss --
+    what ``sama`` preconditions the direction with (reference hypergradient/utils.py:37-63)."""
+    opt = torch.optim.Adam(wl.lower.module.parameters(), lr=lr, betas=(0.9, 0.99), eps=1e-8)
+    for _ in range(steps):
+        opt.zero_grad()
+        wl.lower.training_step_exec(wl.lower.cur_batch).backward()
+        grads = [p.grad.detach().clone() for p in wl.lower.module.parameters()]
+        opt.step()
+        for p, g in zip(wl.lower.module.parameters(), grads):
+            opt.state[p]["last_grad"] = g
+    opt.zero_grad()
+    wl.lower.optimizer = opt
+    return wl
+
+
 FACTORIES = {
     "logistic_regression_hpo": logistic_hpo,
     "mlp_reweight": mlp_reweight,
@@ -417,5 +583,6 @@ FACTORIES = {
     "learning_to_reweight_resnet": resnet_reweight,
     "implicit_maml": fourconv_imaml,
     "neural_architecture_search": darts_search,
+    "neural_architecture_search_full": darts_search_full,
     "bert_data_reweighting": roberta_reweight,
 }

@@ -42,10 +42,13 @@ int bb_scale(float* out, const float* in, float c, int64_t n, void* stream);
 /* ---- K2/K3: conjugate-gradient inner products and updates.  Replaces reference cg.py:42-53
  *      (three to_vec concatenations, three dots, three list-comprehension AXPYs per iteration).
  *      alpha and beta stay in `ws`; `first` != 0 also computes rr = r.r.                        */
-int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, int first, int64_t n, void* ws,
-               void* stream);
+/* `shift`: H p = hp + shift * p -- a declared c*I curvature term (folded L2 / proximal regulariser) applied inside
+ * the vector passes instead of a separate sweep over the arenas (same argument as bb_neumann_update's) */
+int bb_cg_dots(const float* r, const float* hp, const float* p, float cg_alpha, float shift, int first, int64_t n,
+               void* ws, void* stream);
 int bb_cg_init(const float* r, int64_t n, void* ws, void* stream); /* ws.rr = r.r */
-int bb_cg_update_xr(float* x, float* r, const float* p, const float* hp, int64_t n, void* ws, void* stream);
+int bb_cg_update_xr(float* x, float* r, const float* p, const float* hp, float shift, int64_t n, void* ws,
+                    void* stream);
 int bb_cg_update_p(float* p, const float* r, int64_t n, const void* ws, void* stream);
 
 /* ---- K4 + packing: multi-tensor kernels over a chunk table.  Replaces reference darts.py:30-38,
@@ -65,6 +68,19 @@ int bb_mt_sumsq(const bb_mt_chunk* table_dev, int nchunks, void* ws, void* strea
 int bb_fd_eps(void* ws, double darts_alpha, void* stream);                          /* -> ws.eps, inv_2eps */
 /* a <- (a - b) * ws.inv_2eps */
 int bb_mt_fd_combine(const bb_mt_chunk* table_dev, int nchunks, const void* ws, void* stream);
+/* K4 epilogue for `sama` (reference betty/hypergradient/sama.py:24, utils.py:37-63): the Adam preconditioner of the
+ * direction, out = v * lr * ((1-b1) b2 s_old - b1 (1-b2) g m_old) / (sqrt(s) + eps)^3 per element, multi-tensor */
+typedef struct bb_mt_adam_chunk {
+  const void* v;   /* direction                       */
+  const void* g;   /* optimizer state "last_grad"  (0 => zeros) */
+  const void* m;   /* optimizer state "exp_avg"    (0 => zeros) */
+  const void* s;   /* optimizer state "exp_avg_sq" (0 => zeros) */
+  void* out;
+  int32_t n;
+  float beta1, beta2, eps, lr;
+  int32_t pad;
+} bb_mt_adam_chunk;
+int bb_mt_adam_precondition(const bb_mt_adam_chunk* table_dev, int nchunks, void* stream);
 
 /* ---- K5-K9: second-order tape ("HVP plan").  Replaces reference neumann.py:62 / cg.py:39-41
  *      (torch.autograd.grad(in_grad, params, grad_outputs=v, retain_graph=True): reverse-over-reverse
@@ -91,6 +107,9 @@ int bb_plan_launch_count(const bb_plan* plan, int pass);
 int bb_plan_profile(bb_plan* plan, int pass, float* ms_per_node, void* stream);
 /* one H.d product: zero regions, tangent forward, tangent backward */
 int bb_plan_hvp(bb_plan* plan, void* stream);
+/* node `node` is a BB_OP_DIAGSHIFT that adds coef * d to EVERY parameter slice of H.d: the K-loops skip it and hand
+ * `coef` to K1 / K2 / K3 as their `shift` (one pass over the arenas less per iteration); bb_plan_hvp still runs it */
+int bb_plan_set_uniform_shift(bb_plan* plan, int node, double coef);
 /* the same product as ONE graph launch (captured at the first call, kept for the plan's lifetime) */
 int bb_plan_hvp_replay(bb_plan* plan, void* stream);
 /* a cached plan is about to serve new base values written in place behind the same pointers: rebuild the packs of

@@ -35,6 +35,9 @@ CASES = {
     "roberta_tiny_cg": ("bert_data_reweighting", dict(method="cg", batch=4, seq=10, K=3, tiny=True)),
     "roberta_tiny_neumann": ("bert_data_reweighting", dict(method="neumann", batch=4, seq=10, K=4, alpha=0.05, tiny=True)),
     "darts_lite": ("neural_architecture_search", dict(batch=4, c=4, cells=1)),
+    # sama (reference hypergradient/sama.py): the factories attach the lower Adam state (workloads.attach_adam_state, 3 real steps)
+    "logistic_sama": ("logistic_regression_hpo", dict(method="sama")),
+    "mlp_sama": ("mlp_reweight", dict(method="sama")),
 }
 
 

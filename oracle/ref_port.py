@@ -99,13 +99,12 @@ def cg(vector, curr, prev, sync):
     return mixed_product(in_grad, prev, x, sync)
 
 
-def darts(vector, curr, prev, sync):
-    """Central finite difference of grad_lambda L_in along v, eps = darts_alpha/||v||
-    (reference ``betty/hypergradient/darts.py:8-69``, non-FSDP branch)."""
-    cfg = curr.config
+def _finite_difference(vector, curr, prev, sync, radius, multitask):
+    """Shared body of darts.py:27-67 and sama.py:26-59 (non-FSDP branch): central difference of grad_lambda L_in
+    along ``vector``, eps = radius / ||vector||."""
     lam = prev.trainable_parameters()
     w = curr.meta_trainable_parameters()
-    eps = cfg.darts_alpha / (_flat(vector).norm() + 1e-15).item()
+    eps = radius / (_flat(vector).norm() + 1e-15).item()
 
     def grad_lambda(loss):
         g = torch.autograd.grad(loss, lam, allow_unused=True)
@@ -126,7 +125,7 @@ def darts(vector, curr, prev, sync):
         g_minus = None
     else:
         g_minus = grad_lambda(loss_minus)
-    if not cfg.darts_multitask:
+    if not multitask:
         with torch.no_grad():
             for p, vi in zip(w, vector):
                 p.add_(vi, alpha=eps)
@@ -135,7 +134,44 @@ def darts(vector, curr, prev, sync):
     return [(gm - gp) / (2 * eps) for gm, gp in zip(g_minus, g_plus)]
 
 
-METHODS = {"neumann": neumann, "cg": cg, "darts": darts, "finite_diff": darts}
+def darts(vector, curr, prev, sync):
+    """Central finite difference of grad_lambda L_in along v, eps = darts_alpha/||v||
+    (reference ``betty/hypergradient/darts.py:8-69``, non-FSDP branch)."""
+    cfg = curr.config
+    return _finite_difference(vector, curr, prev, sync, cfg.darts_alpha, cfg.darts_multitask)
+
+
+def precondition(vector, problem):
+    """reference betty/hypergradient/utils.py:24-97: identity for SGD; for Adam the derivative of the update w.r.t.
+    the last gradient, from the state before the last step."""
+    name = type(problem.optimizer).__name__.lower()
+    if "adam" not in name:
+        if "rmsprop" in name:
+            raise NotImplementedError("SAMA preconditioning for RMSProp is not implemented!")
+        return list(vector)
+    out = []
+    for v, p in zip(vector, problem.meta_trainable_parameters()):
+        group = problem.get_opt_param_group_for_param(p)
+        state = problem.get_opt_state_for_param(p)
+        b1, b2 = group["betas"]
+        zeros = torch.zeros_like(v)
+        g, m, s = state.get("last_grad", zeros), state.get("exp_avg", zeros), state.get("exp_avg_sq", zeros)
+        m_old = (m - (1 - b1) * g) / b1 if b1 != 0 else 0                  # utils.py:51-53
+        s_old = (s - (1 - b2) * g * g) / b2                                # utils.py:54
+        scale = ((1 - b1) * b2 * s_old - b1 * (1 - b2) * g * m_old) / (torch.sqrt(s) + group["eps"]) ** 3
+        out.append(v * scale * group["lr"])
+    return out
+
+
+def sama(vector, curr, prev, sync):
+    """reference betty/hypergradient/sama.py:7-61: the finite difference of `darts` along the preconditioned
+    direction, radius ``sama_adam_alpha``."""
+    cfg = curr.config
+    v = precondition(vector, curr)                                         # sama.py:24
+    return _finite_difference(v, curr, prev, sync, cfg.sama_adam_alpha, cfg.sama_multitask)
+
+
+METHODS = {"neumann": neumann, "cg": cg, "darts": darts, "finite_diff": darts, "sama": sama}
 
 
 def k_loop_only(method: str, vector, curr):

@@ -45,8 +45,8 @@ def test_cg_iteration_matches_reference_arithmetic(n, cg_alpha):
     beta = torch.dot(r_new, r_new) / rr
     p_new = r_new + beta * p
     s = stream_ptr()
-    N.call("bb_cg_dots", r.data_ptr(), hp.data_ptr(), p.data_ptr(), cg_alpha, 1, n, ws.ptr, s)
-    N.call("bb_cg_update_xr", x.data_ptr(), r.data_ptr(), p.data_ptr(), hp.data_ptr(), n, ws.ptr, s)
+    N.call("bb_cg_dots", r.data_ptr(), hp.data_ptr(), p.data_ptr(), cg_alpha, 0.0, 1, n, ws.ptr, s)
+    N.call("bb_cg_update_xr", x.data_ptr(), r.data_ptr(), p.data_ptr(), hp.data_ptr(), 0.0, n, ws.ptr, s)
     N.call("bb_cg_update_p", p.data_ptr(), r.data_ptr(), n, ws.ptr, s)
     sc = ws.scalars.cpu()
     assert abs(float(sc[3]) - float(alpha)) <= 2e-5 * abs(float(alpha))
@@ -57,8 +57,31 @@ def test_cg_iteration_matches_reference_arithmetic(n, cg_alpha):
     # determinism: same inputs -> bit-identical scalars
     r2, p2, hp2, x2 = _rand(n, 1), _rand(n, 2), _rand(n, 3) + 2 * _rand(n, 2), _rand(n, 4)
     ws2 = Workspace(torch.device(DEV))
-    N.call("bb_cg_dots", r2.data_ptr(), hp2.data_ptr(), p2.data_ptr(), cg_alpha, 1, n, ws2.ptr, s)
+    N.call("bb_cg_dots", r2.data_ptr(), hp2.data_ptr(), p2.data_ptr(), cg_alpha, 0.0, 1, n, ws2.ptr, s)
     assert float(ws2.scalars[3]) == float(sc[3])
+
+
+@pytest.mark.parametrize("n", [62008, 5_000_000])
+def test_cg_iteration_with_a_folded_identity_term(n):
+    """`shift`: the kernels see hp WITHOUT a declared c*I curvature term and add shift*p themselves -- same iteration
+    as handing them hp + shift*p (reference cg.py:42-53 on the full Hessian-vector product)."""
+    shift, cg_alpha = 0.1, 1.0
+    r, p, hp, x = _rand(n, 1), _rand(n, 2), _rand(n, 3), _rand(n, 4)
+    hp = hp + 2 * p
+    full = hp + shift * p
+    outs = []
+    for h, sh in ((hp, shift), (full, 0.0)):
+        rr_, pp_, xx_ = r.clone(), p.clone(), x.clone()
+        ws = Workspace(torch.device(DEV))
+        s = stream_ptr()
+        N.call("bb_cg_dots", rr_.data_ptr(), h.data_ptr(), pp_.data_ptr(), cg_alpha, sh, 1, n, ws.ptr, s)
+        N.call("bb_cg_update_xr", xx_.data_ptr(), rr_.data_ptr(), pp_.data_ptr(), h.data_ptr(), sh, n, ws.ptr, s)
+        N.call("bb_cg_update_p", pp_.data_ptr(), rr_.data_ptr(), n, ws.ptr, s)
+        outs.append((xx_, rr_, pp_, ws.scalars.cpu().clone()))
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert float((a - b).norm() / b.norm()) < 2e-6
+    assert abs(float(outs[0][3][3]) - float(outs[1][3][3])) <= 2e-6 * abs(float(outs[1][3][3]))   # alpha
+    assert abs(float(outs[0][3][4]) - float(outs[1][3][4])) <= 2e-5 * abs(float(outs[1][3][4]))   # beta
 
 
 def test_pack_views_roundtrip_and_padding():

@@ -95,7 +95,7 @@ def test_plan_matches_interpreter_and_autograd(case):
         assert e < (2e-2 if reduced else max(1e-4, tol * 5)), f"{case}: H.v vs autograd double backward {e:.3e}"
         for g_, w_ in zip(got, want_a):   # per-tensor, so a wrong small tensor is not hidden by a big one
             if float(w_.norm()) > 0:
-                assert rel_l2([g_], [w_]) < (1e-1 if reduced else max(3e-4, tol * 20)), f"{case}: tensor {tuple(g_.shape)}"
+                assert rel_l2([g_], [w_]) < (1.5e-1 if reduced else max(3e-4, tol * 20)), f"{case}: tensor {tuple(g_.shape)}"
 
 
 def test_generic_conv_path_on_small_channels(monkeypatch):
