@@ -191,6 +191,40 @@ int launch_corr(const Geo& g, int npairs, const void* const* src_nhwc, int SH, i
   return bb_gemm_tma_launch(G, bn, (int64_t)g.N * G.tiles_per_img, s);
 }
 
+// weight-gradient launch over caller-provided bf16 NHWC operands (accumulates into `out`)
+int launch_wgrad(const Geo& g, int npairs, const void* const* xs, const void* const* gs, float* out, cudaStream_t s) {
+  alignas(64) WgradArgs A;
+  memset(&A, 0, sizeof(A));
+  const int taps = g.KH * g.KW;
+  const int Hb = g.HO < 64 / g.WO ? g.HO : 64 / g.WO;
+  int rc;
+  for (int p = 0; p < npairs; ++p) {
+    if ((rc = bb_tma_map_nhwc(&A.x[p], xs[p], g.N, g.H, g.W, 64, g.WO, Hb))) return rc;
+    if ((rc = bb_tma_map_nhwc(&A.g[p], gs[p], g.N, g.HO, g.WO, 64, g.WO, Hb))) return rc;
+  }
+  A.npairs = npairs; A.taps = taps; A.KW = g.KW; A.ph = g.ph; A.pw = g.pw;
+  A.Hb = Hb; A.rows = g.WO * Hb; A.RK = round_up(A.rows, 16);
+  A.tiles_per_img = (g.HO + Hb - 1) / Hb; A.ntiles = g.N * A.tiles_per_img;
+  A.C = g.C; A.O = g.O;
+  A.out = out;
+  const int slots = 2 * ((taps + 1) / 2) + 1;
+  const size_t stage = (size_t)slots * A.RK * 128;
+  int stages = (int)((220 * 1024 - 2048) / stage);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return BB_DECLINED;
+  A.stages = stages;
+  const size_t smem = stages * stage + 1024 + 256;
+  static BbOncePerDevice configured;
+  if (configured.need()) {
+    BB_CUDA_TRY(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+  }
+  const int grid = A.ntiles < BB_SM_COUNT ? A.ntiles : BB_SM_COUNT;
+  wgrad_tma_kernel<<<grid, WG_THREADS, smem, s>>>(A);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
 // ---- first-layer convolutions (few input channels, input is data: no tangent, no input gradient) -------------------
 // With C*KH*KW <= 64 the reduction fits one k-block, so the im2col matrix is materialised once per pass as bf16
 // [pixels][k] (TMA-addressable, any stride / dilation) and both products are plain GEMMs on gemm_tma_kernel:
@@ -373,8 +407,6 @@ int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
     if (rc) return rc;
   }
   if (need & 2) {
-    alignas(64) WgradArgs A;
-    memset(&A, 0, sizeof(A));
     void* xs = const_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, 0, s, &rc);
     if (rc) return rc;
     if (!xs) {
@@ -382,44 +414,35 @@ int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
       if (!xs) return BB_DECLINED;
       if ((rc = bb_pack_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, xs, 64, s))) return rc;
     }
-    const int Hb = g.HO < 64 / g.WO ? g.HO : 64 / g.WO;
-    int np = 0;
-    if ((rc = bb_tma_map_nhwc(&A.x[np], xs, g.N, g.H, g.W, 64, g.WO, Hb))) return rc;
-    if ((rc = bb_tma_map_nhwc(&A.g[np], gy, g.N, g.HO, g.WO, 64, g.WO, Hb))) return rc;
-    ++np;
+    const void* xs_[2] = {xs, nullptr};
+    const void* gs_[2] = {gy, nullptr};
+    int np = 1;
     if (actX) {
       void* txs = bb_scratch_alloc(in_bytes);
       if (!txs) return BB_DECLINED;
       if ((rc = bb_pack_nhwc(nd.t[0], BB_F32, g.N, g.C, g.H * g.W, txs, 64, s))) return rc;
-      if ((rc = bb_tma_map_nhwc(&A.x[np], txs, g.N, g.H, g.W, 64, g.WO, Hb))) return rc;
-      if ((rc = bb_tma_map_nhwc(&A.g[np], ay, g.N, g.HO, g.WO, 64, g.WO, Hb))) return rc;
-      ++np;
+      xs_[1] = txs; gs_[1] = ay;
+      np = 2;
     }
-    A.npairs = np; A.taps = taps; A.KW = g.KW; A.ph = g.ph; A.pw = g.pw;
-    A.Hb = Hb; A.rows = g.WO * Hb; A.RK = round_up(A.rows, 16);
-    A.tiles_per_img = (g.HO + Hb - 1) / Hb; A.ntiles = g.N * A.tiles_per_img;
-    A.C = g.C; A.O = g.O;
     float* out = reinterpret_cast<float*>(nd.at[1]);
-    A.out = out;
-    const int slots = 2 * ((taps + 1) / 2) + 1;
-    const size_t stage = (size_t)slots * A.RK * 128;
-    int stages = (int)((220 * 1024 - 2048) / stage);
-    if (stages > 4) stages = 4;
-    if (stages < 2) return BB_DECLINED;
-    A.stages = stages;
-    const size_t smem = stages * stage + 1024 + 256;
-    static BbOncePerDevice configured;
-    if (configured.need()) {
-      BB_CUDA_TRY(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    }
     if (!nd.beta[1]) {
       BB_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * g.O * g.C * taps, s));
       bb_launch_tally += 1;
     }
-    const int grid = A.ntiles < BB_SM_COUNT ? A.ntiles : BB_SM_COUNT;
-    wgrad_tma_kernel<<<grid, WG_THREADS, smem, s>>>(A);
-    bb_launch_tally += 1;
-    BB_LAUNCH_CHECK();
+    if ((rc = launch_wgrad(g, np, xs_, gs_, out, s))) return rc;
   }
   return BB_OK;
+}
+
+int bb_conv_tma_corr(const BbConvGeo& c, int npairs, const void* const* src_nhwc, int SH, int SW, const void* const* wmat,
+                     int ncols, int GH, int GW, int flip, float* out, int beta, const float* bias, cudaStream_t s) {
+  Geo g{c.N, c.C, c.H, c.W, c.O, c.KH, c.KW, c.HO, c.WO, c.ph, c.pw};
+  return launch_corr(g, npairs, src_nhwc, SH, SW, 64, wmat, ncols, GH, GW, flip, out, beta, bias, s);
+}
+
+int bb_conv_tma_wgrad(const BbConvGeo& c, int npairs, const void* const* x_nhwc, const void* const* gy_nhwc, float* out,
+                      cudaStream_t s) {
+  Geo g{c.N, c.C, c.H, c.W, c.O, c.KH, c.KW, c.HO, c.WO, c.ph, c.pw};
+  const int rc = launch_wgrad(g, npairs, x_nhwc, gy_nhwc, out, s);
+  return rc == BB_DECLINED ? BB_ERR_UNSUPPORTED : rc;
 }

@@ -19,6 +19,7 @@
 // So neither y-sized tangents nor y-sized adjoints exist: per iteration the block reads x and streams pooled-size
 // arrays (a quarter of y).  All arithmetic fp32 (x / y / q are read in the dtype the forward recorded).
 // Verified against the composition of the three member rules (oracle/plan_interp.py) and autograd's double backward.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "../../include/betty_b200.h"
@@ -107,6 +108,7 @@ struct CbArgs {
   float *at_W, *at_b, *at_gamma, *at_beta;
   // pooled output buffers of the plan (fp32, NCHW)
   float* t_q;
+  __nv_bfloat16* tq_nhwc;     // when the consumer is a fused block: t_q as bf16 NHWC (its TMA operand), t_q unused
   const float* a_q;
   const float* at_q;
   int nparts;     // CTAs that wrote partials
@@ -170,13 +172,21 @@ template <int C>
 __device__ __forceinline__ void load_x_tile(const CbArgs& A, int n, int hp0, float* xs) {
   const CbGeom& g = A.g;
   const int rows = g.xrows, pitch = g.xpitch, cols = g.WO + 2;
-  const int total = C * rows * cols;
-  for (int i = threadIdx.x; i < total; i += NT) {
-    const int c = i / (rows * cols), rem = i - c * rows * cols, r = rem / cols, col = rem - r * cols;
-    const int iy = 2 * hp0 - g.ph + r, ix = col - g.pw;
-    float v = 0.f;
-    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = bb::ldf(A.x, (((int64_t)n * C + c) * g.H + iy) * g.W + ix, A.dtx);
-    xs[(c * rows + r) * pitch + col] = v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // warp per (channel, row), lanes along the row: no divisions, coalesced reads
+  for (int cr = wid; cr < C * rows; cr += NT / 32) {
+    const int c = cr / rows, r = cr - c * rows;
+    const int iy = 2 * hp0 - g.ph + r;
+    float* d = xs + cr * pitch;
+    if (iy < 0 || iy >= g.H) {
+      for (int col = lane; col < cols; col += 32) d[col] = 0.f;
+      continue;
+    }
+    const int64_t rowbase = (((int64_t)n * C + c) * g.H + iy) * g.W - g.pw;
+    for (int col = lane; col < cols; col += 32) {
+      const int ix = col - g.pw;
+      d[col] = (ix >= 0 && ix < g.W) ? bb::ldf(A.x, rowbase + col, A.dtx) : 0.f;
+    }
   }
 }
 
@@ -320,11 +330,15 @@ __global__ void cb_gram_finish_kernel(const CbArgs A) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // tangent forward: t_q and dxhat at the arg-max pixels
+//   lane <-> channel (its 27 direction weights live in registers), warp <-> (channel group, window group); the four
+//   candidate pixels of a window are four distinct shared-memory words -> conflict-free broadcast reads.  Window
+//   indices advance without divisions; the pooled NHWC arrays (code, xhat) of the next window are fetched while the
+//   current one is being computed.
 // ---------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
   extern __shared__ float sm[];
-  const CbGeom& g = A.g;
+  const CbGeom g = A.g;
   constexpr int CKK = C * 9;
   const int plane = g.xrows * g.xpitch;
   float* xs = sm;
@@ -335,6 +349,9 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
   const int o = cg * 32 + lane;
   const bool och = o < g.O && wg < wgs;
   const double invP = 1.0 / ((double)g.N * g.HO * g.WO);
+  const unsigned char* __restrict__ sel = A.w.sel;
+  const float* __restrict__ xhp = A.w.xh;
+  float* __restrict__ dxhp = A.w.dxh;
   // per-lane channel constants
   float tw[CKK];
   float mean_t = 0.f, sdot = 0.f, rstd = 0.f, gam = 1.f, tgam = 0.f, tbeta = 0.f, tb = 0.f;
@@ -363,7 +380,9 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
 #pragma unroll
     for (int k = 0; k < CKK; ++k) tw[k] = 0.f;
   }
-  const int tileW = g.R * g.WP;
+  // t_q = mask * (c_y * t_y + c_x * xhat + c_0)
+  const float c_y = gam * rstd, c_x = tgam - gam * rstd * sdot, c_0 = tbeta + gam * rstd * (tb - mean_t);
+  const float e_0 = (tb - mean_t) * rstd, e_x = -sdot * rstd;          // dxhat = rstd*t_y + e_x*xhat + e_0
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int n = tile / g.tiles_per_img, tr = tile - n * g.tiles_per_img;
     const int hp0 = tr * g.R, rows = min(g.R, g.HP - hp0), nw = rows * g.WP;
@@ -371,26 +390,40 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
     load_x_tile<C>(A, n, hp0, xs);
     __syncthreads();
     if (och) {
+      const int64_t tbase = ((int64_t)n * g.HP + hp0) * g.WP * g.O + o;     // NHWC index of (window 0, channel o)
+      int wr = 0, wc = wg;
+      while (wc >= g.WP) { wc -= g.WP; ++wr; }
+      unsigned code = 0;
+      float xh = 0.f;
+      if (wg < nw) { code = sel[tbase + (int64_t)wg * g.O]; xh = xhp[tbase + (int64_t)wg * g.O]; }
       for (int wl = wg; wl < nw; wl += wgs) {
-        const int wr = wl / g.WP, wc = wl - wr * g.WP;
-        const int64_t pi = (((int64_t)n * g.HP + hp0 + wr) * g.WP + wc) * g.O + o;
-        const unsigned code = A.w.sel[pi];
-        const float xh = A.w.xh[pi];
-        const int base = (2 * wr + ((code >> 1) & 1)) * g.xpitch + 2 * wc + (code & 1);
-        const float ty = patch_dot<C>(xs, base, plane, g.xpitch, tw) + tb;
-        const float dxh = (ty - mean_t - xh * sdot) * rstd;
-        A.w.dxh[pi] = dxh;
-        outs[o * g.wpitch + wl] = (code & 4) ? fmaf(gam, dxh, fmaf(tgam, xh, tbeta)) : 0.f;
+        const unsigned code_c = code;
+        const float xh_c = xh;
+        const int nxt = wl + wgs;
+        if (nxt < nw) { code = sel[tbase + (int64_t)nxt * g.O]; xh = xhp[tbase + (int64_t)nxt * g.O]; }
+        const int base = (2 * wr + ((code_c >> 1) & 1)) * g.xpitch + 2 * wc + (code_c & 1);
+        const float ty = patch_dot<C>(xs, base, plane, g.xpitch, tw);
+        dxhp[tbase + (int64_t)wl * g.O] = fmaf(rstd, ty, fmaf(e_x, xh_c, e_0));
+        const float tq = (code_c & 4) ? fmaf(c_y, ty, fmaf(c_x, xh_c, c_0)) : 0.f;
+        if (A.tq_nhwc)
+          A.tq_nhwc[tbase + (int64_t)wl * g.O] = __float2bfloat16(tq);
+        else
+          outs[o * g.wpitch + wl] = tq;
+        wc += wgs;
+        while (wc >= g.WP) { wc -= g.WP; ++wr; }
       }
     }
-    __syncthreads();
-    // NCHW store: for each channel the tile's windows are `nw` consecutive floats
-    for (int i = threadIdx.x; i < g.O * nw; i += NT) {
-      const int oo = i / nw, wl = i - oo * nw;
-      A.t_q[(((int64_t)n * g.O + oo) * g.HP + hp0) * g.WP + wl] = outs[oo * g.wpitch + wl];
+    if (!A.tq_nhwc) {
+      __syncthreads();
+      // NCHW store: for each channel the tile's windows are `nw` consecutive floats; warp per channel, lanes along them
+      float* dst = A.t_q + (((int64_t)n * g.O) * g.HP + hp0) * g.WP;
+      for (int oo = wid; oo < g.O; oo += NT / 32) {
+        float* d = dst + (int64_t)oo * g.HP * g.WP;
+        const float* sp = outs + oo * g.wpitch;
+        for (int wl = lane; wl < nw; wl += 32) d[wl] = sp[wl];
+      }
     }
   }
-  (void)tileW;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -403,7 +436,7 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
 template <int C, bool BASE>
 __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
   extern __shared__ float sm[];
-  const CbGeom& g = A.g;
+  const CbGeom g = A.g;
   constexpr int CKK = C * 9;
   const int plane = g.xrows * g.xpitch;
   float* xs = sm;
@@ -413,6 +446,10 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
   const int cg = wid % cgs, wg = wid / cgs;
   const int o = cg * 32 + lane;
   const bool och = o < g.O && wg < wgs;
+  const unsigned char* __restrict__ sel = A.w.sel;
+  const float* __restrict__ xhp = A.w.xh;
+  const float* __restrict__ dxhp = A.w.dxh;
+  const float* __restrict__ aqm = A.w.aqm;
   float gw[CKK];
 #pragma unroll
   for (int k = 0; k < CKK; ++k) gw[k] = 0.f;
@@ -423,29 +460,44 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
     __syncthreads();
     load_x_tile<C>(A, n, hp0, xs);
     if (!BASE) {
-      for (int i = threadIdx.x; i < g.O * nw; i += NT) {
-        const int oo = i / nw, wl = i - oo * nw;
-        ins[oo * g.wpitch + wl] = A.at_q[(((int64_t)n * g.O + oo) * g.HP + hp0) * g.WP + wl];
+      const float* src = A.at_q + (((int64_t)n * g.O) * g.HP + hp0) * g.WP;
+      for (int oo = wid; oo < g.O; oo += NT / 32) {
+        const float* sp = src + (int64_t)oo * g.HP * g.WP;
+        float* d = ins + oo * g.wpitch;
+        for (int wl = lane; wl < nw; wl += 32) d[wl] = sp[wl];
       }
     }
     __syncthreads();
     if (och) {
+      const int64_t tbase = ((int64_t)n * g.HP + hp0) * g.WP * g.O + o;
+      int wr = 0, wc = wg;
+      while (wc >= g.WP) { wc -= g.WP; ++wr; }
+      unsigned code = 0;
+      float xh = 0.f, aq = 0.f, dx = 0.f;
+      if (wg < nw) {
+        const int64_t i0 = tbase + (int64_t)wg * g.O;
+        code = sel[i0]; xh = xhp[i0]; aq = aqm[i0];
+        if (!BASE) dx = dxhp[i0];
+      }
       for (int wl = wg; wl < nw; wl += wgs) {
-        const int wr = wl / g.WP, wc = wl - wr * g.WP;
-        const int64_t pi = (((int64_t)n * g.HP + hp0 + wr) * g.WP + wc) * g.O + o;
-        const unsigned code = A.w.sel[pi];
-        const float xh = A.w.xh[pi];
-        const float aq = A.w.aqm[pi];
+        const unsigned code_c = code;
+        const float xh_c = xh, aq_c = aq, dx_c = dx;
+        const int nxt = wl + wgs;
+        if (nxt < nw) {
+          const int64_t i1 = tbase + (int64_t)nxt * g.O;
+          code = sel[i1]; xh = xhp[i1]; aq = aqm[i1];
+          if (!BASE) dx = dxhp[i1];
+        }
         float v;
         if (BASE) {
-          v = aq;
+          v = aq_c;
         } else {
-          v = (code & 4) ? ins[o * g.wpitch + wl] : 0.f;
-          s2 = fmaf(aq, A.w.dxh[pi], s2);
+          v = (code_c & 4) ? ins[o * g.wpitch + wl] : 0.f;
+          s2 = fmaf(aq_c, dx_c, s2);
         }
         s0 += v;
-        s1 = fmaf(v, xh, s1);
-        const int base = (2 * wr + ((code >> 1) & 1)) * g.xpitch + 2 * wc + (code & 1);
+        s1 = fmaf(v, xh_c, s1);
+        const int base = (2 * wr + ((code_c >> 1) & 1)) * g.xpitch + 2 * wc + (code_c & 1);
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
@@ -453,6 +505,8 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
 #pragma unroll
             for (int j = 0; j < 3; ++j)
               gw[(c * 3 + i) * 3 + j] = fmaf(v, xs[base + c * plane + i * g.xpitch + j], gw[(c * 3 + i) * 3 + j]);
+        wc += wgs;
+        while (wc >= g.WP) { wc -= g.WP; ++wr; }
       }
     }
   }
@@ -534,8 +588,6 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
   const int wgs = (NT / 32) / ((g.O + 31) / 32);
   const size_t smem_red = 4 * (size_t)wgs * g.O * (KP + NSUM);
   const size_t smem_k = smem > smem_red ? smem : smem_red;
-  int grid = g.ntiles < GRID_MAX ? g.ntiles : GRID_MAX;
-  if (grid < 1) grid = 1;
   static BbOncePerDevice once;
   if (once.need()) {
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_tf_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -544,6 +596,15 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_gram_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   if (smem_k > 200 * 1024) return BB_ERR_UNSUPPORTED;
+  // persistent grids: exactly the CTAs that are resident at once (a partial second wave would run at a fraction of
+  // the occupancy for as long as a full one)
+  auto resident = [&](const void* fn) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem_k) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int gmax = per_sm * BB_SM_COUNT;
+    if (gmax > GRID_MAX) gmax = GRID_MAX;
+    return g.ntiles < gmax ? (g.ntiles < 1 ? 1 : g.ntiles) : gmax;
+  };
   if (pass == BB_PASS_BASE_BWD) {
     const size_t nd = sizeof(double) * (2 * g.O + KP + g.O + g.O * KP + KP * KP);
     BB_CUDA_TRY(cudaMemsetAsync(A.w.dsum, 0, nd, s));
@@ -558,6 +619,7 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     int ggrid = g.N * bands < GRID_MAX ? g.N * bands : GRID_MAX;
     cb_gram_kernel<C><<<ggrid, NT, smem_k, s>>>(A);
     cb_gram_finish_kernel<<<8, 256, 0, s>>>(A);
+    const int grid = resident((const void*)cb_reduce_kernel<C, true>);
     A.nparts = grid;
     cb_reduce_kernel<C, true><<<grid, NT, smem_k, s>>>(A);
     cb_finish_kernel<true><<<g.O, 64, 0, s>>>(A, C * 9);
@@ -566,11 +628,13 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     return BB_OK;
   }
   if (pass == BB_PASS_TAN_FWD) {
+    const int grid = resident((const void*)cb_tf_kernel<C>);
     cb_tf_kernel<C><<<grid, NT, smem_k, s>>>(A);
     bb_launch_tally += 1;
     BB_LAUNCH_CHECK();
     return BB_OK;
   }
+  const int grid = resident((const void*)cb_reduce_kernel<C, false>);
   A.nparts = grid;
   cb_reduce_kernel<C, false><<<grid, NT, smem_k, s>>>(A);
   cb_finish_kernel<false><<<g.O, 64, 0, s>>>(A, C * 9);
@@ -602,7 +666,10 @@ int bb_launch_convblock(const bb_node& nd, int pass, cudaStream_t s) {
   A.t_b = reinterpret_cast<const float*>(nd.t[1]); A.at_b = reinterpret_cast<float*>(nd.at[1]);
   A.t_gamma = reinterpret_cast<const float*>(nd.t[2]); A.at_gamma = reinterpret_cast<float*>(nd.at[2]);
   A.t_beta = reinterpret_cast<const float*>(nd.aux[1]); A.at_beta = reinterpret_cast<float*>(nd.aux[2]);
-  A.t_q = reinterpret_cast<float*>(nd.t[3]);
+  // kind bit 2: the pooled tangent is the next fused block's bf16 NHWC operand ([N][HP][WP][64], O == 64)
+  const bool tq_nhwc = (nd.kind & 4) && A.g.O == 64;
+  A.t_q = tq_nhwc ? nullptr : reinterpret_cast<float*>(nd.t[3]);
+  A.tq_nhwc = tq_nhwc ? reinterpret_cast<__nv_bfloat16*>(nd.t[3]) : nullptr;
   A.a_q = reinterpret_cast<const float*>(nd.a[3]);
   A.at_q = reinterpret_cast<const float*>(nd.at[3]);
   return A.g.C == 1 ? run<1>(A, pass, s) : run<3>(A, pass, s);

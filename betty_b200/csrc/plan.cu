@@ -103,6 +103,8 @@ int dispatch(const bb_node& nd, int pass, cudaStream_t s) {
       return bb_launch_avgpool2d(nd, pass, s);
     case BB_OP_CONVBLOCK:
       return bb_launch_convblock(nd, pass, s);
+    case BB_OP_CONVBLOCK2:
+      return bb_launch_convblock2(nd, pass, s);
     case BB_OP_DIAGSHIFT: {
       if (pass != BB_PASS_TAN_BWD) return BB_OK;
       bb_launch_tally += 1;

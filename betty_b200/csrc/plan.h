@@ -25,6 +25,7 @@ enum bb_op {
   BB_OP_EMBEDDING = 16, // dims = nidx,D,V,padding_idx  aux[0] = int64 indices
   BB_OP_AVGPOOL2D = 18, // linear: dims = NC,H,W,HO,WO,kh,kw,sh,sw,ph,pw  f[0] = 1/divisor
   BB_OP_CONVBLOCK = 19, // fused data-input conv3x3 -> BatchNorm -> [ReLU] -> MaxPool2d(2) (convblock.cu)
+  BB_OP_CONVBLOCK2 = 20, // fused inner conv3x3 -> BatchNorm -> [ReLU] -> MaxPool2d(2) of a bf16 graph (convblock2.cu)
   BB_OP_DIAGSHIFT = 17, // folded c*sum((w-const)^2): at_w += f[0]*t_w over aux[0] = bb_mt_chunk[dims[0]] {a=t_w, b=at_w}
 };
 
@@ -68,6 +69,7 @@ int bb_launch_bce(const bb_node& nd, int pass, cudaStream_t s);
 int bb_launch_embedding(const bb_node& nd, int pass, cudaStream_t s);
 int bb_launch_avgpool2d(const bb_node& nd, int pass, cudaStream_t s);
 int bb_launch_convblock(const bb_node& nd, int pass, cudaStream_t s);
+int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s);
 // number of kernel launches (incl. memsets) the call above makes, for bench.py's gpu_launches
 extern thread_local int bb_launch_tally;
 #endif

@@ -35,7 +35,7 @@ class Val:
     """A lower-active tensor value."""
 
     __slots__ = ("vid", "base", "param_index", "parent", "viewfn", "full_cover", "name", "t", "a", "at",
-                 "writers", "needed", "zero_init", "ident", "boundary", "interp_only")
+                 "writers", "needed", "zero_init", "ident", "boundary", "interp_only", "tfmt")
 
     def __init__(self, vid, base, param_index=None, parent=None, viewfn=None, full_cover=True, name="", ident=False):
         self.vid = vid
@@ -52,6 +52,7 @@ class Val:
         self.ident = ident                  # alias whose buffers are *exactly* the parent's (cast, x + const)
         self.boundary = False               # upper-dependent constant (requires_grad, not from the lower params)
         self.interp_only = False            # internal value of a fused node: only the torch interpreter gives it buffers
+        self.tfmt = None                    # "nhwc_bf16": the tangent buffer is the next fused block's TMA operand
 
     @property
     def root(self) -> "Val":
@@ -862,14 +863,17 @@ def _fuse_data_conv_block(g: Graph):
             out_nodes.append(n)
             continue
         conv, bn, pool = blk
-        w, b = conv.ins[1], conv.ins[2]
+        x, w, b = conv.ins
         gam, bet = bn.ins[1], bn.ins[2]
         conv.beta, bn.beta, pool.beta = [0, 1, 1], [0, 1, 1], [0]   # what _analyse would give the members
-        node = Node("convblock", [w, b, gam, bet], pool.out,
-                    dict(members=[conv, bn, pool], X=conv.attrs["X"], W=conv.attrs["W"], Y=conv.out.base,
-                         padding=conv.attrs["padding"], eps=bn.attrs["eps"], gamma=bn.attrs["gamma"],
-                         indices=pool.attrs["indices"], relu=bool(pool.attrs.get("relu"))),
-                    src="conv3x3(data)+batch_norm+relu+max_pool2d" if pool.attrs.get("relu") else "conv3x3(data)+batch_norm+max_pool2d")
+        attrs = dict(members=[conv, bn, pool], X=conv.attrs["X"], W=conv.attrs["W"], Y=conv.out.base,
+                     padding=conv.attrs["padding"], eps=bn.attrs["eps"], gamma=bn.attrs["gamma"],
+                     indices=pool.attrs["indices"], relu=bool(pool.attrs.get("relu")))
+        tail = "+batch_norm+relu+max_pool2d" if pool.attrs.get("relu") else "+batch_norm+max_pool2d"
+        if x is None:
+            node = Node("convblock", [w, b, gam, bet], pool.out, attrs, src="conv3x3(data)" + tail)
+        else:
+            node = Node("convblock2", [x, w, b, gam, bet], pool.out, attrs, src="conv3x3" + tail)
         conv.out.interp_only = bn.out.interp_only = True
         out_nodes.append(node)
         dropped.update((id(bn), id(pool)))
@@ -877,16 +881,43 @@ def _fuse_data_conv_block(g: Graph):
     if fused:
         g.nodes = out_nodes
         g.stats = {**g.stats, "conv_blocks_fused": fused}
+        # a pooled tangent that only feeds the next fused inner block is written directly as that block's bf16 NHWC
+        # TMA operand (64 channels): no fp32 buffer, no pack kernel
+        cons: Dict[int, List[Node]] = {}
+        for n in g.nodes:
+            for v in n.ins:
+                if v is not None:
+                    cons.setdefault(id(v.root), []).append(n)
+        for n in g.nodes:
+            if n.op in ("convblock", "convblock2") and n.out.parent is None and n.out.base.shape[1] == 64:
+                users = cons.get(id(n.out), [])
+                if len(users) == 1 and users[0].op == "convblock2" and users[0].ins[0] is n.out and n.out is not g.loss:
+                    n.out.tfmt = "nhwc_bf16"
 
 
 def _match_data_conv_block(g: Graph, conv: Node, consumers) -> Optional[Tuple[Node, Node, Node]]:
-    if conv.op != "conv2d" or conv.ins[0] is not None or conv.ins[1] is None:
+    import os
+
+    if conv.op != "conv2d" or conv.ins[1] is None:
         return None
     at = conv.attrs
-    W = at["W"]
+    W, X = at["W"], at["X"]
     if (at["groups"] != 1 or tuple(at["stride"]) != (1, 1) or tuple(at["dilation"]) != (1, 1)
-            or tuple(W.shape[2:]) != (3, 3) or W.shape[1] not in (1, 3) or W.shape[0] > 64):
+            or tuple(W.shape[2:]) != (3, 3) or W.shape[0] > 64):
         return None
+    if conv.ins[0] is None:
+        if W.shape[1] not in (1, 3):                     # data-input block (convblock.cu)
+            return None
+    else:
+        # inner block (convblock2.cu): bf16-autocast graphs only -- its products run on the TMA tensor-core kernels,
+        # whose shape limits (conv_tma.cu bb_conv_tma_ok) apply
+        x = conv.ins[0]
+        reduced = X.dtype in (torch.bfloat16, torch.float16) and W.dtype in (torch.bfloat16, torch.float16)
+        C, O, Wd, WO = W.shape[1], W.shape[0], X.shape[3], conv.out.base.shape[3]
+        if (os.environ.get("BB200_NO_CONVBLOCK2") or not reduced or x.parent is not None or x.boundary
+                or not (32 <= C <= 64 and 32 <= O <= 64 and 4 <= WO <= 64 and Wd <= 128)
+                or tuple(at["padding"]) != (1, 1) or not X.is_contiguous()):
+            return None
     def is_param(v):
         # the parameter itself, or its autocast copy (an identity alias: same tangent / adjoint-tangent slices)
         while v is not None and v.parent is not None and v.ident:

@@ -18,7 +18,7 @@ from .ir import Graph, Node, UnsupportedGraph, Val, _is_dense, lower_tape
 BB_MAX_DIMS = 6
 OPS = {"unary": 1, "copy": 2, "add2": 3, "mulc": 4, "mul2": 5, "sumall": 6, "gemm": 7, "conv2d": 8,
        "maxpool2d": 9, "batchnorm": 10, "layernorm": 11, "softmax": 12, "logsoftmax": 13, "nll": 14,
-       "bce_logits": 15, "embedding": 16, "diagshift": 17, "avgpool2d": 18, "convblock": 19}
+       "bce_logits": 15, "embedding": 16, "diagshift": 17, "avgpool2d": 18, "convblock": 19, "convblock2": 20}
 UNARY = {"relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4, "pow": 5, "scale": 6, "neg": 6}
 PASS_BB, PASS_TF, PASS_TB = 0, 1, 2
 
@@ -86,7 +86,8 @@ class HvpPlan:
         for v in roots:
             n = _align(v.base.numel())
             place[v.vid] = (sizes["t"], sizes["z" if v.zero_init else "nz"])
-            sizes["t"] += n
+            if v.tfmt is None:
+                sizes["t"] += n
             sizes["z" if v.zero_init else "nz"] += n
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.T = torch.zeros(max(sizes["t"], 1), **f32)
@@ -97,7 +98,13 @@ class HvpPlan:
             ot, oa = place[v.vid]
             k = "z" if v.zero_init else "nz"
             shape, stride = tuple(v.base.shape), tuple(v.base.stride())
-            v.t = torch.as_strided(self.T, shape, stride, ot)
+            if v.tfmt == "nhwc_bf16":
+                # tangent written by a fused block directly as the next fused block's TMA operand: bf16 [N][H][W][64]
+                Nn, Cc, Hh, Ww = shape
+                assert Cc == 64, shape
+                v.t = torch.zeros((Nn, Hh, Ww, 64), dtype=torch.bfloat16, device=self.dev)
+            else:
+                v.t = torch.as_strided(self.T, shape, stride, ot)
             v.a = torch.as_strided(self.A[k], shape, stride, oa)
             v.at = torch.as_strided(self.AT[k], shape, stride, oa)
         dviews, hviews = self.layout.views(self.d_arena), self.layout.views(self.hv_arena)
@@ -430,7 +437,7 @@ class HvpPlan:
         ph, pw = n.attrs["padding"]
         r["dims"][0:16] = (Nn, Cc, H, Wd, O, 3, 3, HO, WO, 1, 1, ph, pw, HP, WP, int(n.attrs["relu"]))
         r["f"][0] = n.attrs["eps"]
-        r["kind"] = int(X.dtype in (torch.bfloat16, torch.float16))
+        r["kind"] = int(X.dtype in (torch.bfloat16, torch.float16)) | (4 if n.out.tfmt == "nhwc_bf16" else 0)
         if not (X.is_contiguous() and Y.is_contiguous()):
             raise UnsupportedGraph("convblock operands must be NCHW-contiguous")
         self._slot(r, 0, w, None)
@@ -447,6 +454,43 @@ class HvpPlan:
         r["aux"][1] = self._ptr(self.buf(bet, "t"))
         r["aux"][2] = self._ptr(self.buf(bet, "at"))
         r["aux"][3] = self._const(n.attrs["indices"], torch.int64).data_ptr()
+
+    def _n_convblock2(self, n: Node, r):
+        """Fused inner conv3x3 -> BatchNorm -> [ReLU] -> MaxPool2d(2) of a bf16 graph (csrc/convblock2.cu; slot map there)."""
+        x, w, b, gam, bet = n.ins
+        X, W, Y = n.attrs["X"], n.attrs["W"], n.attrs["Y"]
+        Nn, Cc, H, Wd = X.shape
+        O = W.shape[0]
+        _, _, HO, WO = Y.shape
+        _, _, HP, WP = n.out.base.shape
+        ph, pw = n.attrs["padding"]
+        r["dims"][0:16] = (Nn, Cc, H, Wd, O, 3, 3, HO, WO, 1, 1, ph, pw, HP, WP, int(n.attrs["relu"]))
+        r["f"][0] = n.attrs["eps"]
+        if not (X.is_contiguous() and Y.is_contiguous() and W.is_contiguous()):
+            raise UnsupportedGraph("convblock2 operands must be contiguous")
+        # kind: bit 0 reduced precision, bit 1: t of x_in is bf16 NHWC, bit 2: t of q is bf16 NHWC
+        r["kind"] = 1 | (2 if x.tfmt == "nhwc_bf16" else 0) | (4 if n.out.tfmt == "nhwc_bf16" else 0)
+        for s_, v in ((0, x), (1, w), (2, gam), (3, n.out)):
+            if v is None:
+                continue
+            for kind in ("t", "a", "at"):
+                r[kind][s_] = self._ptr(self.buf(v, kind))
+        r["base"][0], r["dt"][0] = X.data_ptr(), _dt(X)
+        r["base"][1], r["dt"][1] = W.data_ptr(), _dt(W)
+        g_t = n.attrs["gamma"]
+        r["base"][2] = g_t.data_ptr() if g_t is not None else 0
+        r["base"][3], r["dt"][3] = n.out.base.data_ptr(), _dt(n.out.base)
+        nbytes = int(N.lib().bb_convblock2_ws_bytes(Nn, Cc, H, Wd, O, HO, WO, HP, WP))
+        ws = torch.zeros(nbytes // 8 + 1, dtype=torch.float64, device=self.dev)
+        self._keep.append(ws)
+        r["aux"][0] = ws.data_ptr()
+        r["aux"][1] = self._const(n.attrs["indices"], torch.int64).data_ptr()
+        r["aux"][2] = Y.data_ptr()
+        r["ndim"] = _dt(Y)
+        ptrs = [self._ptr(self.buf(b, "t")), self._ptr(self.buf(b, "at")), self._ptr(self.buf(bet, "t")),
+                self._ptr(self.buf(bet, "at"))]
+        for k, pv in enumerate(ptrs):
+            r["stride"][0][k] = np.int64(np.uint64(pv).astype(np.int64)) if pv >= 2 ** 63 else pv
 
     def _n_avgpool2d(self, n: Node, r):
         x = n.ins[0]
@@ -682,6 +726,13 @@ class HvpPlan:
         n = self.g.nodes[i]
         if n.op == "diagshift":
             return 12 * sum(p.base.numel() for p in n.ins) if pas == PASS_TB else 0
+        if n.op == "convblock2":
+            # what the fused rule moves besides the tensor-core operands: see csrc/convblock2.cu header
+            X, Y, q = n.attrs["X"], n.attrs["Y"], n.out.base.numel()
+            a_in, a_out = X.numel(), Y.numel()
+            if pas == PASS_TF:
+                return int(4 * a_in + 4 * a_out + 6 * a_out + 4 * q + 13 * q)
+            return int((6 + 2.25) * a_out + 2 * a_out + 4 * a_out + 4 * a_in + 4 * a_out + 4 * a_in + 17 * q)
         if n.op == "convblock":
             # what the fused rule streams: x once, then pooled-size arrays (arg-max code 1 B, xhat* 4 B, dxhat* 4 B,
             # pooled tangent / adjoint-tangent 4 B, masked base adjoint 4 B)

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import torch
 
-_PARAMETRIC = ("gemm", "conv2d", "batchnorm", "layernorm", "embedding", "convblock")
+_PARAMETRIC = ("gemm", "conv2d", "batchnorm", "layernorm", "embedding", "convblock", "convblock2")
 
 
 def _is_param(v) -> bool:
@@ -33,7 +33,7 @@ def survey_bytes(graph, method: str) -> dict:
         nonlocal reduced, w_bytes, a_in, a_out
         for m in n.attrs.get("members", ()):
             visit(m)
-        if n.op not in _PARAMETRIC or n.op == "convblock":
+        if n.op not in _PARAMETRIC or n.op in ("convblock", "convblock2"):
             return
         pl = [v for v in n.ins if _is_param(v)]
         if not pl:

@@ -119,6 +119,8 @@ int bb_plan_graph_captures(const bb_plan* plan); /* how many times a K-loop iter
 int bb_plan_node_route(bb_plan* plan, int node, int pass); /* tests: 2 = TMA tensor-core convolution path */
 /* bytes of the per-node workspace of a fused data-input convolution block (BB_OP_CONVBLOCK, csrc/convblock.cu) */
 int64_t bb_convblock_ws_bytes(int N, int C, int H, int W, int O, int HO, int WO, int HP, int WP);
+/* same for a fused inner block of a bf16 graph (BB_OP_CONVBLOCK2, csrc/convblock2.cu) */
+int64_t bb_convblock2_ws_bytes(int N, int C, int H, int W, int O, int HO, int WO, int HP, int WP);
 /* whole K-loops: one iteration is captured into a CUDA graph at the first call and relaunched by every later
  * call with the same arenas / alpha (direction arena `d`, result `hv`) */
 int bb_plan_neumann_loop(bb_plan* plan, int iterations, float alpha, float* v /*direction*/, float* p,

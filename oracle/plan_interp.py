@@ -83,13 +83,21 @@ class Interp:
         for m in n.attrs["members"]:
             getattr(self, "tf_" + m.op)(m)
 
+    def _sync_member_modes(self, n):
+        if n.op == "convblock2":            # the conv member writes x_in's adjoint the way the fused node is told to
+            n.attrs["members"][0].beta[0] = n.beta[0]
+
     def bb_convblock(self, n):
+        self._sync_member_modes(n)
         for m in reversed(n.attrs["members"]):
             getattr(self, "bb_" + m.op)(m)
 
     def tb_convblock(self, n):
+        self._sync_member_modes(n)
         for m in reversed(n.attrs["members"]):
             getattr(self, "tb_" + m.op)(m)
+
+    tf_convblock2, bb_convblock2, tb_convblock2 = tf_convblock, bb_convblock, tb_convblock
 
     # ---- diagshift: folded c*sum((w-const)^2) terms (ir._fold_quadratic_regularisers) -----------------
     def tf_diagshift(self, n):

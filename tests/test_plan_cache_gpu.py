@@ -20,7 +20,8 @@ CASES = {
     "fourconv_neumann": ("implicit_maml", dict(method="neumann", n=10, hidden=16, K=6, alpha=0.01)),
     "fourconv_mini_bf16": ("implicit_maml", dict(method="neumann", n=4, hidden=64, image="miniimagenet", K=6, alpha=0.01, precision="bf16")),
     "roberta_cg": ("bert_data_reweighting", dict(method="cg", batch=3, seq=9, K=4, tiny=True)),
-    "roberta_bf16_cg": ("bert_data_reweighting", dict(method="cg", batch=4, seq=40, K=4, tiny=True, tiny_hidden=256, precision="bf16")),
+    # (Neumann: CG on bf16 products amplifies the run-to-run order of the split-K atomics beyond any fixed tolerance)
+    "roberta_bf16_neumann": ("bert_data_reweighting", dict(method="neumann", batch=4, seq=40, K=4, alpha=0.02, tiny=True, tiny_hidden=256, precision="bf16")),
 }
 
 

@@ -35,6 +35,9 @@ CASES = {
     "roberta_bf16_attn_tc": ("bert_data_reweighting", dict(batch=4, seq=40, tiny=True, tiny_hidden=256, precision="bf16"), 4e-2),
     "fourconv_bf16_tc": ("implicit_maml", dict(n=6, hidden=64, precision="bf16"), 5e-2),
     "fourconv_mini_bf16_tc": ("implicit_maml", dict(n=2, hidden=32, image="miniimagenet", precision="bf16"), 5e-2),
+    # 64 channels: every block fused (data-input block + three inner blocks chained through bf16 NHWC tangents)
+    "fourconv_mini_bf16_c64": ("implicit_maml", dict(n=3, hidden=64, image="miniimagenet", precision="bf16"), 5e-2),
+    "fourconv_omniglot_bf16_c64_n12": ("implicit_maml", dict(n=12, hidden=64, precision="bf16"), 5e-2),
     "roberta_fp16": ("bert_data_reweighting", dict(batch=3, seq=9, tiny=True, precision="fp16"), 3e-2),
     "mlp_fp16_tc": ("mlp_reweight", dict(batch=256, din=192, hidden=256, classes=64, precision="fp16"), 4e-2),
     "mlp_bf16_tc": ("mlp_reweight", dict(batch=256, din=192, hidden=256, classes=64, precision="bf16"), 4e-2),
@@ -62,6 +65,8 @@ def _compare(plan, interp, kinds, tol, what):
             continue
         for k in kinds:
             a, b = getattr(vn, k), getattr(vi, k)
+            if k == "t" and getattr(vn, "tfmt", None) == "nhwc_bf16":
+                a = a.permute(0, 3, 1, 2).float()     # fused blocks hand this tangent over as a bf16 NHWC TMA operand
             err = float((a.double() - b).norm() / (b.norm() + 1e-30)) if float(b.norm()) > 0 else float(a.double().norm())
             if not (err <= tol):
                 prod = [n for n in plan.g.nodes if n.out is vn]
