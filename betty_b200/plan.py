@@ -167,6 +167,8 @@ class HvpPlan:
             for kind in ("t", "a", "at"):
                 b = self.buf(v, kind)
                 rec[kind][s] = self._ptr(b)
+                if kind == "t" and v.root.tfmt is not None:
+                    continue            # bf16 NHWC tangent handed from one fused block to the next
                 if b is not None and base_t is not None and b.numel() > 1 and tuple(b.stride()) != tuple(base_t.stride()):
                     raise UnsupportedGraph(f"buffer/base stride mismatch for {v}: {b.stride()} vs {base_t.stride()}")
 
