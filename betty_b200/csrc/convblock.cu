@@ -190,6 +190,30 @@ __device__ __forceinline__ void load_x_tile(const CbArgs& A, int n, int hp0, flo
   }
 }
 
+// Bulk copy of a contiguous global range into shared memory with cp.async (no register staging: every thread has
+// several independent 16-byte requests in flight, so the pooled arrays of a whole tile stream in at DRAM latency
+// once instead of once per window -- the first version of these kernels ran at 10 % of DRAM throughput on exactly
+// that dependency, profiles/r02_convblock_v0_ncu.md).  Falls back to plain loads for unaligned ranges.
+__device__ __forceinline__ void tile_copy_async(void* dst_smem, const void* src, int nbytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+  if (((a | d | (uintptr_t)nbytes) & 15) == 0) {
+    for (int i = threadIdx.x * 16; i < nbytes; i += NT * 16)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i), "l"(a + i) : "memory");
+  } else if (((a | d | (uintptr_t)nbytes) & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < nbytes; i += NT * 4)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + i), "l"(a + i) : "memory");
+  } else {
+    const unsigned char* sp = reinterpret_cast<const unsigned char*>(src);
+    unsigned char* dp = reinterpret_cast<unsigned char*>(dst_smem);
+    for (int i = threadIdx.x; i < nbytes; i += NT) dp[i] = sp[i];
+  }
+}
+__device__ __forceinline__ void tile_copy_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // dot of the 3x3xC patch whose top-left tap sits at xs[base] with per-lane weights tw[C*9]
 template <int C>
 __device__ __forceinline__ float patch_dot(const float* xs, int base, int plane, int pitch, const float* tw) {
@@ -383,24 +407,26 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
   // t_q = mask * (c_y * t_y + c_x * xhat + c_0)
   const float c_y = gam * rstd, c_x = tgam - gam * rstd * sdot, c_0 = tbeta + gam * rstd * (tb - mean_t);
   const float e_0 = (tb - mean_t) * rstd, e_x = -sdot * rstd;          // dxhat = rstd*t_y + e_x*xhat + e_0
+  const int tcap = g.R * g.WP * g.O;                 // pooled elements of a full tile
+  float* xh_s = outs + g.O * g.wpitch;               // [nw][O] xhat* of the tile
+  unsigned char* sel_s = reinterpret_cast<unsigned char*>(xh_s + tcap);
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int n = tile / g.tiles_per_img, tr = tile - n * g.tiles_per_img;
     const int hp0 = tr * g.R, rows = min(g.R, g.HP - hp0), nw = rows * g.WP;
+    const int64_t t0 = ((int64_t)n * g.HP + hp0) * g.WP * g.O;             // NHWC index of (window 0, channel 0)
     __syncthreads();
+    tile_copy_async(xh_s, xhp + t0, nw * g.O * 4);
+    tile_copy_async(sel_s, sel + t0, nw * g.O);
     load_x_tile<C>(A, n, hp0, xs);
+    tile_copy_wait();
     __syncthreads();
     if (och) {
-      const int64_t tbase = ((int64_t)n * g.HP + hp0) * g.WP * g.O + o;     // NHWC index of (window 0, channel o)
+      const int64_t tbase = t0 + o;
       int wr = 0, wc = wg;
       while (wc >= g.WP) { wc -= g.WP; ++wr; }
-      unsigned code = 0;
-      float xh = 0.f;
-      if (wg < nw) { code = sel[tbase + (int64_t)wg * g.O]; xh = xhp[tbase + (int64_t)wg * g.O]; }
       for (int wl = wg; wl < nw; wl += wgs) {
-        const unsigned code_c = code;
-        const float xh_c = xh;
-        const int nxt = wl + wgs;
-        if (nxt < nw) { code = sel[tbase + (int64_t)nxt * g.O]; xh = xhp[tbase + (int64_t)nxt * g.O]; }
+        const unsigned code_c = sel_s[wl * g.O + o];
+        const float xh_c = xh_s[wl * g.O + o];
         const int base = (2 * wr + ((code_c >> 1) & 1)) * g.xpitch + 2 * wc + (code_c & 1);
         const float ty = patch_dot<C>(xs, base, plane, g.xpitch, tw);
         dxhp[tbase + (int64_t)wl * g.O] = fmaf(rstd, ty, fmaf(e_x, xh_c, e_0));
@@ -454,10 +480,20 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
 #pragma unroll
   for (int k = 0; k < CKK; ++k) gw[k] = 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const int tcap = g.R * g.WP * g.O;
+  float* xh_s = ins + g.O * g.wpitch;
+  float* aq_s = xh_s + tcap;
+  float* dx_s = aq_s + tcap;
+  unsigned char* sel_s = reinterpret_cast<unsigned char*>(dx_s + tcap);
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int n = tile / g.tiles_per_img, tr = tile - n * g.tiles_per_img;
     const int hp0 = tr * g.R, rows = min(g.R, g.HP - hp0), nw = rows * g.WP;
+    const int64_t t0 = ((int64_t)n * g.HP + hp0) * g.WP * g.O;
     __syncthreads();
+    tile_copy_async(xh_s, xhp + t0, nw * g.O * 4);
+    tile_copy_async(aq_s, aqm + t0, nw * g.O * 4);
+    if (!BASE) tile_copy_async(dx_s, dxhp + t0, nw * g.O * 4);
+    tile_copy_async(sel_s, sel + t0, nw * g.O);
     load_x_tile<C>(A, n, hp0, xs);
     if (!BASE) {
       const float* src = A.at_q + (((int64_t)n * g.O) * g.HP + hp0) * g.WP;
@@ -467,33 +503,21 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
         for (int wl = lane; wl < nw; wl += 32) d[wl] = sp[wl];
       }
     }
+    tile_copy_wait();
     __syncthreads();
     if (och) {
-      const int64_t tbase = ((int64_t)n * g.HP + hp0) * g.WP * g.O + o;
       int wr = 0, wc = wg;
       while (wc >= g.WP) { wc -= g.WP; ++wr; }
-      unsigned code = 0;
-      float xh = 0.f, aq = 0.f, dx = 0.f;
-      if (wg < nw) {
-        const int64_t i0 = tbase + (int64_t)wg * g.O;
-        code = sel[i0]; xh = xhp[i0]; aq = aqm[i0];
-        if (!BASE) dx = dxhp[i0];
-      }
       for (int wl = wg; wl < nw; wl += wgs) {
-        const unsigned code_c = code;
-        const float xh_c = xh, aq_c = aq, dx_c = dx;
-        const int nxt = wl + wgs;
-        if (nxt < nw) {
-          const int64_t i1 = tbase + (int64_t)nxt * g.O;
-          code = sel[i1]; xh = xhp[i1]; aq = aqm[i1];
-          if (!BASE) dx = dxhp[i1];
-        }
+        const int si = wl * g.O + o;
+        const unsigned code_c = sel_s[si];
+        const float xh_c = xh_s[si], aq_c = aq_s[si];
         float v;
         if (BASE) {
           v = aq_c;
         } else {
           v = (code_c & 4) ? ins[o * g.wpitch + wl] : 0.f;
-          s2 = fmaf(aq_c, dx_c, s2);
+          s2 = fmaf(aq_c, dx_s[si], s2);
         }
         s0 += v;
         s1 = fmaf(v, xh_c, s1);
@@ -584,10 +608,14 @@ template <int C>
 int run(const CbArgs& A0, int pass, cudaStream_t s) {
   CbArgs A = A0;
   const CbGeom& g = A.g;
-  const size_t smem = 4 * ((size_t)C * g.xrows * g.xpitch + (size_t)g.O * g.wpitch);
+  // x tile + transposed pooled tile (+ staged pooled arrays of one tile: xhat*, mask a_q, dxhat* 4 B each, codes 1 B)
+  const size_t tcap = (size_t)g.R * g.WP * g.O;
+  const size_t tile = 4 * ((size_t)C * g.xrows * g.xpitch + (size_t)g.O * g.wpitch);
   const int wgs = (NT / 32) / ((g.O + 31) / 32);
-  const size_t smem_red = 4 * (size_t)wgs * g.O * (KP + NSUM);
-  const size_t smem_k = smem > smem_red ? smem : smem_red;
+  const size_t smem_part = 4 * (size_t)wgs * g.O * (KP + NSUM);
+  const size_t smem_tf = tile + 5 * tcap + 64;
+  size_t smem_red = tile + 13 * tcap + 64;
+  if (smem_red < smem_part) smem_red = smem_part;
   static BbOncePerDevice once;
   if (once.need()) {
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_tf_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -595,12 +623,12 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_reduce_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_gram_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  if (smem_k > 200 * 1024) return BB_ERR_UNSUPPORTED;
+  if (smem_red > 200 * 1024) return BB_ERR_UNSUPPORTED;
   // persistent grids: exactly the CTAs that are resident at once (a partial second wave would run at a fraction of
   // the occupancy for as long as a full one)
-  auto resident = [&](const void* fn) {
+  auto resident = [&](const void* fn, size_t smem) {
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem_k) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     int gmax = per_sm * BB_SM_COUNT;
     if (gmax > GRID_MAX) gmax = GRID_MAX;
     return g.ntiles < gmax ? (g.ntiles < 1 ? 1 : g.ntiles) : gmax;
@@ -617,26 +645,26 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     cb_prep_kernel<<<4 * BB_SM_COUNT, 256, 0, s>>>(A);
     const int bands = (g.HO + 2 * g.R - 1) / (2 * g.R);
     int ggrid = g.N * bands < GRID_MAX ? g.N * bands : GRID_MAX;
-    cb_gram_kernel<C><<<ggrid, NT, smem_k, s>>>(A);
+    cb_gram_kernel<C><<<ggrid, NT, tile, s>>>(A);
     cb_gram_finish_kernel<<<8, 256, 0, s>>>(A);
-    const int grid = resident((const void*)cb_reduce_kernel<C, true>);
+    const int grid = resident((const void*)cb_reduce_kernel<C, true>, smem_red);
     A.nparts = grid;
-    cb_reduce_kernel<C, true><<<grid, NT, smem_k, s>>>(A);
+    cb_reduce_kernel<C, true><<<grid, NT, smem_red, s>>>(A);
     cb_finish_kernel<true><<<g.O, 64, 0, s>>>(A, C * 9);
     bb_launch_tally += 9;
     BB_LAUNCH_CHECK();
     return BB_OK;
   }
   if (pass == BB_PASS_TAN_FWD) {
-    const int grid = resident((const void*)cb_tf_kernel<C>);
-    cb_tf_kernel<C><<<grid, NT, smem_k, s>>>(A);
+    const int grid = resident((const void*)cb_tf_kernel<C>, smem_tf);
+    cb_tf_kernel<C><<<grid, NT, smem_tf, s>>>(A);
     bb_launch_tally += 1;
     BB_LAUNCH_CHECK();
     return BB_OK;
   }
-  const int grid = resident((const void*)cb_reduce_kernel<C, false>);
+  const int grid = resident((const void*)cb_reduce_kernel<C, false>, smem_red);
   A.nparts = grid;
-  cb_reduce_kernel<C, false><<<grid, NT, smem_k, s>>>(A);
+  cb_reduce_kernel<C, false><<<grid, NT, smem_red, s>>>(A);
   cb_finish_kernel<false><<<g.O, 64, 0, s>>>(A, C * 9);
   bb_launch_tally += 2;
   BB_LAUNCH_CHECK();
