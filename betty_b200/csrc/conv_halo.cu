@@ -1,0 +1,263 @@
+// Halo-resident implicit-GEMM 3x3 convolution on tcgen05 (64 -> 64 channels, stride 1, padding 1), forward and
+// input-gradient form, up to two operand pairs accumulated into one TMEM tile:
+//
+//     out[img][n][y][x] (beta)= sum_pairs sum_(tap, ch) A_p[img][y + dy(tap)][x + dx(tap)][ch] * B_p[n][tap][ch]  (+ bias[n])
+//
+// gemm_tma_kernel's TMA_CONV mode brings one 128-pixel x 64-channel box per TAP into shared memory: nine shifted
+// copies of (almost) the same pixels per tile, 24 KB of shared-memory fill per 2.1 MFLOP.  ncu shows that kernel --
+// and cuDNN's own sm100 implicit-GEMM fprop, 127 us for the 42x42 layer = 0.82 PFLOP/s -- bound by that fill rate
+// (tensor pipe 22 %, profiles/r01_persist_ncu.md), not by the tensor cores.  Here the activation lives in a PADDED
+// NHWC layout  [N][H+2][W+2][64]  (zero border), i.e. one long matrix of 128-byte pixel rows in which a tap
+// displacement (dy, dx) is the constant row offset dy*(W+2) + dx.  A tile is 128 consecutive pixel rows; ONE TMA box of
+// 128 + 2(W+2) + 2 rows is loaded per (tile, pair) and the nine taps are nine UMMA descriptors pointing at different
+// 128-byte row offsets inside that band (SWIZZLE_128B is a function of the shared-memory address bits, the
+// descriptor's base-offset field carries the 1024-byte phase).  The 2 x 9 weight tiles (144 KB) are loaded once per
+// CTA and stay resident.  Shared-memory fill per tile: 2 x 28 KB instead of 2 x 9 x 24 KB -> the MMA issue rate, not
+// the fill, bounds the kernel.  Rows that fall on the zero border compute garbage-free zeros' neighbours and are
+// simply not stored.
+//
+// Roles (192 threads, one CTA per SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issue,
+// warps 2-5 = epilogue (tcgen05.ld -> fp32 NCHW planes).  Two band buffers alternate between the pairs / tiles; the
+// accumulator is double-buffered in TMEM so a tile's epilogue overlaps the next tile's MMAs.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/betty_b200.h"
+#include "bb_common.cuh"
+#include "conv_halo.h"
+#include "gemm_tma.h"
+#include "plan.h"
+#include "tc_ptx.cuh"
+#include "tma.h"
+
+namespace {
+
+using namespace bbtc;
+
+constexpr int BM = 128, BN = 64;
+constexpr int NTHREADS = 192;
+constexpr int BAND_ROWS = 256;                 // TMA box limit; a band needs 128 + 2*(W+2) + 2 rows
+constexpr int BAND_BYTES = BAND_ROWS * 128;    // 32 KB
+constexpr int W_TILE = 64 * 128;               // one tap's weights: 64 rows (n) x 64 ch
+constexpr int NBAND = 2;
+
+struct alignas(64) HaloArgs {
+  CUtensorMap a[2];          // padded activation as a matrix [rows][64] (rank-3 map, batch 1), box (64, band_rows)
+  CUtensorMap b[2];          // weights [64][9*64], box (64, 64)
+  int npairs;
+  int Wp, HpWp;              // W+2, (H+2)*(W+2)
+  int H, W, N;
+  int band_rows;
+  int flip;
+  int64_t total_rows;        // N * (H+2) * (W+2)
+  int ntiles;
+  float* out;
+  int beta;
+  const float* bias;
+  int bo_mode;               // 1: descriptor base offset = (start >> 7) & 7 (PTX ISA), 0: always 0
+};
+
+__device__ __forceinline__ uint64_t desc_k_bo(uint32_t saddr, uint32_t bo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(bo & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* wsm = smem;                                    // [npairs][9][W_TILE]
+  uint8_t* bands = smem + 2 * 9 * W_TILE;                 // [NBAND][BAND_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bands + NBAND * BAND_BYTES);
+  const uint32_t wfull = smem_u32(bars);
+  const uint32_t bfull0 = smem_u32(bars + 1), bempty0 = smem_u32(bars + 1 + NBAND);
+  const uint32_t accf0 = smem_u32(bars + 1 + 2 * NBAND), acce0 = smem_u32(bars + 3 + 2 * NBAND);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NBAND);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(wfull, 1);
+    for (int b = 0; b < NBAND; ++b) {
+      mbar_init(bfull0 + 8 * b, 1);
+      mbar_init(bempty0 + 8 * b, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf0 + 8 * b, 1);
+      mbar_init(acce0 + 8 * b, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * BN));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t band_bytes = (uint32_t)G.band_rows * 128u;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int p = 0; p < G.npairs; ++p) {
+        tma_prefetch_desc(&G.a[p]);
+        tma_prefetch_desc(&G.b[p]);
+      }
+      mbar_expect_tx(wfull, (uint32_t)(G.npairs * 9 * W_TILE));
+      for (int p = 0; p < G.npairs; ++p)
+        for (int t = 0; t < 9; ++t) tma_load_3d(smem_u32(wsm + (p * 9 + t) * W_TILE), &G.b[p], wfull, t * 64, 0, 0);
+      int git = 0;
+      for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
+        const int row0 = tile * BM - G.Wp - 1;             // first band row (may be negative: zero fill)
+        for (int p = 0; p < G.npairs; ++p, ++git) {
+          const int b = git % NBAND;
+          if (git >= NBAND) mbar_wait(bempty0 + 8 * b, ((git / NBAND) - 1) & 1);
+          mbar_expect_tx(bfull0 + 8 * b, band_bytes);
+          tma_load_3d(smem_u32(bands + b * BAND_BYTES), &G.a[p], bfull0 + 8 * b, 0, row0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(BM, BN, false, false);
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int git = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        if (lt >= 2) {
+          mbar_wait(acce0 + 8 * buf, ((lt >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+        for (int p = 0; p < G.npairs; ++p, ++git) {
+          const int b = git % NBAND;
+          mbar_wait(bfull0 + 8 * b, (git / NBAND) & 1);
+          tc_fence_after();
+          const uint32_t band = smem_u32(bands + b * BAND_BYTES);
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const int i = t / 3, j = t - 3 * i;
+            const int dy = G.flip ? 1 - i : i - 1, dx = G.flip ? 1 - j : j - 1;
+            const uint32_t a0 = band + (uint32_t)((G.Wp + 1 + dy * G.Wp + dx) * 128);
+            const uint32_t bo = G.bo_mode ? ((a0 >> 7) & 7u) : 0u;
+            const uint32_t b0 = smem_u32(wsm + (p * 9 + t) * W_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tacc, desc_k_bo(a0 + k * 32, bo), desc_k(b0 + k * 32), idesc, (p > 0 || t > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bempty0 + 8 * b);
+        }
+        umma_commit(accf0 + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int64_t HW = (int64_t)G.H * G.W;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int64_t row = (int64_t)tile * BM + r;          // padded-linear pixel index
+      bool ok = row < G.total_rows;
+      int64_t obase = 0;
+      if (ok) {
+        const int img = (int)(row / G.HpWp);
+        const int rem = (int)(row - (int64_t)img * G.HpWp);
+        const int yy = rem / G.Wp, xx = rem - yy * G.Wp;
+        ok = yy >= 1 && yy <= G.H && xx >= 1 && xx <= G.W;
+        obase = (int64_t)img * BN * HW + (int64_t)(yy - 1) * G.W + (xx - 1);
+      }
+      mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1, 60);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+        }
+        if (!ok) continue;
+        float* q = G.out + obase + (int64_t)(c * 32) * HW;
+        if (G.bias) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + G.bias[c * 32 + jj]);
+        }
+        if (G.beta) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            *q += __uint_as_float(v[jj]);
+            q += HW;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            *q = __uint_as_float(v[jj]);
+            q += HW;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)(2 * BN));
+  }
+}
+
+}  // namespace
+
+bool bb_conv_halo_ok(int C, int O, int H, int W) {
+  static const bool off = getenv("BB200_NO_HALO") != nullptr;
+  return !off && C == 64 && O == 64 && W >= 4 && 128 + 2 * (W + 2) + 2 <= BAND_ROWS && H >= 1;
+}
+
+int bb_conv_halo_run(int N, int H, int W, int npairs, const void* const* act_padded, const void* const* wmat, int flip,
+                     float* out, int beta, const float* bias, cudaStream_t s) {
+  if (npairs < 1 || npairs > 2 || !bb_conv_halo_ok(64, 64, H, W)) return BB_ERR_UNSUPPORTED;
+  alignas(64) HaloArgs G;
+  memset(&G, 0, sizeof(G));
+  G.npairs = npairs;
+  G.Wp = W + 2; G.HpWp = (H + 2) * (W + 2);
+  G.H = H; G.W = W; G.N = N;
+  G.band_rows = BM + 2 * G.Wp + 2;
+  G.flip = flip;
+  G.total_rows = (int64_t)N * G.HpWp;
+  G.ntiles = (int)((G.total_rows + BM - 1) / BM);
+  G.out = out; G.beta = beta; G.bias = bias;
+  static const int bo_env = getenv("BB200_HALO_BO") ? atoi(getenv("BB200_HALO_BO")) : 1;
+  G.bo_mode = bo_env;
+  int rc;
+  for (int p = 0; p < npairs; ++p) {
+    if ((rc = bb_tma_map_2d(&G.a[p], act_padded[p], G.total_rows, 64, 64, G.band_rows))) return rc;
+    if ((rc = bb_tma_map_2d(&G.b[p], wmat[p], 64, 9 * 64, 9 * 64, 64))) return rc;
+  }
+  const size_t smem = 2 * 9 * W_TILE + NBAND * BAND_BYTES + 256 + 1024;
+  static BbOncePerDevice configured;
+  if (configured.need())
+    BB_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = G.ntiles < BB_SM_COUNT ? G.ntiles : BB_SM_COUNT;
+  conv_halo_kernel<<<grid, NTHREADS, smem, s>>>(G);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+// C-ABI hook for the unit test (tests/test_conv_halo_gpu.py)
+extern "C" int bb_conv_halo_bf16(int N, int H, int W, int npairs, const void* act0, const void* act1, const void* w0,
+                                 const void* w1, int flip, float* out, int beta, const float* bias, void* stream) {
+  const void* acts[2] = {act0, act1};
+  const void* ws[2] = {w0, w1};
+  return bb_conv_halo_run(N, H, W, npairs, acts, ws, flip, out, beta, bias, (cudaStream_t)stream);
+}

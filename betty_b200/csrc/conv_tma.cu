@@ -168,7 +168,8 @@ struct Geo {
 
 // forward-form launch: D[pixel of a GH x GW grid][n] = sum_(tap, ch) SRC[pixel + disp(tap)][ch] * WM[n][tap][ch]
 int launch_corr(const Geo& g, int npairs, const void* const* src_nhwc, int SH, int SW, int SCp, const void* const* wmat,
-                int ncols, int GH, int GW, int flip, float* out, int beta, const float* bias, cudaStream_t s) {
+                int ncols, int GH, int GW, int flip, float* out, int beta, const float* bias, cudaStream_t s,
+                bool padded = false) {
   alignas(64) TmaGemmArgs G;
   memset(&G, 0, sizeof(G));
   const int taps = g.KH * g.KW;
@@ -176,7 +177,8 @@ int launch_corr(const Geo& g, int npairs, const void* const* src_nhwc, int SH, i
   const int bn = ncols <= 64 ? 64 : 128;
   const int64_t Kdim = (int64_t)taps * SCp;
   for (int p = 0; p < npairs; ++p) {
-    int rc = bb_tma_map_nhwc(&G.a[p], src_nhwc[p], g.N, SH, SW, SCp, GW, Hb);
+    int rc = padded ? bb_tma_map_nhwc_padded(&G.a[p], src_nhwc[p], g.N, SH, SW, GW, Hb)
+                    : bb_tma_map_nhwc(&G.a[p], src_nhwc[p], g.N, SH, SW, SCp, GW, Hb);
     if (rc) return rc;
     rc = bb_tma_map_2d(&G.b[p], wmat[p], ncols, Kdim, Kdim, bn);
     if (rc) return rc;
@@ -192,15 +194,21 @@ int launch_corr(const Geo& g, int npairs, const void* const* src_nhwc, int SH, i
 }
 
 // weight-gradient launch over caller-provided bf16 NHWC operands (accumulates into `out`)
-int launch_wgrad(const Geo& g, int npairs, const void* const* xs, const void* const* gs, float* out, cudaStream_t s) {
+int launch_wgrad(const Geo& g, int npairs, const void* const* xs, const void* const* gs, float* out, cudaStream_t s,
+                 bool padded = false) {
   alignas(64) WgradArgs A;
   memset(&A, 0, sizeof(A));
   const int taps = g.KH * g.KW;
   const int Hb = g.HO < 64 / g.WO ? g.HO : 64 / g.WO;
   int rc;
   for (int p = 0; p < npairs; ++p) {
-    if ((rc = bb_tma_map_nhwc(&A.x[p], xs[p], g.N, g.H, g.W, 64, g.WO, Hb))) return rc;
-    if ((rc = bb_tma_map_nhwc(&A.g[p], gs[p], g.N, g.HO, g.WO, 64, g.WO, Hb))) return rc;
+    if (padded) {
+      if ((rc = bb_tma_map_nhwc_padded(&A.x[p], xs[p], g.N, g.H, g.W, g.WO, Hb))) return rc;
+      if ((rc = bb_tma_map_nhwc_padded(&A.g[p], gs[p], g.N, g.HO, g.WO, g.WO, Hb))) return rc;
+    } else {
+      if ((rc = bb_tma_map_nhwc(&A.x[p], xs[p], g.N, g.H, g.W, 64, g.WO, Hb))) return rc;
+      if ((rc = bb_tma_map_nhwc(&A.g[p], gs[p], g.N, g.HO, g.WO, 64, g.WO, Hb))) return rc;
+    }
   }
   A.npairs = npairs; A.taps = taps; A.KW = g.KW; A.ph = g.ph; A.pw = g.pw;
   A.Hb = Hb; A.rows = g.WO * Hb; A.RK = round_up(A.rows, 16);
@@ -435,14 +443,15 @@ int bb_conv_tma_run(const bb_node& nd, int pass, cudaStream_t s) {
 }
 
 int bb_conv_tma_corr(const BbConvGeo& c, int npairs, const void* const* src_nhwc, int SH, int SW, const void* const* wmat,
-                     int ncols, int GH, int GW, int flip, float* out, int beta, const float* bias, cudaStream_t s) {
+                     int ncols, int GH, int GW, int flip, float* out, int beta, const float* bias, cudaStream_t s,
+                     bool padded) {
   Geo g{c.N, c.C, c.H, c.W, c.O, c.KH, c.KW, c.HO, c.WO, c.ph, c.pw};
-  return launch_corr(g, npairs, src_nhwc, SH, SW, 64, wmat, ncols, GH, GW, flip, out, beta, bias, s);
+  return launch_corr(g, npairs, src_nhwc, SH, SW, 64, wmat, ncols, GH, GW, flip, out, beta, bias, s, padded);
 }
 
 int bb_conv_tma_wgrad(const BbConvGeo& c, int npairs, const void* const* x_nhwc, const void* const* gy_nhwc, float* out,
-                      cudaStream_t s) {
+                      cudaStream_t s, bool padded) {
   Geo g{c.N, c.C, c.H, c.W, c.O, c.KH, c.KW, c.HO, c.WO, c.ph, c.pw};
-  const int rc = launch_wgrad(g, npairs, x_nhwc, gy_nhwc, out, s);
+  const int rc = launch_wgrad(g, npairs, x_nhwc, gy_nhwc, out, s, padded);
   return rc == BB_DECLINED ? BB_ERR_UNSUPPORTED : rc;
 }

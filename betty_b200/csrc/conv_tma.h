@@ -23,8 +23,9 @@ struct BbConvGeo {
 //   sum_pairs sum_(tap, ch) src[pair][pixel + disp(tap)][ch] * wmat[pair][n][tap][ch]   (+ bias[n]);
 // src: bf16 NHWC [N][SH][SW][64]; wmat: bf16 [ncols][taps][64] (bb_pack_convw); flip = 1: input-gradient form
 int bb_conv_tma_corr(const BbConvGeo& g, int npairs, const void* const* src_nhwc, int SH, int SW, const void* const* wmat,
-                     int ncols, int GH, int GW, int flip, float* out, int beta, const float* bias, cudaStream_t s);
+                     int ncols, int GH, int GW, int flip, float* out, int beta, const float* bias, cudaStream_t s,
+                     bool padded = false);   // padded: the operands are [N][SH+2][SW+2][64] with a zero border
 // weight gradient: out[o][c][tap] += sum_pairs sum_pixels gy[pair][pixel][o] * x[pair][pixel + disp(tap)][c]
 // x: bf16 NHWC [N][H][W][64], gy: bf16 NHWC [N][HO][WO][64]; out accumulates (fp32 atomics)
 int bb_conv_tma_wgrad(const BbConvGeo& g, int npairs, const void* const* x_nhwc, const void* const* gy_nhwc, float* out,
-                      cudaStream_t s);
+                      cudaStream_t s, bool padded = false);

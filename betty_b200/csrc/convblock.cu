@@ -431,8 +431,8 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
         const float ty = patch_dot<C>(xs, base, plane, g.xpitch, tw);
         dxhp[tbase + (int64_t)wl * g.O] = fmaf(rstd, ty, fmaf(e_x, xh_c, e_0));
         const float tq = (code_c & 4) ? fmaf(c_y, ty, fmaf(c_x, xh_c, c_0)) : 0.f;
-        if (A.tq_nhwc)
-          A.tq_nhwc[tbase + (int64_t)wl * g.O] = __float2bfloat16(tq);
+        if (A.tq_nhwc)   // padded NHWC [N][HP+2][WP+2][64] (O == 64): the next fused block's TMA operand
+          A.tq_nhwc[((((int64_t)n * (g.HP + 2) + hp0 + wr + 1) * (g.WP + 2)) + wc + 1) * 64 + o] = __float2bfloat16(tq);
         else
           outs[o * g.wpitch + wl] = tq;
         wc += wgs;
@@ -694,7 +694,7 @@ int bb_launch_convblock(const bb_node& nd, int pass, cudaStream_t s) {
   A.t_b = reinterpret_cast<const float*>(nd.t[1]); A.at_b = reinterpret_cast<float*>(nd.at[1]);
   A.t_gamma = reinterpret_cast<const float*>(nd.t[2]); A.at_gamma = reinterpret_cast<float*>(nd.at[2]);
   A.t_beta = reinterpret_cast<const float*>(nd.aux[1]); A.at_beta = reinterpret_cast<float*>(nd.aux[2]);
-  // kind bit 2: the pooled tangent is the next fused block's bf16 NHWC operand ([N][HP][WP][64], O == 64)
+  // kind bit 2: the pooled tangent is the next fused block's bf16 padded-NHWC operand ([N][HP+2][WP+2][64], O == 64)
   const bool tq_nhwc = (nd.kind & 4) && A.g.O == 64;
   A.t_q = tq_nhwc ? nullptr : reinterpret_cast<float*>(nd.t[3]);
   A.tq_nhwc = tq_nhwc ? reinterpret_cast<__nv_bfloat16*>(nd.t[3]) : nullptr;

@@ -26,6 +26,7 @@
 
 #include "../../include/betty_b200.h"
 #include "bb_common.cuh"
+#include "conv_halo.h"
 #include "conv_tma.h"
 #include "gemm_tma.h"
 #include "plan.h"
@@ -51,10 +52,10 @@ struct Ws2 {
   float* aqm;          // pooled: mask * a_q
   float* tys;          // pooled: t_y at the arg-max pixel (per iteration)
   float* ty;           // [N*O*HO*WO] fp32 NCHW: conv tangent (per iteration)
-  __nv_bfloat16* aty;  // [N*HO*WO*64] bf16 NHWC: adjoint tangent at the conv output (per iteration)
-  __nv_bfloat16* ay;   // [N*HO*WO*64] bf16 NHWC: base adjoint at the conv output (per call)
-  __nv_bfloat16* xin;  // [N*H*W*64]   bf16 NHWC: base input (per call)
-  __nv_bfloat16* tin;  // [N*H*W*64]   bf16 NHWC: packed input tangent when the producer wrote fp32 NCHW
+  __nv_bfloat16* aty;  // [N][HO+2][WO+2][64] bf16: adjoint tangent at the conv output (per iteration)
+  __nv_bfloat16* ay;   // [N][HO+2][WO+2][64] bf16: base adjoint at the conv output (per call)
+  __nv_bfloat16* xin;  // [N][H+2][W+2][64]   bf16: base input (per call)
+  __nv_bfloat16* tin;  // [N][H+2][W+2][64]   bf16: packed input tangent when the producer wrote fp32 NCHW
   __nv_bfloat16* wf;   // [64*taps*64] forward operand of W        (per call)
   __nv_bfloat16* wd;   // [64*taps*64] input-gradient operand of W (per call)
   __nv_bfloat16* twf;  // same for t_W (per iteration)
@@ -69,8 +70,10 @@ Ws2 layout(void* base, const G2& g) {
   size_t at = 0;
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
   auto take = [&](size_t bytes) { size_t o = at; at = up(at + bytes); return b ? b + o : nullptr; };
+  // TMA operands live in the PADDED NHWC layout [N][H+2][W+2][64] (zero border, never written): a tap displacement is
+  // a constant row offset there, which is what the halo-resident convolution (conv_halo.cu) needs
   const size_t O = g.O, pooled = (size_t)g.N * g.O * g.HP * g.WP, full = (size_t)g.N * g.HO * g.WO,
-               fin = (size_t)g.N * g.H * g.W;
+               fullp = (size_t)g.N * (g.HO + 2) * (g.WO + 2), finp = (size_t)g.N * (g.H + 2) * (g.W + 2);
   w.dsum = reinterpret_cast<double*>(take(8 * 10 * O));
   w.mean = reinterpret_cast<float*>(take(4 * O));
   w.rstd = reinterpret_cast<float*>(take(4 * O));
@@ -81,10 +84,10 @@ Ws2 layout(void* base, const G2& g) {
   w.aqm = reinterpret_cast<float*>(take(4 * pooled));
   w.tys = reinterpret_cast<float*>(take(4 * pooled));
   w.ty = reinterpret_cast<float*>(take(4 * full * O));
-  w.aty = reinterpret_cast<__nv_bfloat16*>(take(2 * full * 64));
-  w.ay = reinterpret_cast<__nv_bfloat16*>(take(2 * full * 64));
-  w.xin = reinterpret_cast<__nv_bfloat16*>(take(2 * fin * 64));
-  w.tin = reinterpret_cast<__nv_bfloat16*>(take(2 * fin * 64));
+  w.aty = reinterpret_cast<__nv_bfloat16*>(take(2 * fullp * 64));
+  w.ay = reinterpret_cast<__nv_bfloat16*>(take(2 * fullp * 64));
+  w.xin = reinterpret_cast<__nv_bfloat16*>(take(2 * finp * 64));
+  w.tin = reinterpret_cast<__nv_bfloat16*>(take(2 * finp * 64));
   const size_t wb = (size_t)2 * 64 * 9 * 64;
   w.wf = reinterpret_cast<__nv_bfloat16*>(take(wb));
   w.wd = reinterpret_cast<__nv_bfloat16*>(take(wb));
@@ -105,7 +108,7 @@ struct A2 {
   const float *t_b, *t_gamma, *t_beta;
   float *at_b, *at_gamma, *at_beta;
   float* tq;                 // fp32 NCHW pooled tangent (standard plan buffer), or
-  __nv_bfloat16* tq_nhwc;    // bf16 NHWC [N][HP][WP][64] when the consumer is a fused block
+  __nv_bfloat16* tq_nhwc;    // bf16 padded NHWC [N][HP+2][WP+2][64] when the consumer is a fused block
   const float* a_q;
   const float* at_q;
   int base;                  // dense kernel: 1 = base adjoint a_y (per call), 0 = adjoint tangent at_y
@@ -185,14 +188,31 @@ __global__ void __launch_bounds__(256) cb2_stats_kernel(const A2 A) {
   const int o = blockIdx.x, PW = g.HP * g.WP, HW = g.HO * g.WO;
   const float mean = A.w.mean[o], rstd = A.w.rstd[o];
   float s0 = 0.f, s1 = 0.f;
+  const bool vec = (HW & 3) == 0 && A.dty == BB_BF16;
   for (int n = blockIdx.y; n < g.N; n += gridDim.y) {
     const int64_t pbase = ((int64_t)n * g.O + o) * PW, ybase = ((int64_t)n * g.O + o) * HW;
     const float* ty = A.w.ty + ybase;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      const float t = ty[i];
-      const float xh = (bb::ldf(A.y, ybase + i, A.dty) - mean) * rstd;
-      s0 += t;
-      s1 = fmaf(xh, t, s1);
+    if (vec) {
+      // plane offsets are multiples of 4 elements: 128-bit t_y loads, 64-bit loads of the bf16 base activation
+      const uint2* yb = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(A.y) + ybase);
+      for (int i = threadIdx.x; i < (HW >> 2); i += blockDim.x) {
+        const float4 t = bb::ld4(ty + 4 * i);
+        const uint2 r = yb[i];
+        const float y0 = __uint_as_float(r.x << 16), y1 = __uint_as_float(r.x & 0xffff0000u);
+        const float y2 = __uint_as_float(r.y << 16), y3 = __uint_as_float(r.y & 0xffff0000u);
+        s0 += (t.x + t.y) + (t.z + t.w);
+        s1 = fmaf((y0 - mean) * rstd, t.x, s1);
+        s1 = fmaf((y1 - mean) * rstd, t.y, s1);
+        s1 = fmaf((y2 - mean) * rstd, t.z, s1);
+        s1 = fmaf((y3 - mean) * rstd, t.w, s1);
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        const float t = ty[i];
+        const float xh = (bb::ldf(A.y, ybase + i, A.dty) - mean) * rstd;
+        s0 += t;
+        s1 = fmaf(xh, t, s1);
+      }
     }
     for (int i = threadIdx.x; i < PW; i += blockDim.x) {
       const int hp = i / g.WP, wp = i - hp * g.WP;
@@ -208,40 +228,57 @@ __global__ void __launch_bounds__(256) cb2_stats_kernel(const A2 A) {
   }
 }
 
-// pooled finalize: dxhat*, t_q (fp32 NCHW or bf16 NHWC).  grid (N, HP): one pooled row of every channel per block
+// pooled finalize: dxhat*, t_q (fp32 NCHW, or bf16 padded NHWC).  grid (N, HP): one pooled row of every channel per
+// block; per-channel constants once per block, warp per channel, lanes along the row
 __global__ void __launch_bounds__(256) cb2_final_kernel(const A2 A) {
-  extern __shared__ float sm[];                 // [WP][O + 1] transposed tile for the NHWC store
+  extern __shared__ float sm[];                 // [O][8] constants | [WP][O + 1] transposed tile for the NHWC store
   const G2& g = A.g;
   const int n = blockIdx.x, hp = blockIdx.y;
-  const double P = (double)g.N * g.HO * g.WO;
-  const int tot = g.O * g.WP;
-  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
-    const int o = i / g.WP, wp = i - o * g.WP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* cst = sm;
+  float* tile = sm + 8 * g.O;
+  if ((int)threadIdx.x < g.O) {
+    const int o = threadIdx.x;
+    const double P = (double)g.N * g.HO * g.WO;
     const double mt = A.w.dsum[2 * g.O + o] / P;
     const float mean_t = (float)mt;
     const float sdot = (float)((A.w.dsum[3 * g.O + o] - mt * A.w.dsum[9 * g.O + o]) / P);
     const float rstd = A.w.rstd[o];
     const float gam = A.gamma ? A.gamma[o] : 1.f, tgam = A.t_gamma ? A.t_gamma[o] : 0.f, tbet = A.t_beta ? A.t_beta[o] : 0.f;
-    const int64_t pi = (((int64_t)n * g.O + o) * g.HP + hp) * g.WP + wp;
-    const float xh = A.w.xh[pi];
-    const float dxh = (A.w.tys[pi] - mean_t - xh * sdot) * rstd;
-    A.w.dxh[pi] = dxh;
-    const float tq = (A.w.sel[pi] & 4) ? fmaf(gam, dxh, fmaf(tgam, xh, tbet)) : 0.f;
-    if (A.tq_nhwc)
-      sm[wp * (g.O + 1) + o] = tq;
-    else
-      A.tq[pi] = tq;
-    if (n == 0 && hp == 0 && wp == 0) {
+    cst[o * 8 + 0] = rstd;                       // dxhat = rstd * (t_y* - mean_t - xhat* sdot)
+    cst[o * 8 + 1] = mean_t;
+    cst[o * 8 + 2] = sdot;
+    cst[o * 8 + 3] = gam;
+    cst[o * 8 + 4] = tgam;
+    cst[o * 8 + 5] = tbet;
+    if (n == 0 && hp == 0) {
       A.w.coef[5 * g.O + o] = mean_t;
       A.w.coef[6 * g.O + o] = sdot;
     }
   }
+  __syncthreads();
+  for (int o = warp; o < g.O; o += 8) {
+    const float rstd = cst[o * 8], mean_t = cst[o * 8 + 1], sdot = cst[o * 8 + 2], gam = cst[o * 8 + 3],
+                tgam = cst[o * 8 + 4], tbet = cst[o * 8 + 5];
+    const int64_t row = (((int64_t)n * g.O + o) * g.HP + hp) * g.WP;
+    for (int wp = lane; wp < g.WP; wp += 32) {
+      const float xh = A.w.xh[row + wp];
+      const float dxh = (A.w.tys[row + wp] - mean_t - xh * sdot) * rstd;
+      A.w.dxh[row + wp] = dxh;
+      const float tq = (A.w.sel[row + wp] & 4) ? fmaf(gam, dxh, fmaf(tgam, xh, tbet)) : 0.f;
+      if (A.tq_nhwc)
+        tile[wp * (g.O + 1) + o] = tq;
+      else
+        A.tq[row + wp] = tq;
+    }
+  }
   if (A.tq_nhwc) {
     __syncthreads();
-    __nv_bfloat16* dst = A.tq_nhwc + (((int64_t)n * g.HP + hp) * g.WP) * 64;
-    for (int i = threadIdx.x; i < g.WP * 64; i += blockDim.x) {
-      const int wp = i >> 6, o = i & 63;
-      dst[i] = __float2bfloat16(o < g.O ? sm[wp * (g.O + 1) + o] : 0.f);
+    __nv_bfloat16* dst = A.tq_nhwc + ((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + 1) * 64;
+    for (int i = threadIdx.x; i < g.WP * 32; i += blockDim.x) {        // two channels per thread
+      const int wp = i >> 5, o = (i & 31) * 2;
+      const float v0 = o < g.O ? tile[wp * (g.O + 1) + o] : 0.f, v1 = o + 1 < g.O ? tile[wp * (g.O + 1) + o + 1] : 0.f;
+      reinterpret_cast<__nv_bfloat162*>(dst)[i] = __floats2bfloat162_rn(v0, v1);
     }
   }
 }
@@ -307,39 +344,77 @@ __global__ void cb2_coef_kernel(const A2 A) {
   if (A.at_b) A.at_b[o] += (float)((double)cw * S_at + (double)cd * Sa + (double)d0 * P + (double)d1 * sx + (double)d2 * P * mean_t);
 }
 
-// dense rule on the conv-output grid, written as the bf16 NHWC TMA operand.  grid (N, HO): one output row of every
-// channel per block; reads are NCHW rows (coalesced along x), the store is the transposed tile.
+// dense rule on the conv-output grid, written as the bf16 padded-NHWC TMA operand.  grid (N, ceil(HO/2)): the two
+// output rows of one pooled row, every channel, per block; warp per channel (its coefficients are warp-uniform),
+// lanes along the two rows (NCHW reads coalesced along x), the store is the transposed tile.
 __global__ void __launch_bounds__(256) cb2_dense_kernel(const A2 A) {
-  extern __shared__ float sm[];                 // [WO][O + 1]
+  extern __shared__ float sm[];                 // [2][WO][O + 1]
   const G2& g = A.g;
-  const int n = blockIdx.x, hy = blockIdx.y;
-  const int hp = hy >> 1, dy = hy & 1;
-  const bool in_pool = hp < g.HP;
+  const int n = blockIdx.x, hpb = blockIdx.y;
+  const int hy0 = 2 * hpb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* c = A.w.coef;
-  const int tot = g.O * g.WO;
-  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
-    const int o = i / g.WO, x = i - o * g.WO;
-    const int64_t yi = (((int64_t)n * g.O + o) * g.HO + hy) * g.WO + x;
-    const float xh = (bb::ldf(A.y, yi, A.dty) - A.w.mean[o]) * A.w.rstd[o];
-    float v = c[0 * g.O + o] + xh * c[1 * g.O + o];
-    if (!A.base) v = fmaf(A.w.ty[yi], c[2 * g.O + o], v);
-    const int wp = x >> 1;
-    if (in_pool && wp < g.WP) {
-      const int64_t pi = (((int64_t)n * g.O + o) * g.HP + hp) * g.WP + wp;
-      const unsigned code = A.w.sel[pi];
-      if ((int)((code >> 1) & 1) == dy && (int)(code & 1) == (x & 1)) {
-        v = fmaf(c[4 * g.O + o], A.w.aqm[pi], v);
-        if (!A.base && (code & 4)) v = fmaf(c[3 * g.O + o], A.at_q[pi], v);
+  const bool in_pool = hpb < g.HP;
+  const int rows = (hy0 + 1 < g.HO) ? 2 : 1;
+  for (int o = warp; o < g.O; o += 8) {
+    const float c0 = c[0 * g.O + o], c1 = c[1 * g.O + o], c2 = c[2 * g.O + o], c3 = c[3 * g.O + o], c4 = c[4 * g.O + o];
+    const float mean = A.w.mean[o], rstd = A.w.rstd[o];
+    const int64_t ybase = (((int64_t)n * g.O + o) * g.HO + hy0) * g.WO;
+    const int64_t pbase = (((int64_t)n * g.O + o) * g.HP + hpb) * g.WP;
+    for (int e = lane; e < rows * g.WO; e += 32) {
+      const int dy = e >= g.WO ? 1 : 0, x = e - dy * g.WO;
+      const float xh = (bb::ldf(A.y, ybase + e, A.dty) - mean) * rstd;
+      float v = fmaf(xh, c1, c0);
+      if (!A.base) v = fmaf(A.w.ty[ybase + e], c2, v);
+      const int wp = x >> 1;
+      if (in_pool && wp < g.WP) {
+        const unsigned code = A.w.sel[pbase + wp];
+        if ((int)((code >> 1) & 1) == dy && (int)(code & 1) == (x & 1)) {
+          v = fmaf(c4, A.w.aqm[pbase + wp], v);
+          if (!A.base && (code & 4)) v = fmaf(c3, A.at_q[pbase + wp], v);
+        }
       }
+      sm[e * (g.O + 1) + o] = v;
     }
-    sm[x * (g.O + 1) + o] = v;
   }
   __syncthreads();
-  __nv_bfloat16* dst = (A.base ? A.w.ay : A.w.aty) + (((int64_t)n * g.HO + hy) * g.WO) * 64;
-  for (int i = threadIdx.x; i < g.WO * 64; i += blockDim.x) {
-    const int x = i >> 6, o = i & 63;
-    dst[i] = __float2bfloat16(o < g.O ? sm[x * (g.O + 1) + o] : 0.f);
+  __nv_bfloat16* base = A.base ? A.w.ay : A.w.aty;
+  for (int dy = 0; dy < rows; ++dy) {
+    __nv_bfloat16* dst = base + ((((int64_t)n * (g.HO + 2) + hy0 + dy + 1) * (g.WO + 2)) + 1) * 64;
+    const float* src = sm + dy * g.WO * (g.O + 1);
+    for (int i = threadIdx.x; i < g.WO * 32; i += blockDim.x) {
+      const int x = i >> 5, o = (i & 31) * 2;
+      const float v0 = o < g.O ? src[x * (g.O + 1) + o] : 0.f, v1 = o + 1 < g.O ? src[x * (g.O + 1) + o + 1] : 0.f;
+      reinterpret_cast<__nv_bfloat162*>(dst)[i] = __floats2bfloat162_rn(v0, v1);
+    }
   }
+}
+
+// NCHW (any base dtype) -> bf16 padded NHWC [N][H+2][W+2][64].  grid (N, H)
+__global__ void __launch_bounds__(256) cb2_pack_padded_kernel(const void* src, int dt, int C, int H, int W,
+                                                              __nv_bfloat16* dst) {
+  extern __shared__ float sm[];                 // [W][C + 1]
+  const int n = blockIdx.x, y = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < C; c += 8) {
+    const int64_t row = (((int64_t)n * C + c) * H + y) * W;
+    for (int x = lane; x < W; x += 32) sm[x * (C + 1) + c] = bb::ldf(src, row + x, dt);
+  }
+  __syncthreads();
+  __nv_bfloat16* d = dst + ((((int64_t)n * (H + 2) + y + 1) * (W + 2)) + 1) * 64;
+  for (int i = threadIdx.x; i < W * 32; i += blockDim.x) {
+    const int x = i >> 5, c = (i & 31) * 2;
+    const float v0 = c < C ? sm[x * (C + 1) + c] : 0.f, v1 = c + 1 < C ? sm[x * (C + 1) + c + 1] : 0.f;
+    reinterpret_cast<__nv_bfloat162*>(d)[i] = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
+// forward-form product over padded operands: the halo-resident kernel where it applies, else the per-tap TMA kernel
+int corr(const G2& g, const BbConvGeo& cg, int npairs, const void* const* src, int SH, int SW, const void* const* wm, int ncols,
+         int flip, float* out, int beta, const float* bias, cudaStream_t s) {
+  if (g.C == 64 && g.O == 64 && bb_conv_halo_ok(64, 64, SH, SW))
+    return bb_conv_halo_run(g.N, SH, SW, npairs, src, wm, flip, out, beta, bias, s);
+  return bb_conv_tma_corr(cg, npairs, src, SH, SW, wm, ncols, SH, SW, flip, out, beta, bias, s, true);
 }
 
 }  // namespace
@@ -377,7 +452,8 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
   BbConvGeo cg{g.N, g.C, g.H, g.W, g.O, 3, 3, g.HO, g.WO, g.ph, g.pw};
   const int chunks = g.N < 8 ? g.N : (g.N < 64 ? 8 : 32);
   const dim3 per_channel(g.O, chunks);
-  const size_t tile_q = 4 * (size_t)g.WP * (g.O + 1), tile_y = 4 * (size_t)g.WO * (g.O + 1);
+  const size_t tile_q = 4 * ((size_t)g.WP * (g.O + 1) + 8 * g.O), tile_y = 4 * (size_t)2 * g.WO * (g.O + 1);
+  const dim3 dense_grid(g.N, (g.HO + 1) / 2);
   int rc;
   if (pass == BB_PASS_BASE_BWD) {
     BB_CUDA_TRY(cudaMemsetAsync(A.w.dsum, 0, sizeof(double) * 10 * g.O, s));
@@ -386,19 +462,19 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
     cb2_prep_kernel<<<per_channel, 256, 0, s>>>(A);
     A.base = 1;
     cb2_coef_kernel<<<1, 64, 0, s>>>(A);
-    cb2_dense_kernel<<<dim3(g.N, g.HO), 256, tile_y, s>>>(A);
+    cb2_dense_kernel<<<dense_grid, 256, tile_y, s>>>(A);
     bb_launch_tally += 6;
     BB_LAUNCH_CHECK();
     // per-call operand packs: x_in (NHWC bf16), W in its forward and input-gradient layouts
-    if ((rc = bb_pack_nhwc(nd.base[0], nd.dt[0], g.N, g.C, g.H * g.W, A.w.xin, 64, s))) return rc;
+    cb2_pack_padded_kernel<<<dim3(g.N, g.H), 256, 4 * (size_t)g.W * (g.C + 1), s>>>(nd.base[0], nd.dt[0], g.C, g.H, g.W, A.w.xin);
+    bb_launch_tally += 1;
     if ((rc = bb_pack_convw(nd.base[1], nd.dt[1], g.O, g.C, taps, 0, A.w.wf, 64, s))) return rc;
     if ((rc = bb_pack_convw(nd.base[1], nd.dt[1], g.O, g.C, taps, 1, A.w.wd, 64, s))) return rc;
     if (nd.pad0 & 1) {
       // a_in (beta) = dgrad(a_y, W): the previous block's base adjoint
       const void* src[1] = {A.w.ay};
       const void* wm[1] = {A.w.wd};
-      if ((rc = bb_conv_tma_corr(cg, 1, src, g.HO, g.WO, wm, g.C, g.H, g.W, 1, reinterpret_cast<float*>(nd.a[0]), nd.beta[0],
-                                 nullptr, s)))
+      if ((rc = corr(g, cg, 1, src, g.HO, g.WO, wm, g.C, 1, reinterpret_cast<float*>(nd.a[0]), nd.beta[0], nullptr, s)))
         return rc;
     }
     return BB_OK;
@@ -406,13 +482,14 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
   if (pass == BB_PASS_TAN_FWD) {
     const void* tin = nd.t[0];
     if (!tin_nhwc) {
-      if ((rc = bb_pack_nhwc(nd.t[0], BB_F32, g.N, g.C, g.H * g.W, A.w.tin, 64, s))) return rc;
+      cb2_pack_padded_kernel<<<dim3(g.N, g.H), 256, 4 * (size_t)g.W * (g.C + 1), s>>>(nd.t[0], BB_F32, g.C, g.H, g.W, A.w.tin);
+      bb_launch_tally += 1;
       tin = A.w.tin;
     }
     if ((rc = bb_pack_convw(nd.t[1], BB_F32, g.O, g.C, taps, 0, A.w.twf, 64, s))) return rc;
     const void* src[2] = {tin, A.w.xin};
     const void* wm[2] = {A.w.wf, A.w.twf};
-    if ((rc = bb_conv_tma_corr(cg, 2, src, g.H, g.W, wm, g.O, g.HO, g.WO, 0, A.w.ty, 0, A.t_b, s))) return rc;
+    if ((rc = corr(g, cg, 2, src, g.H, g.W, wm, g.O, 0, A.w.ty, 0, A.t_b, s))) return rc;
     BB_CUDA_TRY(cudaMemsetAsync(A.w.dsum + 2 * g.O, 0, sizeof(double) * 2 * g.O, s));     // this pass's sums
     cb2_stats_kernel<<<per_channel, 256, 0, s>>>(A);
     cb2_final_kernel<<<dim3(g.N, g.HP), 256, tile_q, s>>>(A);
@@ -425,21 +502,20 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
   BB_CUDA_TRY(cudaMemsetAsync(A.w.dsum + 4 * g.O, 0, sizeof(double) * 3 * g.O, s));
   cb2_reduce_kernel<<<per_channel, 256, 0, s>>>(A);
   cb2_coef_kernel<<<1, 64, 0, s>>>(A);
-  cb2_dense_kernel<<<dim3(g.N, g.HO), 256, tile_y, s>>>(A);
+  cb2_dense_kernel<<<dense_grid, 256, tile_y, s>>>(A);
   bb_launch_tally += 4;
   BB_LAUNCH_CHECK();
   if ((rc = bb_pack_convw(nd.t[1], BB_F32, g.O, g.C, taps, 1, A.w.twd, 64, s))) return rc;
   {
     const void* src[2] = {A.w.aty, A.w.ay};
     const void* wm[2] = {A.w.wd, A.w.twd};
-    if ((rc = bb_conv_tma_corr(cg, 2, src, g.HO, g.WO, wm, g.C, g.H, g.W, 1, reinterpret_cast<float*>(nd.at[0]), nd.beta[0],
-                               nullptr, s)))
+    if ((rc = corr(g, cg, 2, src, g.HO, g.WO, wm, g.C, 1, reinterpret_cast<float*>(nd.at[0]), nd.beta[0], nullptr, s)))
       return rc;
   }
   const void* tin = tin_nhwc ? nd.t[0] : (const void*)A.w.tin;     // packed by this iteration's tangent-forward pass
   const void* xs[2] = {A.w.xin, tin};
   const void* gs[2] = {A.w.aty, A.w.ay};
-  return bb_conv_tma_wgrad(cg, 2, xs, gs, reinterpret_cast<float*>(nd.at[1]), s);
+  return bb_conv_tma_wgrad(cg, 2, xs, gs, reinterpret_cast<float*>(nd.at[1]), s, true);
 }
 
 extern "C" int64_t bb_convblock2_ws_bytes(int N, int C, int H, int W, int O, int HO, int WO, int HP, int WP) {

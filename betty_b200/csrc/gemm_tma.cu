@@ -791,6 +791,15 @@ int bb_tma_map_nhwc(CUtensorMap* out, const void* p, int N, int H, int W, int Cp
   return encode_cached(out, 4, p, dims, strides, box);
 }
 
+int bb_tma_map_nhwc_padded(CUtensorMap* out, const void* p, int N, int H, int W, int bw, int bh) {
+  const cuuint64_t Wp = (cuuint64_t)W + 2, Hp = (cuuint64_t)H + 2;
+  const cuuint64_t dims[4] = {64u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {64u * 2, Wp * 64 * 2, Hp * Wp * 64 * 2};
+  const cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, 1u};
+  const char* interior = reinterpret_cast<const char*>(p) + (Wp + 1) * 64 * 2;
+  return encode_cached(out, 4, interior, dims, strides, box);
+}
+
 int bb_pack2d(const void* src, int dt, int64_t os, int64_t is, int64_t outer, int64_t inner, void* dst, int64_t dp,
               cudaStream_t s) {
   if (outer <= 0 || inner <= 0) return BB_OK;

@@ -44,3 +44,6 @@ int bb_tma_map_3d(CUtensorMap* out, const void* p, int64_t batch, int64_t rows, 
                   int64_t bstride, int box_rows);
 // bf16 NHWC tensor [N][H][W][Cp] (Cp multiple of 64): box = (64 channels, bw, bh, 1), SWIZZLE_128B.
 int bb_tma_map_nhwc(CUtensorMap* out, const void* p, int N, int H, int W, int Cp, int bw, int bh);
+// the same view of a PADDED array [N][H+2][W+2][64] (zero border): `p` = the padded base; coordinates address the
+// interior, out-of-range taps are zero-filled by TMA as before
+int bb_tma_map_nhwc_padded(CUtensorMap* out, const void* p, int N, int H, int W, int bw, int bh);

@@ -99,10 +99,11 @@ class HvpPlan:
             k = "z" if v.zero_init else "nz"
             shape, stride = tuple(v.base.shape), tuple(v.base.stride())
             if v.tfmt == "nhwc_bf16":
-                # tangent written by a fused block directly as the next fused block's TMA operand: bf16 [N][H][W][64]
+                # tangent written by a fused block directly as the next fused block's TMA operand: bf16 padded NHWC
+                # [N][H+2][W+2][64], zero border (never written)
                 Nn, Cc, Hh, Ww = shape
                 assert Cc == 64, shape
-                v.t = torch.zeros((Nn, Hh, Ww, 64), dtype=torch.bfloat16, device=self.dev)
+                v.t = torch.zeros((Nn, Hh + 2, Ww + 2, 64), dtype=torch.bfloat16, device=self.dev)
             else:
                 v.t = torch.as_strided(self.T, shape, stride, ot)
             v.a = torch.as_strided(self.A[k], shape, stride, oa)

@@ -118,6 +118,11 @@ int bb_plan_invalidate_constants(bb_plan* plan);
 int bb_plan_graph_captures(const bb_plan* plan); /* how many times a K-loop iteration was captured (tests) */
 int bb_plan_node_route(bb_plan* plan, int node, int pass); /* tests: 2 = TMA tensor-core convolution path */
 /* bytes of the per-node workspace of a fused data-input convolution block (BB_OP_CONVBLOCK, csrc/convblock.cu) */
+/* ---- K6 building block exposed for unit tests: halo-resident 3x3 convolution (csrc/conv_halo.cu), 64 -> 64 channels,
+ *      activations bf16 in the padded NHWC layout [N][H+2][W+2][64] (zero border), weights bf16 [64][9][64] (n, tap, ch);
+ *      out fp32 NCHW; flip = 1: tap (i, j) reads the pixel at (+1-i, +1-j) (input-gradient form) */
+int bb_conv_halo_bf16(int N, int H, int W, int npairs, const void* act0, const void* act1, const void* w0, const void* w1,
+                      int flip, float* out, int beta, const float* bias, void* stream);
 int64_t bb_convblock_ws_bytes(int N, int C, int H, int W, int O, int HO, int WO, int HP, int WP);
 /* same for a fused inner block of a bf16 graph (BB_OP_CONVBLOCK2, csrc/convblock2.cu) */
 int64_t bb_convblock2_ws_bytes(int N, int C, int H, int W, int O, int HO, int WO, int HP, int WP);
