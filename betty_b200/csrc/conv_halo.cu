@@ -10,8 +10,8 @@
 // NHWC layout  [N][H+2][W+2][64]  (zero border), i.e. one long matrix of 128-byte pixel rows in which a tap
 // displacement (dy, dx) is the constant row offset dy*(W+2) + dx.  A tile is 128 consecutive pixel rows; ONE TMA box of
 // 128 + 2(W+2) + 2 rows is loaded per (tile, pair) and the nine taps are nine UMMA descriptors pointing at different
-// 128-byte row offsets inside that band (SWIZZLE_128B is a function of the shared-memory address bits, the
-// descriptor's base-offset field carries the 1024-byte phase).  The 2 x 9 weight tiles (144 KB) are loaded once per
+// 128-byte row offsets inside that band (SWIZZLE_128B is a function of the shared-memory address bits alone, so a
+// descriptor may start on any 128-byte row of a 1024-byte-aligned band; base-offset field 0, verified on B200).  The 2 x 9 weight tiles (144 KB) are loaded once per
 // CTA and stay resident.  Shared-memory fill per tile: 2 x 28 KB instead of 2 x 9 x 24 KB -> the MMA issue rate, not
 // the fill, bounds the kernel.  Rows that fall on the zero border compute garbage-free zeros' neighbours and are
 // simply not stored.
@@ -236,7 +236,10 @@ int bb_conv_halo_run(int N, int H, int W, int npairs, const void* const* act_pad
   G.total_rows = (int64_t)N * G.HpWp;
   G.ntiles = (int)((G.total_rows + BM - 1) / BM);
   G.out = out; G.beta = beta; G.bias = bias;
-  static const int bo_env = getenv("BB200_HALO_BO") ? atoi(getenv("BB200_HALO_BO")) : 1;
+  // measured on B200 (tests/test_conv_halo_gpu.py, GPU call #52): SWIZZLE_128B is a pure function of the shared-memory
+  // address bits, so a descriptor that starts on any 128-byte row reads the TMA-written band correctly with base offset 0
+  // (setting the field to (start >> 7) & 7 gives wrong products); BB200_HALO_BO=1 keeps the other convention testable
+  static const int bo_env = getenv("BB200_HALO_BO") ? atoi(getenv("BB200_HALO_BO")) : 0;
   G.bo_mode = bo_env;
   int rc;
   for (int p = 0; p < npairs; ++p) {

@@ -33,8 +33,18 @@ constexpr int NT = 256;         // threads per CTA
 constexpr int MAXO = 64;
 constexpr int NSUM = 4;         // per-channel scalar sums carried next to GW
 
+// pooled arrays (xhat*, dxhat*, mask a_q) are fp32 for fp32 graphs and bf16 for reduced-precision graphs (they are
+// streamed once per iteration: 13 -> 7 bytes per pooled element)
+template <typename PT> __device__ __forceinline__ float ldp(const PT* p, int64_t i);
+template <> __device__ __forceinline__ float ldp<float>(const float* p, int64_t i) { return p[i]; }
+template <> __device__ __forceinline__ float ldp<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <typename PT> __device__ __forceinline__ void stp(PT* p, int64_t i, float v);
+template <> __device__ __forceinline__ void stp<float>(float* p, int64_t i, float v) { p[i] = v; }
+template <> __device__ __forceinline__ void stp<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16(v); }
+
 struct CbGeom {
   int N, C, H, W, O, HO, WO, ph, pw, HP, WP, relu;
+  int ps;         // bytes per pooled-array element (4 or 2)
   int R;          // window rows per tile
   int tiles_per_img, ntiles;
   int xrows, xpitch;   // input tile rows / pitch in shared memory
@@ -57,9 +67,9 @@ struct CbWs {
   float* sdot;      // [O]
   float* part;      // [grid][O][KP + NSUM] per-CTA partial sums of the reduce kernels
   unsigned char* sel;   // [N*HP*WP*O] NHWC: code (dy*2+dx) | mask << 2
-  float* xh;        // [N*HP*WP*O] NHWC xhat at the arg-max pixel
-  float* dxh;       // [N*HP*WP*O] NHWC dxhat at the arg-max pixel (per iteration)
-  float* aqm;       // [N*HP*WP*O] NHWC mask * a_q
+  void* xh;         // [N*HP*WP*O] NHWC xhat at the arg-max pixel          (fp32 or bf16, CbGeom::ps)
+  void* dxh;        // [N*HP*WP*O] NHWC dxhat at the arg-max pixel (per iteration)
+  void* aqm;        // [N*HP*WP*O] NHWC mask * a_q
   size_t bytes;
 };
 
@@ -87,9 +97,10 @@ CbWs cb_layout(void* base, const CbGeom& g) {
   w.sdot = reinterpret_cast<float*>(take(4 * O));
   w.part = reinterpret_cast<float*>(take(4 * (size_t)GRID_MAX * O * (KP + NSUM)));
   w.sel = reinterpret_cast<unsigned char*>(take(pooled));
-  w.xh = reinterpret_cast<float*>(take(4 * pooled));
-  w.dxh = reinterpret_cast<float*>(take(4 * pooled));
-  w.aqm = reinterpret_cast<float*>(take(4 * pooled));
+  const size_t ps = g.ps == 2 ? 2 : 4;
+  w.xh = take(ps * pooled);
+  w.dxh = take(ps * pooled);
+  w.aqm = take(ps * pooled);
   w.bytes = at;
   return w;
 }
@@ -119,7 +130,8 @@ CbGeom make_geom(const bb_node& nd) {
   g.N = (int)nd.dims[0]; g.C = (int)nd.dims[1]; g.H = (int)nd.dims[2]; g.W = (int)nd.dims[3]; g.O = (int)nd.dims[4];
   g.HO = (int)nd.dims[7]; g.WO = (int)nd.dims[8]; g.ph = (int)nd.dims[11]; g.pw = (int)nd.dims[12];
   g.HP = (int)nd.dims[13]; g.WP = (int)nd.dims[14]; g.relu = (int)nd.dims[15];
-  int R = 96 / (g.WP > 0 ? g.WP : 1);
+  g.ps = (nd.kind & 1) ? 2 : 4;
+  int R = 48 / (g.WP > 0 ? g.WP : 1);     // ~48 windows x O channels per tile: small tiles, many resident CTAs
   if (R < 1) R = 1;
   if (R > g.HP) R = g.HP;
   g.R = R;
@@ -230,6 +242,7 @@ __device__ __forceinline__ float patch_dot(const float* xs, int base, int plane,
 // ---------------------------------------------------------------------------------------------------------------
 // base-backward preparation: arg-max codes, ReLU mask, xhat at the arg-max pixel, masked base adjoint (NHWC)
 // ---------------------------------------------------------------------------------------------------------------
+template <typename PT>
 __global__ void __launch_bounds__(256) cb_prep_kernel(const CbArgs A) {
   const CbGeom& g = A.g;
   const int64_t total = (int64_t)g.N * g.HP * g.WP * g.O;
@@ -248,8 +261,8 @@ __global__ void __launch_bounds__(256) cb_prep_kernel(const CbArgs A) {
     const float yv = bb::ldf(A.y, ((int64_t)n * g.O + o) * g.HO * g.WO + id, A.dty);
     const int64_t pi = (((int64_t)n * g.HP + hp) * g.WP + wp) * g.O + o;
     A.w.sel[pi] = (unsigned char)((dy & 1) * 2 + (dx & 1) + (m ? 4 : 0));
-    A.w.xh[pi] = (yv - A.w.mean[o]) * A.w.rstd[o];
-    A.w.aqm[pi] = m ? A.a_q[i] : 0.f;
+    stp<PT>(reinterpret_cast<PT*>(A.w.xh), pi, (yv - A.w.mean[o]) * A.w.rstd[o]);
+    stp<PT>(reinterpret_cast<PT*>(A.w.aqm), pi, m ? A.a_q[i] : 0.f);
   }
 }
 
@@ -359,8 +372,8 @@ __global__ void cb_gram_finish_kernel(const CbArgs A) {
 //   indices advance without divisions; the pooled NHWC arrays (code, xhat) of the next window are fetched while the
 //   current one is being computed.
 // ---------------------------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
+template <int C, typename PT>
+__global__ void __launch_bounds__(NT, 4) cb_tf_kernel(const CbArgs A) {
   extern __shared__ float sm[];
   const CbGeom g = A.g;
   constexpr int CKK = C * 9;
@@ -374,8 +387,8 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
   const bool och = o < g.O && wg < wgs;
   const double invP = 1.0 / ((double)g.N * g.HO * g.WO);
   const unsigned char* __restrict__ sel = A.w.sel;
-  const float* __restrict__ xhp = A.w.xh;
-  float* __restrict__ dxhp = A.w.dxh;
+  const PT* __restrict__ xhp = reinterpret_cast<const PT*>(A.w.xh);
+  PT* __restrict__ dxhp = reinterpret_cast<PT*>(A.w.dxh);
   // per-lane channel constants
   float tw[CKK];
   float mean_t = 0.f, sdot = 0.f, rstd = 0.f, gam = 1.f, tgam = 0.f, tbeta = 0.f, tb = 0.f;
@@ -408,14 +421,14 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
   const float c_y = gam * rstd, c_x = tgam - gam * rstd * sdot, c_0 = tbeta + gam * rstd * (tb - mean_t);
   const float e_0 = (tb - mean_t) * rstd, e_x = -sdot * rstd;          // dxhat = rstd*t_y + e_x*xhat + e_0
   const int tcap = g.R * g.WP * g.O;                 // pooled elements of a full tile
-  float* xh_s = outs + g.O * g.wpitch;               // [nw][O] xhat* of the tile
+  PT* xh_s = reinterpret_cast<PT*>(outs + g.O * g.wpitch);               // [nw][O] xhat* of the tile
   unsigned char* sel_s = reinterpret_cast<unsigned char*>(xh_s + tcap);
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int n = tile / g.tiles_per_img, tr = tile - n * g.tiles_per_img;
     const int hp0 = tr * g.R, rows = min(g.R, g.HP - hp0), nw = rows * g.WP;
     const int64_t t0 = ((int64_t)n * g.HP + hp0) * g.WP * g.O;             // NHWC index of (window 0, channel 0)
     __syncthreads();
-    tile_copy_async(xh_s, xhp + t0, nw * g.O * 4);
+    tile_copy_async(xh_s, xhp + t0, nw * g.O * (int)sizeof(PT));
     tile_copy_async(sel_s, sel + t0, nw * g.O);
     load_x_tile<C>(A, n, hp0, xs);
     tile_copy_wait();
@@ -426,10 +439,10 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
       while (wc >= g.WP) { wc -= g.WP; ++wr; }
       for (int wl = wg; wl < nw; wl += wgs) {
         const unsigned code_c = sel_s[wl * g.O + o];
-        const float xh_c = xh_s[wl * g.O + o];
+        const float xh_c = ldp<PT>(xh_s, wl * g.O + o);
         const int base = (2 * wr + ((code_c >> 1) & 1)) * g.xpitch + 2 * wc + (code_c & 1);
         const float ty = patch_dot<C>(xs, base, plane, g.xpitch, tw);
-        dxhp[tbase + (int64_t)wl * g.O] = fmaf(rstd, ty, fmaf(e_x, xh_c, e_0));
+        stp<PT>(dxhp, tbase + (int64_t)wl * g.O, fmaf(rstd, ty, fmaf(e_x, xh_c, e_0)));
         const float tq = (code_c & 4) ? fmaf(c_y, ty, fmaf(c_x, xh_c, c_0)) : 0.f;
         if (A.tq_nhwc)   // padded NHWC [N][HP+2][WP+2][64] (O == 64): the next fused block's TMA operand
           A.tq_nhwc[((((int64_t)n * (g.HP + 2) + hp0 + wr + 1) * (g.WP + 2)) + wc + 1) * 64 + o] = __float2bfloat16(tq);
@@ -459,7 +472,7 @@ __global__ void __launch_bounds__(NT) cb_tf_kernel(const CbArgs A) {
 //   part[cta][o][KP + 1]  = sum_w v * xhat_sel
 //   part[cta][o][KP + 2]  = sum_w mask*a_q * dxhat_sel         (TB only)
 // ---------------------------------------------------------------------------------------------------------------
-template <int C, bool BASE>
+template <int C, bool BASE, typename PT>
 __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
   extern __shared__ float sm[];
   const CbGeom g = A.g;
@@ -473,26 +486,26 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
   const int o = cg * 32 + lane;
   const bool och = o < g.O && wg < wgs;
   const unsigned char* __restrict__ sel = A.w.sel;
-  const float* __restrict__ xhp = A.w.xh;
-  const float* __restrict__ dxhp = A.w.dxh;
-  const float* __restrict__ aqm = A.w.aqm;
+  const PT* __restrict__ xhp = reinterpret_cast<const PT*>(A.w.xh);
+  const PT* __restrict__ dxhp = reinterpret_cast<const PT*>(A.w.dxh);
+  const PT* __restrict__ aqm = reinterpret_cast<const PT*>(A.w.aqm);
   float gw[CKK];
 #pragma unroll
   for (int k = 0; k < CKK; ++k) gw[k] = 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   const int tcap = g.R * g.WP * g.O;
-  float* xh_s = ins + g.O * g.wpitch;
-  float* aq_s = xh_s + tcap;
-  float* dx_s = aq_s + tcap;
+  PT* xh_s = reinterpret_cast<PT*>(ins + g.O * g.wpitch);
+  PT* aq_s = xh_s + tcap;
+  PT* dx_s = aq_s + tcap;
   unsigned char* sel_s = reinterpret_cast<unsigned char*>(dx_s + tcap);
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int n = tile / g.tiles_per_img, tr = tile - n * g.tiles_per_img;
     const int hp0 = tr * g.R, rows = min(g.R, g.HP - hp0), nw = rows * g.WP;
     const int64_t t0 = ((int64_t)n * g.HP + hp0) * g.WP * g.O;
     __syncthreads();
-    tile_copy_async(xh_s, xhp + t0, nw * g.O * 4);
-    tile_copy_async(aq_s, aqm + t0, nw * g.O * 4);
-    if (!BASE) tile_copy_async(dx_s, dxhp + t0, nw * g.O * 4);
+    tile_copy_async(xh_s, xhp + t0, nw * g.O * (int)sizeof(PT));
+    tile_copy_async(aq_s, aqm + t0, nw * g.O * (int)sizeof(PT));
+    if (!BASE) tile_copy_async(dx_s, dxhp + t0, nw * g.O * (int)sizeof(PT));
     tile_copy_async(sel_s, sel + t0, nw * g.O);
     load_x_tile<C>(A, n, hp0, xs);
     if (!BASE) {
@@ -511,13 +524,13 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
       for (int wl = wg; wl < nw; wl += wgs) {
         const int si = wl * g.O + o;
         const unsigned code_c = sel_s[si];
-        const float xh_c = xh_s[si], aq_c = aq_s[si];
+        const float xh_c = ldp<PT>(xh_s, si), aq_c = ldp<PT>(aq_s, si);
         float v;
         if (BASE) {
           v = aq_c;
         } else {
           v = (code_c & 4) ? ins[o * g.wpitch + wl] : 0.f;
-          s2 = fmaf(aq_c, dx_s[si], s2);
+          s2 = fmaf(aq_c, ldp<PT>(dx_s, si), s2);
         }
         s0 += v;
         s1 = fmaf(v, xh_c, s1);
@@ -604,7 +617,7 @@ __global__ void __launch_bounds__(64) cb_finish_kernel(const CbArgs A, int CKK) 
   }
 }
 
-template <int C>
+template <int C, typename PT>
 int run(const CbArgs& A0, int pass, cudaStream_t s) {
   CbArgs A = A0;
   const CbGeom& g = A.g;
@@ -613,14 +626,14 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
   const size_t tile = 4 * ((size_t)C * g.xrows * g.xpitch + (size_t)g.O * g.wpitch);
   const int wgs = (NT / 32) / ((g.O + 31) / 32);
   const size_t smem_part = 4 * (size_t)wgs * g.O * (KP + NSUM);
-  const size_t smem_tf = tile + 5 * tcap + 64;
-  size_t smem_red = tile + 13 * tcap + 64;
+  const size_t smem_tf = tile + (sizeof(PT) + 1) * tcap + 64;
+  size_t smem_red = tile + (3 * sizeof(PT) + 1) * tcap + 64;
   if (smem_red < smem_part) smem_red = smem_part;
   static BbOncePerDevice once;
   if (once.need()) {
-    BB_CUDA_TRY(cudaFuncSetAttribute(cb_tf_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    BB_CUDA_TRY(cudaFuncSetAttribute(cb_reduce_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    BB_CUDA_TRY(cudaFuncSetAttribute(cb_reduce_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BB_CUDA_TRY(cudaFuncSetAttribute(cb_tf_kernel<C, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BB_CUDA_TRY(cudaFuncSetAttribute(cb_reduce_kernel<C, false, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BB_CUDA_TRY(cudaFuncSetAttribute(cb_reduce_kernel<C, true, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_gram_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   if (smem_red > 200 * 1024) return BB_ERR_UNSUPPORTED;
@@ -642,29 +655,29 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     if (chunks < 1) chunks = 1;
     cb_stats_kernel<<<dim3(g.O, chunks), 256, 0, s>>>(A);
     cb_stats_finish_kernel<<<1, 64, 0, s>>>(A);
-    cb_prep_kernel<<<4 * BB_SM_COUNT, 256, 0, s>>>(A);
+    cb_prep_kernel<PT><<<4 * BB_SM_COUNT, 256, 0, s>>>(A);
     const int bands = (g.HO + 2 * g.R - 1) / (2 * g.R);
     int ggrid = g.N * bands < GRID_MAX ? g.N * bands : GRID_MAX;
     cb_gram_kernel<C><<<ggrid, NT, tile, s>>>(A);
     cb_gram_finish_kernel<<<8, 256, 0, s>>>(A);
-    const int grid = resident((const void*)cb_reduce_kernel<C, true>, smem_red);
+    const int grid = resident((const void*)cb_reduce_kernel<C, true, PT>, smem_red);
     A.nparts = grid;
-    cb_reduce_kernel<C, true><<<grid, NT, smem_red, s>>>(A);
+    cb_reduce_kernel<C, true, PT><<<grid, NT, smem_red, s>>>(A);
     cb_finish_kernel<true><<<g.O, 64, 0, s>>>(A, C * 9);
     bb_launch_tally += 9;
     BB_LAUNCH_CHECK();
     return BB_OK;
   }
   if (pass == BB_PASS_TAN_FWD) {
-    const int grid = resident((const void*)cb_tf_kernel<C>, smem_tf);
-    cb_tf_kernel<C><<<grid, NT, smem_tf, s>>>(A);
+    const int grid = resident((const void*)cb_tf_kernel<C, PT>, smem_tf);
+    cb_tf_kernel<C, PT><<<grid, NT, smem_tf, s>>>(A);
     bb_launch_tally += 1;
     BB_LAUNCH_CHECK();
     return BB_OK;
   }
-  const int grid = resident((const void*)cb_reduce_kernel<C, false>, smem_red);
+  const int grid = resident((const void*)cb_reduce_kernel<C, false, PT>, smem_red);
   A.nparts = grid;
-  cb_reduce_kernel<C, false><<<grid, NT, smem_red, s>>>(A);
+  cb_reduce_kernel<C, false, PT><<<grid, NT, smem_red, s>>>(A);
   cb_finish_kernel<false><<<g.O, 64, 0, s>>>(A, C * 9);
   bb_launch_tally += 2;
   BB_LAUNCH_CHECK();
@@ -700,11 +713,13 @@ int bb_launch_convblock(const bb_node& nd, int pass, cudaStream_t s) {
   A.tq_nhwc = tq_nhwc ? reinterpret_cast<__nv_bfloat16*>(nd.t[3]) : nullptr;
   A.a_q = reinterpret_cast<const float*>(nd.a[3]);
   A.at_q = reinterpret_cast<const float*>(nd.at[3]);
-  return A.g.C == 1 ? run<1>(A, pass, s) : run<3>(A, pass, s);
+  if (A.g.ps == 2) return A.g.C == 1 ? run<1, __nv_bfloat16>(A, pass, s) : run<3, __nv_bfloat16>(A, pass, s);
+  return A.g.C == 1 ? run<1, float>(A, pass, s) : run<3, float>(A, pass, s);
 }
 
 extern "C" int64_t bb_convblock_ws_bytes(int N, int C, int H, int W, int O, int HO, int WO, int HP, int WP) {
   CbGeom g{};
+  g.ps = 4;    // upper bound (fp32 pooled arrays)
   g.N = N; g.C = C; g.H = H; g.W = W; g.O = O; g.HO = HO; g.WO = WO; g.HP = HP; g.WP = WP;
   return (int64_t)cb_layout(nullptr, g).bytes;
 }
