@@ -216,6 +216,129 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient with the same halo trick:  D[tap][c][o] += sum_pixels X[pixel + d(tap)][c] * G[pixel][o]
+// Both operands are MN-major (rows = pixels = the reduction dimension), X and G in the padded NHWC layout.  Per tile of
+// 128 padded-linear pixels: ONE TMA box of G (128 rows) and ONE band of X (128 + 2(W+2) + 2 rows); the nine taps are
+// nine row offsets into the X band, two taps per M=128 instruction (the MN-major leading-dimension byte offset is the
+// row distance between the two taps).  wgrad_tma_kernel (conv_tma.cu) loads one X box per tap and tile of <= 64 pixels.
+// Accumulators stay in TMEM over all tiles of the CTA (5 x 64 columns); one atomic flush per CTA at the end.
+// ---------------------------------------------------------------------------------------------------------------
+struct alignas(64) WHaloArgs {
+  CUtensorMap x[2], g[2];
+  int npairs;
+  int Wp;
+  int band_rows;
+  int64_t total_rows;
+  int ntiles;
+  int stages;
+  float* out;                 // [64 (o)][64 (c)][9] fp32, accumulated with atomics
+  int C, O;
+};
+
+constexpr int WH_G_BYTES = 128 * 128;     // 16 KB
+constexpr int WH_STAGE = BAND_BYTES + WH_G_BYTES;
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo_kernel(const __grid_constant__ WHaloArgs G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G.stages * WH_STAGE);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 4), accum = smem_u32(bars + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < G.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = ((int)blockIdx.x < G.ntiles) ? (G.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_tiles * G.npairs;
+  const uint32_t bytes = (uint32_t)G.band_rows * 128u + (uint32_t)WH_G_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int p = 0; p < G.npairs; ++p) {
+        tma_prefetch_desc(&G.x[p]);
+        tma_prefetch_desc(&G.g[p]);
+      }
+      for (int it = 0; it < total; ++it) {
+        const int s = it % G.stages;
+        if (it >= G.stages) mbar_wait(empty0 + 8 * s, ((it / G.stages) - 1) & 1);
+        const int pair = it % G.npairs;
+        const int tile = (int)blockIdx.x + (it / G.npairs) * (int)gridDim.x;
+        const int m0 = tile * BM;
+        const uint32_t bar = full0 + 8 * s;
+        const uint32_t base = smem_u32(smem + s * WH_STAGE);
+        mbar_expect_tx(bar, bytes);
+        tma_load_3d(base, &G.x[pair], bar, 0, m0 - G.Wp - 1, 0);
+        tma_load_3d(base + BAND_BYTES, &G.g[pair], bar, 0, m0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, 64, true, true);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % G.stages;
+        mbar_wait(full0 + 8 * s, (it / G.stages) & 1);
+        tc_fence_after();
+        const uint32_t band = smem_u32(smem + s * WH_STAGE), g_addr = band + BAND_BYTES;
+#pragma unroll 1
+        for (int tp = 0; tp < 5; ++tp) {
+          const int t1 = 2 * tp, t2 = (2 * tp + 1 < 9) ? 2 * tp + 1 : 2 * tp;
+          const int d1 = (t1 / 3 - 1) * G.Wp + (t1 % 3 - 1), d2 = (t2 / 3 - 1) * G.Wp + (t2 % 3 - 1);
+          const uint32_t x_addr = band + (uint32_t)((G.Wp + 1 + d1) * 128);
+          const uint32_t lbo = t2 == t1 ? 128u : (uint32_t)((d2 - d1) * 128);   // (tap 8 alone: the upper half is ignored)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16(tmem_base + (uint32_t)(tp * 64), desc_mn(x_addr + ks * 2048, lbo), desc_mn(g_addr + ks * 2048, 8192),
+                      idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);
+      }
+      if (total > 0) umma_commit(accum);
+    }
+    __syncwarp();
+  } else {
+    if (total > 0) {
+      mbar_wait(accum, 0, 200);
+      tc_fence_after();
+      const int quarter = warp & 3;
+      const int L = quarter * 32 + lane;
+      const int half = L >> 6, c = L & 63;
+#pragma unroll 1
+      for (int tp = 0; tp < 5; ++tp) {
+        const int tap = 2 * tp + half;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tp * 64 + cc * 32), v);
+          if (tap < 9 && c < G.C) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int o = cc * 32 + j;
+              if (o < G.O) atomicAdd(G.out + ((int64_t)o * G.C + c) * 9 + tap, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 }  // namespace
 
 bool bb_conv_halo_ok(int C, int O, int H, int W) {
@@ -263,4 +386,39 @@ extern "C" int bb_conv_halo_bf16(int N, int H, int W, int npairs, const void* ac
   const void* acts[2] = {act0, act1};
   const void* ws[2] = {w0, w1};
   return bb_conv_halo_run(N, H, W, npairs, acts, ws, flip, out, beta, bias, (cudaStream_t)stream);
+}
+
+int bb_wgrad_halo_run(int N, int H, int W, int C, int O, int npairs, const void* const* x_padded, const void* const* gy_padded,
+                      float* out, cudaStream_t s) {
+  if (npairs < 1 || npairs > 2 || C > 64 || O > 64 || !bb_conv_halo_ok(64, 64, H, W)) return BB_ERR_UNSUPPORTED;
+  alignas(64) WHaloArgs G;
+  memset(&G, 0, sizeof(G));
+  G.npairs = npairs;
+  G.Wp = W + 2;
+  G.band_rows = BM + 2 * G.Wp + 2;
+  G.total_rows = (int64_t)N * (H + 2) * (W + 2);
+  G.ntiles = (int)((G.total_rows + BM - 1) / BM);
+  G.stages = 4;
+  G.out = out; G.C = C; G.O = O;
+  int rc;
+  for (int p = 0; p < npairs; ++p) {
+    if ((rc = bb_tma_map_2d(&G.x[p], x_padded[p], G.total_rows, 64, 64, G.band_rows))) return rc;
+    if ((rc = bb_tma_map_2d(&G.g[p], gy_padded[p], G.total_rows, 64, 64, BM))) return rc;
+  }
+  const size_t smem = (size_t)G.stages * WH_STAGE + 256 + 1024;
+  static BbOncePerDevice configured;
+  if (configured.need())
+    BB_CUDA_TRY(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = G.ntiles < BB_SM_COUNT ? G.ntiles : BB_SM_COUNT;
+  wgrad_halo_kernel<<<grid, NTHREADS, smem, s>>>(G);
+  bb_launch_tally += 1;
+  BB_LAUNCH_CHECK();
+  return BB_OK;
+}
+
+extern "C" int bb_wgrad_halo_bf16(int N, int H, int W, int npairs, const void* x0, const void* x1, const void* g0, const void* g1,
+                                  float* out, void* stream) {
+  const void* xs[2] = {x0, x1};
+  const void* gs[2] = {g0, g1};
+  return bb_wgrad_halo_run(N, H, W, 64, 64, npairs, xs, gs, out, (cudaStream_t)stream);
 }

@@ -10,3 +10,7 @@ bool bb_conv_halo_ok(int C, int O, int H, int W);
 // wmat[pair][n][tap][ch] (+ bias[n]);  wmat: bf16 [64][9][64] (bb_pack_convw);  flip = 1: input-gradient form
 int bb_conv_halo_run(int N, int H, int W, int npairs, const void* const* act_padded, const void* const* wmat, int flip,
                      float* out, int beta, const float* bias, cudaStream_t s);
+// weight gradient over padded operands: out[o][c][tap] += sum_pairs sum_pixels gy[pair][pixel][o] * x[pair][pixel + d(tap)][c]
+// (out: fp32 [O][C][9], accumulated with atomics)
+int bb_wgrad_halo_run(int N, int H, int W, int C, int O, int npairs, const void* const* x_padded, const void* const* gy_padded,
+                      float* out, cudaStream_t s);

@@ -515,6 +515,9 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
   const void* tin = tin_nhwc ? nd.t[0] : (const void*)A.w.tin;     // packed by this iteration's tangent-forward pass
   const void* xs[2] = {A.w.xin, tin};
   const void* gs[2] = {A.w.aty, A.w.ay};
+  static const bool no_wh = getenv("BB200_NO_WGRAD_HALO") != nullptr;
+  if (!no_wh && bb_conv_halo_ok(64, 64, g.H, g.W))
+    return bb_wgrad_halo_run(g.N, g.H, g.W, g.C, g.O, 2, xs, gs, reinterpret_cast<float*>(nd.at[1]), s);
   return bb_conv_tma_wgrad(cg, 2, xs, gs, reinterpret_cast<float*>(nd.at[1]), s, true);
 }
 

@@ -47,3 +47,23 @@ def test_halo_convolution_against_float64(case, npairs, flip, beta):
         want = want + bias.double().view(1, -1, 1, 1)
     err = float((out.double() - want).norm() / want.norm())
     assert err < 2e-5, f"{case} npairs={npairs} flip={flip}: rel {err:.3e}"
+
+
+@pytest.mark.parametrize("case", sorted(SHAPES))
+@pytest.mark.parametrize("npairs", [1, 2])
+def test_halo_weight_gradient_against_float64(case, npairs):
+    n, h, w = SHAPES[case]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    xs = [torch.randn(n, 64, h, w, generator=g, device="cuda").bfloat16().float() for _ in range(npairs)]
+    gys = [torch.randn(n, 64, h, w, generator=g, device="cuda").bfloat16().float() for _ in range(npairs)]
+    out0 = torch.randn(64, 64, 3, 3, generator=g, device="cuda")
+    out = out0.clone()
+    xp, gp = [_padded(t) for t in xs], [_padded(t) for t in gys]
+    N.call("bb_wgrad_halo_bf16", n, h, w, npairs, xp[0].data_ptr(), xp[1].data_ptr() if npairs > 1 else 0,
+           gp[0].data_ptr(), gp[1].data_ptr() if npairs > 1 else 0, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = out0.double()
+    for x, gy in zip(xs, gys):
+        want = want + torch.nn.grad.conv2d_weight(x.double(), (64, 64, 3, 3), gy.double(), padding=1)
+    err = float((out.double() - want).norm() / want.norm())
+    assert err < 2e-5, f"{case} npairs={npairs}: rel {err:.3e}"
