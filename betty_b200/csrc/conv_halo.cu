@@ -53,6 +53,8 @@ struct alignas(64) HaloArgs {
   int64_t total_rows;        // N * (H+2) * (W+2)
   int ntiles;
   float* out;
+  __nv_bfloat16* out_bf16;   // when set: the result goes out as bf16 in the SAME padded NHWC layout (row r of a tile is
+                             // row tile*128 + r of the output matrix: one contiguous 16 KB block per tile), border rows 0
   int beta;
   const float* bias;
   int bo_mode;               // 1: descriptor base offset = (start >> 7) & 7 (PTX ISA), 0: always 0
@@ -185,6 +187,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+        }
+        if (G.out_bf16) {
+          // bf16 padded-NHWC output: this thread's pixel row, 32 channels = 64 contiguous bytes; border rows are zeros
+          if (row >= G.total_rows) continue;
+          uint4* q = reinterpret_cast<uint4*>(G.out_bf16 + row * 64 + c * 32);
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 8) {
+            uint4 o;
+            if (ok) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[jj + e]) + (G.bias ? G.bias[c * 32 + jj + e] : 0.f);
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+              o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+              o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+            } else {
+              o = make_uint4(0, 0, 0, 0);
+            }
+            q[jj >> 3] = o;
+          }
+          continue;
         }
         if (!ok) continue;
         float* q = G.out + obase + (int64_t)(c * 32) * HW;
@@ -347,7 +371,7 @@ bool bb_conv_halo_ok(int C, int O, int H, int W) {
 }
 
 int bb_conv_halo_run(int N, int H, int W, int npairs, const void* const* act_padded, const void* const* wmat, int flip,
-                     float* out, int beta, const float* bias, cudaStream_t s) {
+                     float* out, int beta, const float* bias, cudaStream_t s, void* out_bf16_padded) {
   if (npairs < 1 || npairs > 2 || !bb_conv_halo_ok(64, 64, H, W)) return BB_ERR_UNSUPPORTED;
   alignas(64) HaloArgs G;
   memset(&G, 0, sizeof(G));
@@ -385,7 +409,15 @@ extern "C" int bb_conv_halo_bf16(int N, int H, int W, int npairs, const void* ac
                                  const void* w1, int flip, float* out, int beta, const float* bias, void* stream) {
   const void* acts[2] = {act0, act1};
   const void* ws[2] = {w0, w1};
-  return bb_conv_halo_run(N, H, W, npairs, acts, ws, flip, out, beta, bias, (cudaStream_t)stream);
+  return bb_conv_halo_run(N, H, W, npairs, acts, ws, flip, out, beta, bias, (cudaStream_t)stream, nullptr);
+}
+
+// same product written as bf16 in the padded NHWC layout (out_padded: [N][H+2][W+2][64], border rows written as zeros)
+extern "C" int bb_conv_halo_bf16_nhwc(int N, int H, int W, int npairs, const void* act0, const void* act1, const void* w0,
+                                      const void* w1, int flip, void* out_padded, const float* bias, void* stream) {
+  const void* acts[2] = {act0, act1};
+  const void* ws[2] = {w0, w1};
+  return bb_conv_halo_run(N, H, W, npairs, acts, ws, flip, nullptr, 0, bias, (cudaStream_t)stream, out_padded);
 }
 
 int bb_wgrad_halo_run(int N, int H, int W, int C, int O, int npairs, const void* const* x_padded, const void* const* gy_padded,

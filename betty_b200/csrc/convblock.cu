@@ -122,6 +122,9 @@ struct CbArgs {
   __nv_bfloat16* tq_nhwc;     // when the consumer is a fused block: t_q as bf16 NHWC (its TMA operand), t_q unused
   const float* a_q;
   const float* at_q;
+  // when the consumer is a fused inner block it hands a_q / at_q over as bf16 padded NHWC [N][HP+2][WP+2][64]
+  const __nv_bfloat16* aq_nhwc;
+  const __nv_bfloat16* atq_nhwc;
   int nparts;     // CTAs that wrote partials
 };
 
@@ -131,7 +134,8 @@ CbGeom make_geom(const bb_node& nd) {
   g.HO = (int)nd.dims[7]; g.WO = (int)nd.dims[8]; g.ph = (int)nd.dims[11]; g.pw = (int)nd.dims[12];
   g.HP = (int)nd.dims[13]; g.WP = (int)nd.dims[14]; g.relu = (int)nd.dims[15];
   g.ps = (nd.kind & 1) ? 2 : 4;
-  int R = 48 / (g.WP > 0 ? g.WP : 1);     // ~48 windows x O channels per tile: small tiles, many resident CTAs
+  int R = 128 / (g.WP > 0 ? g.WP : 1);    // ~128 windows x O channels per tile: the per-tile fixed cost (tile loads,
+                                          // two barriers) was 40 % of the time at 42 windows
   if (R < 1) R = 1;
   if (R > g.HP) R = g.HP;
   g.R = R;
@@ -262,7 +266,9 @@ __global__ void __launch_bounds__(256) cb_prep_kernel(const CbArgs A) {
     const int64_t pi = (((int64_t)n * g.HP + hp) * g.WP + wp) * g.O + o;
     A.w.sel[pi] = (unsigned char)((dy & 1) * 2 + (dx & 1) + (m ? 4 : 0));
     stp<PT>(reinterpret_cast<PT*>(A.w.xh), pi, (yv - A.w.mean[o]) * A.w.rstd[o]);
-    stp<PT>(reinterpret_cast<PT*>(A.w.aqm), pi, m ? A.a_q[i] : 0.f);
+    const float aq = A.aq_nhwc ? __bfloat162float(A.aq_nhwc[((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + o])
+                               : A.a_q[i];
+    stp<PT>(reinterpret_cast<PT*>(A.w.aqm), pi, m ? aq : 0.f);
   }
 }
 
@@ -420,6 +426,10 @@ __global__ void __launch_bounds__(NT, 4) cb_tf_kernel(const CbArgs A) {
   // t_q = mask * (c_y * t_y + c_x * xhat + c_0)
   const float c_y = gam * rstd, c_x = tgam - gam * rstd * sdot, c_0 = tbeta + gam * rstd * (tb - mean_t);
   const float e_0 = (tb - mean_t) * rstd, e_x = -sdot * rstd;          // dxhat = rstd*t_y + e_x*xhat + e_0
+  const int pitch = g.xpitch, WPc = g.WP, Oc = g.O;
+  int roff[C * 3];                                                      // (channel, tap row) offsets inside the x tile
+#pragma unroll
+  for (int r = 0; r < C * 3; ++r) roff[r] = (r / 3) * plane + (r % 3) * pitch;
   const int tcap = g.R * g.WP * g.O;                 // pooled elements of a full tile
   PT* xh_s = reinterpret_cast<PT*>(outs + g.O * g.wpitch);               // [nw][O] xhat* of the tile
   unsigned char* sel_s = reinterpret_cast<unsigned char*>(xh_s + tcap);
@@ -434,22 +444,43 @@ __global__ void __launch_bounds__(NT, 4) cb_tf_kernel(const CbArgs A) {
     tile_copy_wait();
     __syncthreads();
     if (och) {
-      const int64_t tbase = t0 + o;
+      // strength-reduced indices: everything below advances by additions (the first version spent ~50 integer
+      // multiply-adds per window on address arithmetic, profiles/r02_convblock_v1_ncu.md)
       int wr = 0, wc = wg;
-      while (wc >= g.WP) { wc -= g.WP; ++wr; }
+      while (wc >= WPc) { wc -= WPc; ++wr; }
+      int rowbase = 2 * wr * pitch + 2 * wc;                    // xs offset of the window's top-left candidate pixel
+      int sidx = wg * Oc + o;                                   // index into the staged pooled arrays
+      PT* dxo = dxhp + t0 + sidx;                               // global dxhat* slot
+      __nv_bfloat16* tqo = A.tq_nhwc
+          ? A.tq_nhwc + ((((int64_t)n * (g.HP + 2) + hp0 + wr + 1) * (WPc + 2)) + wc + 1) * 64 + o : nullptr;
       for (int wl = wg; wl < nw; wl += wgs) {
-        const unsigned code_c = sel_s[wl * g.O + o];
-        const float xh_c = ldp<PT>(xh_s, wl * g.O + o);
-        const int base = (2 * wr + ((code_c >> 1) & 1)) * g.xpitch + 2 * wc + (code_c & 1);
-        const float ty = patch_dot<C>(xs, base, plane, g.xpitch, tw);
-        stp<PT>(dxhp, tbase + (int64_t)wl * g.O, fmaf(rstd, ty, fmaf(e_x, xh_c, e_0)));
+        const unsigned code_c = sel_s[sidx];
+        const float xh_c = ldp<PT>(xh_s, sidx);
+        const float* px = xs + rowbase + ((code_c & 2) ? pitch : 0) + (code_c & 1);
+        float ty = 0.f;
+#pragma unroll
+        for (int r = 0; r < C * 3; ++r) {
+          const float* q = px + roff[r];
+          ty = fmaf(q[0], tw[3 * r], ty);
+          ty = fmaf(q[1], tw[3 * r + 1], ty);
+          ty = fmaf(q[2], tw[3 * r + 2], ty);
+        }
+        stp<PT>(dxo, 0, fmaf(rstd, ty, fmaf(e_x, xh_c, e_0)));
         const float tq = (code_c & 4) ? fmaf(c_y, ty, fmaf(c_x, xh_c, c_0)) : 0.f;
-        if (A.tq_nhwc)   // padded NHWC [N][HP+2][WP+2][64] (O == 64): the next fused block's TMA operand
-          A.tq_nhwc[((((int64_t)n * (g.HP + 2) + hp0 + wr + 1) * (g.WP + 2)) + wc + 1) * 64 + o] = __float2bfloat16(tq);
+        if (tqo)
+          *tqo = __float2bfloat16(tq);
         else
           outs[o * g.wpitch + wl] = tq;
+        sidx += wgs * Oc;
+        dxo += wgs * Oc;
         wc += wgs;
-        while (wc >= g.WP) { wc -= g.WP; ++wr; }
+        rowbase += 2 * wgs;
+        if (tqo) tqo += wgs * 64;
+        while (wc >= WPc) {
+          wc -= WPc; ++wr;
+          rowbase += 2 * pitch - 2 * WPc;
+          if (tqo) tqo += 2 * 64;                                // skip the right border of this row and the left of the next
+        }
       }
     }
     if (!A.tq_nhwc) {
@@ -493,6 +524,10 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
 #pragma unroll
   for (int k = 0; k < CKK; ++k) gw[k] = 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const int pitch = g.xpitch, WPc = g.WP, Oc = g.O;
+  int roff[C * 3];
+#pragma unroll
+  for (int r = 0; r < C * 3; ++r) roff[r] = (r / 3) * plane + (r % 3) * pitch;
   const int tcap = g.R * g.WP * g.O;
   PT* xh_s = reinterpret_cast<PT*>(ins + g.O * g.wpitch);
   PT* aq_s = xh_s + tcap;
@@ -508,7 +543,7 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
     if (!BASE) tile_copy_async(dx_s, dxhp + t0, nw * g.O * (int)sizeof(PT));
     tile_copy_async(sel_s, sel + t0, nw * g.O);
     load_x_tile<C>(A, n, hp0, xs);
-    if (!BASE) {
+    if (!BASE && !A.atq_nhwc) {
       const float* src = A.at_q + (((int64_t)n * g.O) * g.HP + hp0) * g.WP;
       for (int oo = wid; oo < g.O; oo += NT / 32) {
         const float* sp = src + (int64_t)oo * g.HP * g.WP;
@@ -520,30 +555,41 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
     __syncthreads();
     if (och) {
       int wr = 0, wc = wg;
-      while (wc >= g.WP) { wc -= g.WP; ++wr; }
+      while (wc >= WPc) { wc -= WPc; ++wr; }
+      int rowbase = 2 * wr * pitch + 2 * wc;
+      int si = wg * Oc + o;
+      const __nv_bfloat16* atq = A.atq_nhwc
+          ? A.atq_nhwc + ((((int64_t)n * (g.HP + 2) + hp0 + wr + 1) * (WPc + 2)) + wc + 1) * 64 + o : nullptr;
       for (int wl = wg; wl < nw; wl += wgs) {
-        const int si = wl * g.O + o;
         const unsigned code_c = sel_s[si];
         const float xh_c = ldp<PT>(xh_s, si), aq_c = ldp<PT>(aq_s, si);
         float v;
         if (BASE) {
           v = aq_c;
         } else {
-          v = (code_c & 4) ? ins[o * g.wpitch + wl] : 0.f;
+          const float a = atq ? __bfloat162float(*atq) : ins[o * g.wpitch + wl];
+          v = (code_c & 4) ? a : 0.f;
           s2 = fmaf(aq_c, ldp<PT>(dx_s, si), s2);
         }
         s0 += v;
         s1 = fmaf(v, xh_c, s1);
-        const int base = (2 * wr + ((code_c >> 1) & 1)) * g.xpitch + 2 * wc + (code_c & 1);
+        const float* px = xs + rowbase + ((code_c & 2) ? pitch : 0) + (code_c & 1);
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-              gw[(c * 3 + i) * 3 + j] = fmaf(v, xs[base + c * plane + i * g.xpitch + j], gw[(c * 3 + i) * 3 + j]);
+        for (int r = 0; r < C * 3; ++r) {
+          const float* q = px + roff[r];
+          gw[3 * r] = fmaf(v, q[0], gw[3 * r]);
+          gw[3 * r + 1] = fmaf(v, q[1], gw[3 * r + 1]);
+          gw[3 * r + 2] = fmaf(v, q[2], gw[3 * r + 2]);
+        }
+        si += wgs * Oc;
         wc += wgs;
-        while (wc >= g.WP) { wc -= g.WP; ++wr; }
+        rowbase += 2 * wgs;
+        if (atq) atq += wgs * 64;
+        while (wc >= WPc) {
+          wc -= WPc; ++wr;
+          rowbase += 2 * pitch - 2 * WPc;
+          if (atq) atq += 2 * 64;
+        }
       }
     }
   }
@@ -711,8 +757,12 @@ int bb_launch_convblock(const bb_node& nd, int pass, cudaStream_t s) {
   const bool tq_nhwc = (nd.kind & 4) && A.g.O == 64;
   A.t_q = tq_nhwc ? nullptr : reinterpret_cast<float*>(nd.t[3]);
   A.tq_nhwc = tq_nhwc ? reinterpret_cast<__nv_bfloat16*>(nd.t[3]) : nullptr;
-  A.a_q = reinterpret_cast<const float*>(nd.a[3]);
-  A.at_q = reinterpret_cast<const float*>(nd.at[3]);
+  // kind bit 3: a_q / at_q arrive as bf16 padded NHWC too (written by the next fused block's input-gradient epilogue)
+  const bool adj_nhwc = (nd.kind & 8) && A.g.O == 64;
+  A.a_q = adj_nhwc ? nullptr : reinterpret_cast<const float*>(nd.a[3]);
+  A.at_q = adj_nhwc ? nullptr : reinterpret_cast<const float*>(nd.at[3]);
+  A.aq_nhwc = adj_nhwc ? reinterpret_cast<const __nv_bfloat16*>(nd.a[3]) : nullptr;
+  A.atq_nhwc = adj_nhwc ? reinterpret_cast<const __nv_bfloat16*>(nd.at[3]) : nullptr;
   if (A.g.ps == 2) return A.g.C == 1 ? run<1, __nv_bfloat16>(A, pass, s) : run<3, __nv_bfloat16>(A, pass, s);
   return A.g.C == 1 ? run<1, float>(A, pass, s) : run<3, float>(A, pass, s);
 }

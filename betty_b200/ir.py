@@ -52,7 +52,8 @@ class Val:
         self.ident = ident                  # alias whose buffers are *exactly* the parent's (cast, x + const)
         self.boundary = False               # upper-dependent constant (requires_grad, not from the lower params)
         self.interp_only = False            # internal value of a fused node: only the torch interpreter gives it buffers
-        self.tfmt = None                    # "nhwc_bf16": the tangent buffer is the next fused block's TMA operand
+        self.tfmt = None                    # "nhwc_bf16": t / a / at are bf16 padded NHWC [N][H+2][W+2][64], handed from
+                                            # one fused block to the next as TMA operands (no fp32 NCHW buffers)
 
     @property
     def root(self) -> "Val":
@@ -914,8 +915,9 @@ def _match_data_conv_block(g: Graph, conv: Node, consumers) -> Optional[Tuple[No
         x = conv.ins[0]
         reduced = X.dtype in (torch.bfloat16, torch.float16) and W.dtype in (torch.bfloat16, torch.float16)
         C, O, Wd, WO = W.shape[1], W.shape[0], X.shape[3], conv.out.base.shape[3]
+        # 64 -> 64 channels, and a band of 128 + 2(W+2) + 2 pixel rows must fit one TMA box (conv_halo.cu)
         if (os.environ.get("BB200_NO_CONVBLOCK2") or not reduced or x.parent is not None or x.boundary
-                or not (32 <= C <= 64 and 32 <= O <= 64 and 4 <= WO <= 64 and Wd <= 128)
+                or C != 64 or O != 64 or not (4 <= WO <= 61) or Wd != WO
                 or tuple(at["padding"]) != (1, 1) or not X.is_contiguous()):
             return None
     def is_param(v):

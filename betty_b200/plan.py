@@ -88,7 +88,7 @@ class HvpPlan:
             place[v.vid] = (sizes["t"], sizes["z" if v.zero_init else "nz"])
             if v.tfmt is None:
                 sizes["t"] += n
-            sizes["z" if v.zero_init else "nz"] += n
+                sizes["z" if v.zero_init else "nz"] += n
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.T = torch.zeros(max(sizes["t"], 1), **f32)
         self.A = {"z": torch.zeros(max(sizes["z"], 1), **f32), "nz": torch.zeros(max(sizes["nz"], 1), **f32)}
@@ -103,9 +103,10 @@ class HvpPlan:
                 # [N][H+2][W+2][64], zero border (never written)
                 Nn, Cc, Hh, Ww = shape
                 assert Cc == 64, shape
-                v.t = torch.zeros((Nn, Hh + 2, Ww + 2, 64), dtype=torch.bfloat16, device=self.dev)
-            else:
-                v.t = torch.as_strided(self.T, shape, stride, ot)
+                mk = lambda: torch.zeros((Nn, Hh + 2, Ww + 2, 64), dtype=torch.bfloat16, device=self.dev)
+                v.t, v.a, v.at = mk(), mk(), mk()       # (single producer each, every interior element overwritten)
+                continue
+            v.t = torch.as_strided(self.T, shape, stride, ot)
             v.a = torch.as_strided(self.A[k], shape, stride, oa)
             v.at = torch.as_strided(self.AT[k], shape, stride, oa)
         dviews, hviews = self.layout.views(self.d_arena), self.layout.views(self.hv_arena)
@@ -168,8 +169,8 @@ class HvpPlan:
             for kind in ("t", "a", "at"):
                 b = self.buf(v, kind)
                 rec[kind][s] = self._ptr(b)
-                if kind == "t" and v.root.tfmt is not None:
-                    continue            # bf16 NHWC tangent handed from one fused block to the next
+                if v.root.tfmt is not None:
+                    continue            # bf16 padded-NHWC buffers handed from one fused block to the next
                 if b is not None and base_t is not None and b.numel() > 1 and tuple(b.stride()) != tuple(base_t.stride()):
                     raise UnsupportedGraph(f"buffer/base stride mismatch for {v}: {b.stride()} vs {base_t.stride()}")
 
@@ -440,7 +441,8 @@ class HvpPlan:
         ph, pw = n.attrs["padding"]
         r["dims"][0:16] = (Nn, Cc, H, Wd, O, 3, 3, HO, WO, 1, 1, ph, pw, HP, WP, int(n.attrs["relu"]))
         r["f"][0] = n.attrs["eps"]
-        r["kind"] = int(X.dtype in (torch.bfloat16, torch.float16)) | (4 if n.out.tfmt == "nhwc_bf16" else 0)
+        # kind: bit 0 reduced precision, bit 2: t of q is bf16 padded NHWC, bit 3: so are a / at of q
+        r["kind"] = int(X.dtype in (torch.bfloat16, torch.float16)) | (12 if n.out.tfmt == "nhwc_bf16" else 0)
         if not (X.is_contiguous() and Y.is_contiguous()):
             raise UnsupportedGraph("convblock operands must be NCHW-contiguous")
         self._slot(r, 0, w, None)
@@ -730,18 +732,21 @@ class HvpPlan:
         if n.op == "diagshift":
             return 12 * sum(p.base.numel() for p in n.ins) if pas == PASS_TB else 0
         if n.op == "convblock2":
-            # what the fused rule moves besides the tensor-core operands: see csrc/convblock2.cu header
-            X, Y, q = n.attrs["X"], n.attrs["Y"], n.out.base.numel()
-            a_in, a_out = X.numel(), Y.numel()
-            if pas == PASS_TF:
-                return int(4 * a_in + 4 * a_out + 6 * a_out + 4 * q + 13 * q)
-            return int((6 + 2.25) * a_out + 2 * a_out + 4 * a_out + 4 * a_in + 4 * a_out + 4 * a_in + 17 * q)
+            # bytes the fused inner block moves (bf16 padded NHWC everywhere, csrc/convblock2.cu): A = conv-output
+            # elements (= input elements), q = pooled elements
+            A_, q = n.attrs["Y"].numel(), n.out.base.numel()
+            if pas == PASS_TF:      # conv reads t_in, x_in writes t_y | stats reads t_y, y | finalize: gather + pooled arrays
+                return int(2 * (2 * A_) + 2 * A_ + 2 * (2 * A_) + 2 * A_ + 7 * q)
+            # reduce (pooled) | dense reads t_y, y (+ pooled) writes at_y | dgrad reads at_y, a_y writes at_in | wgrad reads 4 operands
+            return int(9 * q + 2 * (2 * A_) + 5 * q + 2 * A_ + 2 * (2 * A_) + 2 * A_ + 4 * (2 * A_))
         if n.op == "convblock":
             # what the fused rule streams: x once, then pooled-size arrays (arg-max code 1 B, xhat* 4 B, dxhat* 4 B,
             # pooled tangent / adjoint-tangent 4 B, masked base adjoint 4 B)
             X, q = n.attrs["X"], n.out.base.numel()
             xb = X.numel() * X.element_size()
-            return int(xb + q * {PASS_TF: 13, PASS_TB: 17}.get(pas, 17))
+            ps = 2 if X.dtype in (torch.bfloat16, torch.float16) else 4       # pooled arrays follow the graph precision
+            io = 2 if n.out.tfmt == "nhwc_bf16" else 4                        # pooled tangent / adjoint-tangent
+            return int(xb + q * (1 + 2 * ps + io if pas == PASS_TF else 1 + 3 * ps + io))
         out_n = n.out.base.numel()
         total = 0
         uses_base = {"unary": (0,), "mul2": (0, 1), "gemm": (0, 1), "conv2d": (0, 1), "batchnorm": (0,),

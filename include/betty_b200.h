@@ -123,6 +123,9 @@ int bb_plan_node_route(bb_plan* plan, int node, int pass); /* tests: 2 = TMA ten
  *      out fp32 NCHW; flip = 1: tap (i, j) reads the pixel at (+1-i, +1-j) (input-gradient form) */
 int bb_conv_halo_bf16(int N, int H, int W, int npairs, const void* act0, const void* act1, const void* w0, const void* w1,
                       int flip, float* out, int beta, const float* bias, void* stream);
+int bb_conv_halo_bf16_nhwc(int N, int H, int W, int npairs, const void* act0, const void* act1, const void* w0,
+                           const void* w1, int flip, void* out_padded /* bf16 [N][H+2][W+2][64] */, const float* bias,
+                           void* stream);
 /* weight-gradient companion (wgrad_halo_kernel): out[o][c][tap] (fp32 [64][64][9], accumulated) +=
  * sum_pixels gy[pixel][o] * x[pixel + d(tap)][c], x / gy bf16 padded NHWC */
 int bb_wgrad_halo_bf16(int N, int H, int W, int npairs, const void* x0, const void* x1, const void* g0, const void* g1,

@@ -67,3 +67,30 @@ def test_halo_weight_gradient_against_float64(case, npairs):
         want = want + torch.nn.grad.conv2d_weight(x.double(), (64, 64, 3, 3), gy.double(), padding=1)
     err = float((out.double() - want).norm() / want.norm())
     assert err < 2e-5, f"{case} npairs={npairs}: rel {err:.3e}"
+
+
+@pytest.mark.parametrize("case", ["42x42_n6", "21x21_n9", "5x7_n33"])
+@pytest.mark.parametrize("flip", [0, 1])
+def test_halo_convolution_bf16_padded_output(case, flip):
+    """Output mode of the fused blocks: the product lands as bf16 in the padded NHWC layout (the next kernel's TMA
+    operand), border rows written as zeros."""
+    n, h, w = SHAPES[case]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = [torch.randn(n, 64, h, w, generator=g, device="cuda").bfloat16().float() for _ in range(2)]
+    wms = [(0.1 * torch.randn(64, 9, 64, generator=g, device="cuda")).bfloat16() for _ in range(2)]
+    bias = torch.randn(64, generator=g, device="cuda")
+    pads = [_padded(a) for a in acts]
+    out = torch.full((n, h + 2, w + 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    N.call("bb_conv_halo_bf16_nhwc", n, h, w, 2, pads[0].data_ptr(), pads[1].data_ptr(), wms[0].data_ptr(), wms[1].data_ptr(),
+           flip, out.data_ptr(), bias.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = torch.zeros(n, 64, h, w, dtype=torch.float64, device="cuda")
+    for a, wm in zip(acts, wms):
+        k = wm.double().reshape(64, 3, 3, 64).permute(0, 3, 1, 2)
+        want = want + F.conv2d(a.double(), k.flip(2, 3) if flip else k, padding=1)
+    want = want + bias.double().view(1, -1, 1, 1)
+    got = out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).double()
+    assert float((got - want).norm() / want.norm()) < 4e-3          # bf16 rounding of the result
+    border = out.clone()
+    border[:, 1:-1, 1:-1, :] = 0
+    assert float(border.float().abs().max()) == 0.0                 # NaN-filled border was overwritten with zeros

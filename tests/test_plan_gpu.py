@@ -65,7 +65,7 @@ def _compare(plan, interp, kinds, tol, what):
             continue
         for k in kinds:
             a, b = getattr(vn, k), getattr(vi, k)
-            if k == "t" and getattr(vn, "tfmt", None) == "nhwc_bf16":
+            if getattr(vn, "tfmt", None) == "nhwc_bf16":
                 a = a[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).float()     # bf16 padded-NHWC TMA operand of the next fused block
             err = float((a.double() - b).norm() / (b.norm() + 1e-30)) if float(b.norm()) > 0 else float(a.double().norm())
             if not (err <= tol):

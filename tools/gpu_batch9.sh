@@ -1,0 +1,4 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"cb_tf_kernel|cb_reduce_kernel|cb2_dense_kernel|conv_halo_kernel" -s 12 -c 8 -f -o gpurun_out/r2b9_cb python bench.py --workload implicit_maml --steps 1 --warmup 3 --no-cpu-baseline --no-graph --e2e-steps 1 > gpurun_out/r2b9_ncu.log 2>&1
+tail -3 gpurun_out/r2b9_ncu.log
