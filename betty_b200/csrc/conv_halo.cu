@@ -383,6 +383,8 @@ int bb_conv_halo_run(int N, int H, int W, int npairs, const void* const* act_pad
   G.total_rows = (int64_t)N * G.HpWp;
   G.ntiles = (int)((G.total_rows + BM - 1) / BM);
   G.out = out; G.beta = beta; G.bias = bias;
+  G.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16_padded);
+  if (G.out_bf16 ? beta != 0 : out == nullptr) return BB_ERR_ARG;
   // measured on B200 (tests/test_conv_halo_gpu.py, GPU call #52): SWIZZLE_128B is a pure function of the shared-memory
   // address bits, so a descriptor that starts on any 128-byte row reads the TMA-written band correctly with base offset 0
   // (setting the field to (start >> 7) & 7 gives wrong products); BB200_HALO_BO=1 keeps the other convention testable
