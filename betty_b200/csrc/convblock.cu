@@ -134,8 +134,7 @@ CbGeom make_geom(const bb_node& nd) {
   g.HO = (int)nd.dims[7]; g.WO = (int)nd.dims[8]; g.ph = (int)nd.dims[11]; g.pw = (int)nd.dims[12];
   g.HP = (int)nd.dims[13]; g.WP = (int)nd.dims[14]; g.relu = (int)nd.dims[15];
   g.ps = (nd.kind & 1) ? 2 : 4;
-  int R = 128 / (g.WP > 0 ? g.WP : 1);    // ~128 windows x O channels per tile: the per-tile fixed cost (tile loads,
-                                          // two barriers) was 40 % of the time at 42 windows
+  int R = 96 / (g.WP > 0 ? g.WP : 1);     // ~96 windows x O channels per tile (two pooled rows of the 84x84 layer)
   if (R < 1) R = 1;
   if (R > g.HP) R = g.HP;
   g.R = R;
@@ -431,7 +430,8 @@ __global__ void __launch_bounds__(NT, 4) cb_tf_kernel(const CbArgs A) {
 #pragma unroll
   for (int r = 0; r < C * 3; ++r) roff[r] = (r / 3) * plane + (r % 3) * pitch;
   const int tcap = g.R * g.WP * g.O;                 // pooled elements of a full tile
-  PT* xh_s = reinterpret_cast<PT*>(outs + g.O * g.wpitch);               // [nw][O] xhat* of the tile
+  PT* xh_s = reinterpret_cast<PT*>(outs + (A.tq_nhwc ? 0 : g.O * g.wpitch));   // [nw][O] xhat* of the tile (no NCHW
+                                                                                // staging tile in NHWC mode)
   unsigned char* sel_s = reinterpret_cast<unsigned char*>(xh_s + tcap);
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int n = tile / g.tiles_per_img, tr = tile - n * g.tiles_per_img;
@@ -529,10 +529,14 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
 #pragma unroll
   for (int r = 0; r < C * 3; ++r) roff[r] = (r / 3) * plane + (r % 3) * pitch;
   const int tcap = g.R * g.WP * g.O;
-  PT* xh_s = reinterpret_cast<PT*>(ins + g.O * g.wpitch);
+  // pooled arrays of the tile; in NHWC mode the transposed NCHW staging tile `ins` is not needed and its place is taken
+  // by the adjoint-tangent rows themselves ([rows][WP][64] bf16, copied row by row out of the padded array)
+  const bool nhwc_in = !BASE && A.atq_nhwc != nullptr;
+  PT* xh_s = reinterpret_cast<PT*>(ins + (nhwc_in ? 0 : g.O * g.wpitch));
   PT* aq_s = xh_s + tcap;
   PT* dx_s = aq_s + tcap;
   unsigned char* sel_s = reinterpret_cast<unsigned char*>(dx_s + tcap);
+  __nv_bfloat16* at_s = reinterpret_cast<__nv_bfloat16*>(sel_s + ((tcap + 15) & ~15));
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int n = tile / g.tiles_per_img, tr = tile - n * g.tiles_per_img;
     const int hp0 = tr * g.R, rows = min(g.R, g.HP - hp0), nw = rows * g.WP;
@@ -542,6 +546,10 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
     tile_copy_async(aq_s, aqm + t0, nw * g.O * (int)sizeof(PT));
     if (!BASE) tile_copy_async(dx_s, dxhp + t0, nw * g.O * (int)sizeof(PT));
     tile_copy_async(sel_s, sel + t0, nw * g.O);
+    if (nhwc_in)
+      for (int rr = 0; rr < rows; ++rr)
+        tile_copy_async(at_s + rr * WPc * 64, A.atq_nhwc + ((((int64_t)n * (g.HP + 2) + hp0 + rr + 1) * (WPc + 2)) + 1) * 64,
+                        WPc * 64 * 2);
     load_x_tile<C>(A, n, hp0, xs);
     if (!BASE && !A.atq_nhwc) {
       const float* src = A.at_q + (((int64_t)n * g.O) * g.HP + hp0) * g.WP;
@@ -558,8 +566,6 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
       while (wc >= WPc) { wc -= WPc; ++wr; }
       int rowbase = 2 * wr * pitch + 2 * wc;
       int si = wg * Oc + o;
-      const __nv_bfloat16* atq = A.atq_nhwc
-          ? A.atq_nhwc + ((((int64_t)n * (g.HP + 2) + hp0 + wr + 1) * (WPc + 2)) + wc + 1) * 64 + o : nullptr;
       for (int wl = wg; wl < nw; wl += wgs) {
         const unsigned code_c = sel_s[si];
         const float xh_c = ldp<PT>(xh_s, si), aq_c = ldp<PT>(aq_s, si);
@@ -567,7 +573,7 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
         if (BASE) {
           v = aq_c;
         } else {
-          const float a = atq ? __bfloat162float(*atq) : ins[o * g.wpitch + wl];
+          const float a = nhwc_in ? __bfloat162float(at_s[wl * 64 + o]) : ins[o * g.wpitch + wl];
           v = (code_c & 4) ? a : 0.f;
           s2 = fmaf(aq_c, ldp<PT>(dx_s, si), s2);
         }
@@ -584,11 +590,9 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
         si += wgs * Oc;
         wc += wgs;
         rowbase += 2 * wgs;
-        if (atq) atq += wgs * 64;
         while (wc >= WPc) {
           wc -= WPc; ++wr;
           rowbase += 2 * pitch - 2 * WPc;
-          if (atq) atq += 2 * 64;
         }
       }
     }
@@ -672,8 +676,11 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
   const size_t tile = 4 * ((size_t)C * g.xrows * g.xpitch + (size_t)g.O * g.wpitch);
   const int wgs = (NT / 32) / ((g.O + 31) / 32);
   const size_t smem_part = 4 * (size_t)wgs * g.O * (KP + NSUM);
-  const size_t smem_tf = tile + (sizeof(PT) + 1) * tcap + 64;
-  size_t smem_red = tile + (3 * sizeof(PT) + 1) * tcap + 64;
+  // NHWC mode (fused neighbour): no transposed NCHW staging tile; the reduce kernel stages the bf16 adjoint-tangent rows
+  const bool nhwc = A.tq_nhwc != nullptr || A.atq_nhwc != nullptr;
+  const size_t xt = 4 * (size_t)C * g.xrows * g.xpitch, nchw_tile = nhwc ? 0 : 4 * (size_t)g.O * g.wpitch;
+  const size_t smem_tf = xt + nchw_tile + (sizeof(PT) + 1) * tcap + 64;
+  size_t smem_red = xt + nchw_tile + (3 * sizeof(PT) + 1) * tcap + (nhwc ? 2 * (size_t)g.R * g.WP * 64 : 0) + 128;
   if (smem_red < smem_part) smem_red = smem_part;
   static BbOncePerDevice once;
   if (once.need()) {

@@ -204,119 +204,196 @@ __global__ void __launch_bounds__(256) cb2_pack_padded_kernel(const void* src, i
   }
 }
 
-// ---- tangent forward -----------------------------------------------------------------------------------------------
-// sum t_y and sum xhat t_y per channel: one pass over the padded rows of t_y and y (border rows of t_y are zeros),
-// lane <-> channel pair, warp <-> pixel rows
-__global__ void __launch_bounds__(256) cb2_stats_kernel(const A2 A) {
-  __shared__ float red[8][4][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t rows = (int64_t)A.g.N * (A.g.H + 2) * (A.g.W + 2);
-  const float2 mean = make_float2(A.w.mean[2 * lane], A.w.mean[2 * lane + 1]);
-  const float2 rstd = make_float2(A.w.rstd[2 * lane], A.w.rstd[2 * lane + 1]);
-  float s0x = 0.f, s0y = 0.f, s1x = 0.f, s1y = 0.f;
-  const int64_t stride = (int64_t)gridDim.x * 8;
-  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < rows; r += stride) {
-    const float2 t = ldbf2(A.w.ty + r * 64 + 2 * lane);
-    const float2 yv = ldbf2(A.w.yb + r * 64 + 2 * lane);
-    s0x += t.x; s0y += t.y;
-    s1x = fmaf((yv.x - mean.x) * rstd.x, t.x, s1x);
-    s1y = fmaf((yv.y - mean.y) * rstd.y, t.y, s1y);
+// ---- streaming kernels: a lane owns 8 channels (one 16-byte bf16 chunk), four lanes-groups of a warp take four rows ----
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld8(const bf16* p) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  F8 o;
+  o.v[0] = __uint_as_float(r.x << 16); o.v[1] = __uint_as_float(r.x & 0xffff0000u);
+  o.v[2] = __uint_as_float(r.y << 16); o.v[3] = __uint_as_float(r.y & 0xffff0000u);
+  o.v[4] = __uint_as_float(r.z << 16); o.v[5] = __uint_as_float(r.z & 0xffff0000u);
+  o.v[6] = __uint_as_float(r.w << 16); o.v[7] = __uint_as_float(r.w & 0xffff0000u);
+  return o;
+}
+__device__ __forceinline__ void st8(bf16* p, const F8& f) {
+  bf162 a = __floats2bfloat162_rn(f.v[0], f.v[1]), b = __floats2bfloat162_rn(f.v[2], f.v[3]);
+  bf162 c = __floats2bfloat162_rn(f.v[4], f.v[5]), d = __floats2bfloat162_rn(f.v[6], f.v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ F8 ld8f(const float* p) {       // 8 fp32 parameters / coefficients
+  const float4 a = bb::ld4(p), b = bb::ld4(p + 4);
+  F8 o;
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+  return o;
+}
+// 8 arg-max codes of a window (one byte per channel)
+__device__ __forceinline__ void ld_codes(const unsigned char* p, unsigned (&c)[8]) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    c[e] = (r.x >> (8 * e)) & 0xffu;
+    c[4 + e] = (r.y >> (8 * e)) & 0xffu;
   }
-  red[warp][0][lane] = s0x; red[warp][1][lane] = s0y; red[warp][2][lane] = s1x; red[warp][3][lane] = s1y;
+}
+// pooled adjoint tangent of a window: bf16 padded NHWC, or the plan's fp32 NCHW buffer (last fused block)
+__device__ __forceinline__ F8 load_atq8(const A2& A, int n, int hp, int wp, int c0) {
+  const G2& g = A.g;
+  if (A.atq_nhwc) return ld8(A.atq_nhwc + ((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + c0);
+  F8 o;
+  const int64_t b = (((int64_t)n * 64 + c0) * g.HP + hp) * g.WP + wp, cs = (int64_t)g.HP * g.WP;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = A.atq_f32[b + e * cs];
+  return o;
+}
+
+// ---- tangent forward -----------------------------------------------------------------------------------------------
+// sum t_y and sum xhat t_y per channel: one pass over the padded rows of t_y and y (border rows of t_y are zeros)
+__global__ void __launch_bounds__(256) cb2_stats_kernel(const A2 A) {
+  __shared__ float red[8][2][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, c0 = (lane & 7) * 8;
+  const int64_t rows = (int64_t)A.g.N * (A.g.H + 2) * (A.g.W + 2);
+  const F8 mean = ld8f(A.w.mean + c0), rstd = ld8f(A.w.rstd + c0);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * 32;
+  for (int64_t r = (int64_t)blockIdx.x * 32 + warp * 4 + sub; r < rows; r += stride) {
+    const F8 t = ld8(A.w.ty + r * 64 + c0), yv = ld8(A.w.yb + r * 64 + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s0[e] += t.v[e];
+      s1[e] = fmaf((yv.v[e] - mean.v[e]) * rstd.v[e], t.v[e], s1[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 8); s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 16);
+    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8); s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[warp][0][c0 + e] = s0[e];
+      red[warp][1][c0 + e] = s1[e];
+    }
+  }
   __syncthreads();
-  if (warp < 4) {
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x >> 6, o = threadIdx.x & 63;
     float acc = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) acc += red[w][warp][lane];
-    const int o = 2 * lane + (warp & 1);
-    atomicAdd(&A.w.dsum[(2 + (warp >> 1)) * 64 + o], (double)acc);
+    for (int w = 0; w < 8; ++w) acc += red[w][k][o];
+    atomicAdd(&A.w.dsum[(2 + k) * 64 + o], (double)acc);
   }
 }
 
-// pooled finalize: gather t_y at the arg-max pixel, dxhat*, t_q.  lane <-> channel pair, warp <-> windows
+// pooled finalize: t_y at the arg-max pixel, dxhat*, t_q
 __global__ void __launch_bounds__(256) cb2_final_kernel(const A2 A) {
   const G2& g = A.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, c0 = (lane & 7) * 8;
   const double P = (double)g.N * g.H * g.W;
-  float rstd[2], mean_t[2], sdot[2], gam[2], tgam[2], tbet[2];
+  F8 rstd = ld8f(A.w.rstd + c0), mean_t, sdot, gam, tgam, tbet;
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int o = 2 * lane + e;
+  for (int e = 0; e < 8; ++e) {
+    const int o = c0 + e;
     const double mt = A.w.dsum[2 * 64 + o] / P;
-    mean_t[e] = (float)mt;
-    sdot[e] = (float)((A.w.dsum[3 * 64 + o] - mt * A.w.dsum[9 * 64 + o]) / P);
-    rstd[e] = A.w.rstd[o];
-    gam[e] = A.gamma ? A.gamma[o] : 1.f;
-    tgam[e] = A.t_gamma ? A.t_gamma[o] : 0.f;
-    tbet[e] = A.t_beta ? A.t_beta[o] : 0.f;
-    if (blockIdx.x == 0 && warp == 0) {
-      A.w.coef[5 * 64 + o] = mean_t[e];
-      A.w.coef[6 * 64 + o] = sdot[e];
+    mean_t.v[e] = (float)mt;
+    sdot.v[e] = (float)((A.w.dsum[3 * 64 + o] - mt * A.w.dsum[9 * 64 + o]) / P);
+    gam.v[e] = A.gamma ? A.gamma[o] : 1.f;
+    tgam.v[e] = A.t_gamma ? A.t_gamma[o] : 0.f;
+    tbet.v[e] = A.t_beta ? A.t_beta[o] : 0.f;
+    if (blockIdx.x == 0 && warp == 0 && sub == 0) {
+      A.w.coef[5 * 64 + o] = mean_t.v[e];
+      A.w.coef[6 * 64 + o] = sdot.v[e];
     }
   }
   const int64_t nwin = (int64_t)g.N * g.HP * g.WP;
   const int Wp = g.W + 2;
-  for (int64_t w = (int64_t)blockIdx.x * 8 + warp; w < nwin; w += (int64_t)gridDim.x * 8) {
+  for (int64_t w = (int64_t)blockIdx.x * 32 + warp * 4 + sub; w < nwin; w += (int64_t)gridDim.x * 32) {
     const int wp = (int)(w % g.WP);
     const int64_t t = w / g.WP;
     const int hp = (int)(t % g.HP), n = (int)(t / g.HP);
-    const int64_t pi = w * 64 + 2 * lane;
-    const uchar2 code = *reinterpret_cast<const uchar2*>(A.w.sel + pi);
-    const float2 xh = ldbf2(A.w.xh + pi);
-    // padded row of the window's top-left pixel (2hp, 2wp)
-    const int64_t r0 = ((int64_t)n * (g.H + 2) + 2 * hp + 1) * Wp + 2 * wp + 1;
-    const float ty0 = __bfloat162float(A.w.ty[(r0 + ((code.x >> 1) & 1) * Wp + (code.x & 1)) * 64 + 2 * lane]);
-    const float ty1 = __bfloat162float(A.w.ty[(r0 + ((code.y >> 1) & 1) * Wp + (code.y & 1)) * 64 + 2 * lane + 1]);
-    const float dx0 = (ty0 - mean_t[0] - xh.x * sdot[0]) * rstd[0], dx1 = (ty1 - mean_t[1] - xh.y * sdot[1]) * rstd[1];
-    stbf2(A.w.dxh + pi, dx0, dx1);
-    const float q0 = (code.x & 4) ? fmaf(gam[0], dx0, fmaf(tgam[0], xh.x, tbet[0])) : 0.f;
-    const float q1 = (code.y & 4) ? fmaf(gam[1], dx1, fmaf(tgam[1], xh.y, tbet[1])) : 0.f;
+    const int64_t pi = w * 64 + c0;
+    unsigned code[8];
+    ld_codes(A.w.sel + pi, code);
+    const F8 xh = ld8(A.w.xh + pi);
+    // the four candidate pixels of the window (padded rows r0, r0+1, r0+Wp, r0+Wp+1)
+    const bf16* t0 = A.w.ty + (((int64_t)n * (g.H + 2) + 2 * hp + 1) * Wp + 2 * wp + 1) * 64 + c0;
+    const F8 ta = ld8(t0), tb = ld8(t0 + 64), tc = ld8(t0 + (int64_t)Wp * 64), td = ld8(t0 + (int64_t)(Wp + 1) * 64);
+    F8 dx, tq;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const unsigned cd = code[e] & 3u;
+      const float ty = cd == 0 ? ta.v[e] : cd == 1 ? tb.v[e] : cd == 2 ? tc.v[e] : td.v[e];
+      dx.v[e] = (ty - mean_t.v[e] - xh.v[e] * sdot.v[e]) * rstd.v[e];
+      tq.v[e] = (code[e] & 4u) ? fmaf(gam.v[e], dx.v[e], fmaf(tgam.v[e], xh.v[e], tbet.v[e])) : 0.f;
+    }
+    st8(A.w.dxh + pi, dx);
     if (A.tq_nhwc) {
-      stbf2(A.tq_nhwc + ((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + 2 * lane, q0, q1);
+      st8(A.tq_nhwc + ((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + c0, tq);
     } else {
-      const int64_t b = (((int64_t)n * 64 + 2 * lane) * g.HP + hp) * g.WP + wp;
-      A.tq_f32[b] = q0;
-      A.tq_f32[b + (int64_t)g.HP * g.WP] = q1;
+      const int64_t b = (((int64_t)n * 64 + c0) * g.HP + hp) * g.WP + wp, cs = (int64_t)g.HP * g.WP;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) A.tq_f32[b + e * cs] = tq.v[e];
     }
   }
 }
 
 // ---- tangent backward ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 load_atq(const A2& A, int n, int hp, int wp, int lane) {
-  const G2& g = A.g;
-  if (A.atq_nhwc) return ldbf2(A.atq_nhwc + ((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + 2 * lane);
-  const int64_t b = (((int64_t)n * 64 + 2 * lane) * g.HP + hp) * g.WP + wp;
-  return make_float2(A.atq_f32[b], A.atq_f32[b + (int64_t)g.HP * g.WP]);
-}
-
 __global__ void __launch_bounds__(256) cb2_reduce_kernel(const A2 A) {
-  __shared__ float red[8][6][32];
+  __shared__ float red[8][3][64];
   const G2& g = A.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // S_at, S_atxh, S_adxh for the lane's two channels
+  const int sub = lane >> 3, c0 = (lane & 7) * 8;
+  float s0[8], s1[8], s2[8];       // S_at, S_atxh, S_adxh
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = s2[e] = 0.f;
   const int64_t nwin = (int64_t)g.N * g.HP * g.WP;
-  for (int64_t w = (int64_t)blockIdx.x * 8 + warp; w < nwin; w += (int64_t)gridDim.x * 8) {
+  for (int64_t w = (int64_t)blockIdx.x * 32 + warp * 4 + sub; w < nwin; w += (int64_t)gridDim.x * 32) {
     const int wp = (int)(w % g.WP);
     const int64_t t = w / g.WP;
     const int hp = (int)(t % g.HP), n = (int)(t / g.HP);
-    const int64_t pi = w * 64 + 2 * lane;
-    const uchar2 code = *reinterpret_cast<const uchar2*>(A.w.sel + pi);
-    const float2 xh = ldbf2(A.w.xh + pi), aq = ldbf2(A.w.aqm + pi), dx = ldbf2(A.w.dxh + pi);
-    float2 v = load_atq(A, n, hp, wp, lane);
-    v.x = (code.x & 4) ? v.x : 0.f;
-    v.y = (code.y & 4) ? v.y : 0.f;
-    s[0] += v.x; s[1] += v.y;
-    s[2] = fmaf(v.x, xh.x, s[2]); s[3] = fmaf(v.y, xh.y, s[3]);
-    s[4] = fmaf(aq.x, dx.x, s[4]); s[5] = fmaf(aq.y, dx.y, s[5]);
+    const int64_t pi = w * 64 + c0;
+    unsigned code[8];
+    ld_codes(A.w.sel + pi, code);
+    const F8 xh = ld8(A.w.xh + pi), aq = ld8(A.w.aqm + pi), dx = ld8(A.w.dxh + pi);
+    const F8 at = load_atq8(A, n, hp, wp, c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = (code[e] & 4u) ? at.v[e] : 0.f;
+      s0[e] += v;
+      s1[e] = fmaf(v, xh.v[e], s1[e]);
+      s2[e] = fmaf(aq.v[e], dx.v[e], s2[e]);
+    }
   }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) red[warp][k][lane] = s[k];
+  for (int e = 0; e < 8; ++e) {
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 8); s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 16);
+    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8); s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+    s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8); s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[warp][0][c0 + e] = s0[e];
+      red[warp][1][c0 + e] = s1[e];
+      red[warp][2][c0 + e] = s2[e];
+    }
+  }
   __syncthreads();
-  if (warp < 6) {
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x >> 6, o = threadIdx.x & 63;
     float acc = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) acc += red[w][warp][lane];
-    atomicAdd(&A.w.dsum[(4 + (warp >> 1)) * 64 + 2 * lane + (warp & 1)], (double)acc);
+    for (int w = 0; w < 8; ++w) acc += red[w][k][o];
+    atomicAdd(&A.w.dsum[(4 + k) * 64 + o], (double)acc);
   }
 }
 
@@ -356,51 +433,49 @@ __global__ void cb2_coef_kernel(const A2 A) {
   if (A.at_b) A.at_b[o] += (float)((double)cw * S_at + (double)cd * Sa + (double)d0 * P + (double)d1 * sx + (double)d2 * P * mean_t);
 }
 
-// dense rule on the conv-output grid: at_y (or the base a_y) as bf16 padded NHWC.  grid (N, H): one image row per block,
-// warp <-> pixels, lane <-> channel pair; the pooled window of a pixel is (y >> 1, x >> 1)
+// dense rule on the conv-output grid: at_y (or the base a_y) as bf16 padded NHWC.  grid (N, ceil(H/2)): the two image
+// rows of one pooled row per block; the pooled window of pixel (y, x) is (y >> 1, x >> 1)
 __global__ void __launch_bounds__(256) cb2_dense_kernel(const A2 A) {
   const G2& g = A.g;
-  const int n = blockIdx.x, y = blockIdx.y;
+  const int n = blockIdx.x, hp = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, c0 = (lane & 7) * 8;
   const float* c = A.w.coef;
-  const int o = 2 * lane;
-  const float2 c0 = make_float2(c[o], c[o + 1]), c1 = make_float2(c[64 + o], c[64 + o + 1]),
-               c2 = make_float2(c[128 + o], c[128 + o + 1]), c3 = make_float2(c[192 + o], c[192 + o + 1]),
-               c4 = make_float2(c[256 + o], c[256 + o + 1]);
-  const float2 mean = make_float2(A.w.mean[o], A.w.mean[o + 1]), rstd = make_float2(A.w.rstd[o], A.w.rstd[o + 1]);
-  const int hp = y >> 1, dy = y & 1;
+  const F8 k0 = ld8f(c + c0), k1 = ld8f(c + 64 + c0), k2 = ld8f(c + 128 + c0), k3 = ld8f(c + 192 + c0), k4 = ld8f(c + 256 + c0);
+  const F8 mean = ld8f(A.w.mean + c0), rstd = ld8f(A.w.rstd + c0);
+  const int y0 = 2 * hp;
+  const int npix = (y0 + 1 < g.H ? 2 : 1) * g.W;
   const bool row_pooled = hp < g.HP;
-  const int64_t prow = ((int64_t)n * (g.H + 2) + y + 1) * (g.W + 2) + 1;
-  bf16* dst = (A.base ? A.w.ay : A.w.aty) + prow * 64 + o;
-  const bf16* yb = A.w.yb + prow * 64 + o;
-  const bf16* ty = A.w.ty + prow * 64 + o;
-  for (int x = warp; x < g.W; x += 8) {
-    const float2 yv = ldbf2(yb + (int64_t)x * 64);
-    const float xh0 = (yv.x - mean.x) * rstd.x, xh1 = (yv.y - mean.y) * rstd.y;
-    float v0 = fmaf(xh0, c1.x, c0.x), v1 = fmaf(xh1, c1.y, c0.y);
-    if (!A.base) {
-      const float2 t = ldbf2(ty + (int64_t)x * 64);
-      v0 = fmaf(t.x, c2.x, v0);
-      v1 = fmaf(t.y, c2.y, v1);
-    }
+  bf16* out = A.base ? A.w.ay : A.w.aty;
+  for (int p = warp * 4 + sub; p < npix; p += 32) {
+    const int dy = p >= g.W ? 1 : 0, x = p - dy * g.W;
+    const int64_t off = ((((int64_t)n * (g.H + 2) + y0 + dy + 1) * (g.W + 2)) + x + 1) * 64 + c0;
+    const F8 yv = ld8(A.w.yb + off);
+    F8 t, aq, at;
+    if (!A.base) t = ld8(A.w.ty + off);
     const int wp = x >> 1;
-    if (row_pooled && wp < g.WP) {
-      const int64_t pi = ((((int64_t)n * g.HP + hp) * g.WP) + wp) * 64 + o;
-      const uchar2 code = *reinterpret_cast<const uchar2*>(A.w.sel + pi);
-      const unsigned here = (unsigned)(dy * 2 + (x & 1));
-      const bool h0 = (code.x & 3u) == here, h1 = (code.y & 3u) == here;
-      if (h0 || h1) {
-        const float2 aq = ldbf2(A.w.aqm + pi);
-        if (h0) v0 = fmaf(c4.x, aq.x, v0);
-        if (h1) v1 = fmaf(c4.y, aq.y, v1);
-        if (!A.base) {
-          const float2 at = load_atq(A, n, hp, wp, lane);
-          if (h0 && (code.x & 4)) v0 = fmaf(c3.x, at.x, v0);
-          if (h1 && (code.y & 4)) v1 = fmaf(c3.y, at.y, v1);
-        }
-      }
+    const bool pooled = row_pooled && wp < g.WP;
+    unsigned code[8];
+    if (pooled) {
+      const int64_t pi = ((((int64_t)n * g.HP + hp) * g.WP) + wp) * 64 + c0;
+      ld_codes(A.w.sel + pi, code);
+      aq = ld8(A.w.aqm + pi);
+      if (!A.base) at = load_atq8(A, n, hp, wp, c0);
     }
-    stbf2(dst + (int64_t)x * 64, v0, v1);
+    const unsigned here = (unsigned)(dy * 2 + (x & 1));
+    F8 v;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (yv.v[e] - mean.v[e]) * rstd.v[e];
+      float r = fmaf(xh, k1.v[e], k0.v[e]);
+      if (!A.base) r = fmaf(t.v[e], k2.v[e], r);
+      if (pooled && (code[e] & 3u) == here) {
+        r = fmaf(k4.v[e], aq.v[e], r);
+        if (!A.base && (code[e] & 4u)) r = fmaf(k3.v[e], at.v[e], r);
+      }
+      v.v[e] = r;
+    }
+    st8(out + off, v);
   }
 }
 
@@ -446,11 +521,12 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
   const int chunks = g.N < 8 ? g.N : (g.N < 64 ? 8 : 32);
   const dim3 per_channel(64, chunks);
   const int64_t rows = (int64_t)g.N * (g.H + 2) * (g.W + 2), nwin = (int64_t)g.N * g.HP * g.WP;
-  auto stream_grid = [](int64_t units) {
-    int64_t b = (units + 7) / 8;
+  auto stream_grid = [](int64_t units) {          // 32 rows / windows per block step, a few waves of persistent blocks
+    int64_t b = (units + 31) / 32;
     if (b > 8 * BB_SM_COUNT) b = 8 * BB_SM_COUNT;
     return (int)(b < 1 ? 1 : b);
   };
+  const dim3 dense_grid(g.N, (g.H + 1) / 2);
   const size_t pack_smem = 4 * (size_t)g.W * 65;
   int rc;
   if (pass == BB_PASS_BASE_BWD) {
@@ -462,7 +538,7 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
     cb2_pack_padded_kernel<<<dim3(g.N, g.H), 256, pack_smem, s>>>(nd.base[0], nd.dt[0], 64, g.H, g.W, A.w.xin);
     A.base = 1;
     cb2_coef_kernel<<<1, 64, 0, s>>>(A);
-    cb2_dense_kernel<<<dim3(g.N, g.H), 256, 0, s>>>(A);
+    cb2_dense_kernel<<<dense_grid, 256, 0, s>>>(A);
     bb_launch_tally += 8;
     BB_LAUNCH_CHECK();
     if ((rc = bb_pack_convw(nd.base[1], nd.dt[1], 64, 64, taps, 0, A.w.wf, 64, s))) return rc;
@@ -502,7 +578,7 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
   BB_CUDA_TRY(cudaMemsetAsync(A.w.dsum + 4 * 64, 0, sizeof(double) * 3 * 64, s));
   cb2_reduce_kernel<<<stream_grid(nwin), 256, 0, s>>>(A);
   cb2_coef_kernel<<<1, 64, 0, s>>>(A);
-  cb2_dense_kernel<<<dim3(g.N, g.H), 256, 0, s>>>(A);
+  cb2_dense_kernel<<<dense_grid, 256, 0, s>>>(A);
   bb_launch_tally += 4;
   BB_LAUNCH_CHECK();
   if ((rc = bb_pack_convw(nd.t[1], BB_F32, 64, 64, taps, 1, A.w.twd, 64, s))) return rc;
