@@ -531,8 +531,9 @@ __global__ void __launch_bounds__(NT) cb_reduce_kernel(const CbArgs A) {
   const int tcap = g.R * g.WP * g.O;
   // pooled arrays of the tile; in NHWC mode the transposed NCHW staging tile `ins` is not needed and its place is taken
   // by the adjoint-tangent rows themselves ([rows][WP][64] bf16, copied row by row out of the padded array)
+  const bool nhwc_mode = A.atq_nhwc != nullptr || A.tq_nhwc != nullptr;     // (the launcher sizes shared memory by this)
   const bool nhwc_in = !BASE && A.atq_nhwc != nullptr;
-  PT* xh_s = reinterpret_cast<PT*>(ins + (nhwc_in ? 0 : g.O * g.wpitch));
+  PT* xh_s = reinterpret_cast<PT*>(ins + (nhwc_mode ? 0 : g.O * g.wpitch));
   PT* aq_s = xh_s + tcap;
   PT* dx_s = aq_s + tcap;
   unsigned char* sel_s = reinterpret_cast<unsigned char*>(dx_s + tcap);
