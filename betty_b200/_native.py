@@ -124,8 +124,11 @@ def lib() -> C.CDLL:
                 raise NativeError(
                     f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ "
                     "as g; g.build()').  betty_b200 has no CPU or PyTorch fallback.")
-            l = C.CDLL(LIB_PATH)
+            alt = os.environ.get("BB200_LIB")                   # A/B runs of tools/ against another build
+            l = C.CDLL(alt or LIB_PATH)
             for name, (argtypes, _) in _SIGS.items():
+                if alt and not hasattr(l, name):
+                    continue
                 fn = getattr(l, name)
                 fn.argtypes = argtypes
                 fn.restype = C.c_int64 if name.endswith("_bytes") and name != "bb_node_bytes" and name != "bb_kloop_ws_bytes" else C.c_int

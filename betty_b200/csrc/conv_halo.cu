@@ -40,9 +40,7 @@ constexpr int NTHREADS = 192;
 constexpr int BAND_ROWS = 256;                 // TMA box limit; a band needs 128 + 2*(W+2) + 2 rows
 constexpr int BAND_BYTES = BAND_ROWS * 128;    // 32 KB
 constexpr int W_TILE = 64 * 128;               // one tap's weights: 64 rows (n) x 64 ch
-constexpr int MAXBAND = 4;                     // activation bands in flight (as many as fit)
-constexpr int WRING = 4;                       // ring slots for the streamed weights of pair 1
-constexpr int NTHREADS_HALO = 224;             // + warp 6: producer of the streamed weights
+constexpr int MAXBAND = 4;                     // activation bands in flight: 4 with one operand pair, 2 with two
 
 struct alignas(64) HaloArgs {
   CUtensorMap a[2];          // padded activation as a matrix [rows][64] (rank-3 map, batch 1), box (64, band_rows)
@@ -75,24 +73,21 @@ __device__ __forceinline__ uint64_t desc_k_bo(uint32_t saddr, uint32_t bo) {
   return d;
 }
 
-// Shared memory: [9 x 8 KB] weights of pair 0 (resident) | [WRING x 8 KB] ring for the weights of pair 1 (streamed per
-// tile: 72 KB from L2, still 3.4x less fill than one box per tap) | [nband x band_alloc] activation bands | barriers.
-// With both pairs resident only two bands fit, and a band's refill latency (~3 us under load) then sits on the critical
-// path of every 0.6 us of MMA work (tensor pipe 31 %, profiles/r02_conv_halo_v0_ncu.md); three or four bands in flight
-// hide it.
-__global__ void __launch_bounds__(NTHREADS_HALO, 1) conv_halo_kernel(const __grid_constant__ HaloArgs G) {
+// Shared memory: [npairs x 9 x 8 KB] weights (resident for the whole kernel) | [NB x band_alloc] activation bands |
+// barriers.  The MMA issue loop must stay free of waits: a variant that streamed the second pair's weights through a
+// ring (mbarrier wait + commit per tap inside the tap loop) ran 1.9x slower even with the ring path never taken
+// (554 vs 297 us at 800x42x42, tools/halo_bench.py), so both pairs' weights stay resident and two bands are in flight.
+template <int NB, bool BF16OUT>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs G) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* wsm = smem;                                    // [9][W_TILE] pair 0
-  uint8_t* ring = smem + 9 * W_TILE;                      // [WRING][W_TILE] pair 1 (npairs == 2)
-  uint8_t* bands = ring + (G.npairs > 1 ? WRING * W_TILE : 0);
-  const int NB = G.nband;
+  uint8_t* wsm = smem;                                    // [npairs][9][W_TILE]
+  uint8_t* bands = smem + (size_t)G.npairs * 9 * W_TILE;  // [NB][band_alloc]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bands + (size_t)NB * G.band_alloc);
   const uint32_t wfull = smem_u32(bars);
   const uint32_t bfull0 = smem_u32(bars + 1), bempty0 = smem_u32(bars + 1 + MAXBAND);
-  const uint32_t rfull0 = smem_u32(bars + 1 + 2 * MAXBAND), rempty0 = smem_u32(bars + 1 + 2 * MAXBAND + WRING);
-  const uint32_t accf0 = smem_u32(bars + 1 + 2 * MAXBAND + 2 * WRING), acce0 = accf0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * MAXBAND + 2 * WRING);
+  const uint32_t accf0 = smem_u32(bars + 1 + 2 * MAXBAND), acce0 = accf0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * MAXBAND);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -100,10 +95,6 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) conv_halo_kernel(const __gri
     for (int b = 0; b < MAXBAND; ++b) {
       mbar_init(bfull0 + 8 * b, 1);
       mbar_init(bempty0 + 8 * b, 1);
-    }
-    for (int b = 0; b < WRING; ++b) {
-      mbar_init(rfull0 + 8 * b, 1);
-      mbar_init(rempty0 + 8 * b, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf0 + 8 * b, 1);
@@ -125,8 +116,9 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) conv_halo_kernel(const __gri
         tma_prefetch_desc(&G.a[p]);
         tma_prefetch_desc(&G.b[p]);
       }
-      mbar_expect_tx(wfull, (uint32_t)(9 * W_TILE));
-      for (int t = 0; t < 9; ++t) tma_load_3d(smem_u32(wsm + t * W_TILE), &G.b[0], wfull, t * 64, 0, 0);
+      mbar_expect_tx(wfull, (uint32_t)(G.npairs * 9 * W_TILE));
+      for (int p = 0; p < G.npairs; ++p)
+        for (int t = 0; t < 9; ++t) tma_load_3d(smem_u32(wsm + (p * 9 + t) * W_TILE), &G.b[p], wfull, t * 64, 0, 0);
       int git = 0;
       for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
         const int row0 = tile * BM - G.Wp - 1;             // first band row (may be negative: zero fill)
@@ -138,26 +130,13 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) conv_halo_kernel(const __gri
         }
       }
     }
-  } else if (warp == 6) {
-    // ---------------- TMA producer: the streamed weights of pair 1 ----------------
-    if (lane == 0 && G.npairs > 1) {
-      int wit = 0;
-      for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
-        for (int t = 0; t < 9; ++t, ++wit) {
-          const int sl = wit % WRING;
-          if (wit >= WRING) mbar_wait(rempty0 + 8 * sl, ((wit / WRING) - 1) & 1);
-          mbar_expect_tx(rfull0 + 8 * sl, (uint32_t)W_TILE);
-          tma_load_3d(smem_u32(ring + sl * W_TILE), &G.b[1], rfull0 + 8 * sl, t * 64, 0, 0);
-        }
-      }
-    }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(BM, BN, false, false);
       mbar_wait(wfull, 0);
       tc_fence_after();
-      int git = 0, lt = 0, wit = 0;
+      int git = 0, lt = 0;
       for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         if (lt >= 2) {
@@ -176,23 +155,10 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) conv_halo_kernel(const __gri
             const int dy = G.flip ? 1 - i : i - 1, dx = G.flip ? 1 - j : j - 1;
             const uint32_t a0 = band + (uint32_t)((G.Wp + 1 + dy * G.Wp + dx) * 128);
             const uint32_t bo = G.bo_mode ? ((a0 >> 7) & 7u) : 0u;
-            uint32_t b0;
-            int sl = 0;
-            if (p == 0) {
-              b0 = smem_u32(wsm + t * W_TILE);
-            } else {
-              sl = wit % WRING;
-              mbar_wait(rfull0 + 8 * sl, (wit / WRING) & 1);
-              tc_fence_after();
-              b0 = smem_u32(ring + sl * W_TILE);
-            }
+            const uint32_t b0 = smem_u32(wsm + (p * 9 + t) * W_TILE);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tacc, desc_k_bo(a0 + k * 32, bo), desc_k(b0 + k * 32), idesc, (p > 0 || t > 0 || k > 0) ? 1u : 0u);
-            if (p > 0) {
-              umma_commit(rempty0 + 8 * sl);
-              ++wit;
-            }
           }
           umma_commit(bempty0 + 8 * b);
         }
@@ -200,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) conv_halo_kernel(const __gri
       }
     }
     __syncwarp();
-  } else if (warp >= 2 && warp <= 5) {
+  } else {
     // ---------------- epilogue (warps 2..5) ----------------
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -229,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS_HALO, 1) conv_halo_kernel(const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(acce0 + 8 * buf);
         }
-        if (G.out_bf16) {
+        if (BF16OUT) {
           // bf16 padded-NHWC output: this thread's pixel row, 32 channels = 64 contiguous bytes; border rows are zeros
           if (row >= G.total_rows) continue;
           uint4* q = reinterpret_cast<uint4*>(G.out_bf16 + row * 64 + c * 32);
@@ -431,23 +397,33 @@ int bb_conv_halo_run(int N, int H, int W, int npairs, const void* const* act_pad
   // (setting the field to (start >> 7) & 7 gives wrong products); BB200_HALO_BO=1 keeps the other convention testable
   static const int bo_env = getenv("BB200_HALO_BO") ? atoi(getenv("BB200_HALO_BO")) : 0;
   G.bo_mode = bo_env;
+  G.band_rows = (G.band_rows + 7) & ~7;
   int rc;
   for (int p = 0; p < npairs; ++p) {
     if ((rc = bb_tma_map_2d(&G.a[p], act_padded[p], G.total_rows, 64, 64, G.band_rows))) return rc;
     if ((rc = bb_tma_map_2d(&G.b[p], wmat[p], 64, 9 * 64, 9 * 64, 64))) return rc;
   }
   G.band_alloc = (G.band_rows * 128 + 1023) & ~1023;
-  const size_t fixed = 9 * W_TILE + (npairs > 1 ? WRING * W_TILE : 0) + 512 + 1024;
-  int nb = (int)((227 * 1024 - fixed) / (size_t)G.band_alloc);
-  if (nb > MAXBAND) nb = MAXBAND;
-  if (nb < 2) return BB_ERR_UNSUPPORTED;
+  const size_t fixed = (size_t)npairs * 9 * W_TILE + 512 + 1024;
+  const int fit = (int)((227 * 1024 - fixed) / (size_t)G.band_alloc);
+  if (fit < 2) return BB_ERR_UNSUPPORTED;
+  const int nb = fit >= 4 ? 4 : 2;
   G.nband = nb;
   const size_t smem = fixed + (size_t)nb * G.band_alloc;
-  static BbOncePerDevice configured;
-  if (configured.need())
-    BB_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int grid = G.ntiles < BB_SM_COUNT ? G.ntiles : BB_SM_COUNT;
-  conv_halo_kernel<<<grid, NTHREADS_HALO, smem, s>>>(G);
+  const bool bf = G.out_bf16 != nullptr;
+  static BbOncePerDevice configured[4];
+  auto launch = [&](auto kern, int slot) -> int {
+    if (configured[slot].need())
+      BB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<grid, NTHREADS, smem, s>>>(G);
+    return BB_OK;
+  };
+  if (nb == 4)
+    rc = bf ? launch(conv_halo_kernel<4, true>, 0) : launch(conv_halo_kernel<4, false>, 1);
+  else
+    rc = bf ? launch(conv_halo_kernel<2, true>, 2) : launch(conv_halo_kernel<2, false>, 3);
+  if (rc) return rc;
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();
   return BB_OK;
