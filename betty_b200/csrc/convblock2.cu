@@ -435,47 +435,107 @@ __global__ void cb2_coef_kernel(const A2 A) {
 
 // dense rule on the conv-output grid: at_y (or the base a_y) as bf16 padded NHWC.  grid (N, ceil(H/2)): the two image
 // rows of one pooled row per block; the pooled window of pixel (y, x) is (y >> 1, x >> 1)
+// A warp takes DU consecutive 2x2 windows per step: lane group `sub` owns one pixel of the window (16 bytes = 8 channels
+// per lane), the window's codes / pooled adjoints are one broadcast read.  All loads of the DU windows are issued before
+// the first use (the row-per-block version with one load batch per iteration sat at 1.9 TB/s).  Windows cover
+// ceil(H/2) x ceil(W/2), so the odd last row / column (no pooled contribution) is written too.
+constexpr int DU = 4;
+__device__ __forceinline__ void unpack8(const uint4& r, float (&o)[8]) {
+  o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
+  o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
+  o[4] = __uint_as_float(r.z << 16); o[5] = __uint_as_float(r.z & 0xffff0000u);
+  o[6] = __uint_as_float(r.w << 16); o[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+template <bool BASE, bool ATQF32>
 __global__ void __launch_bounds__(256) cb2_dense_kernel(const A2 A) {
   const G2& g = A.g;
-  const int n = blockIdx.x, hp = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, c0 = (lane & 7) * 8;
+  const int dy = sub >> 1, dx = sub & 1;
   const float* c = A.w.coef;
-  const F8 k0 = ld8f(c + c0), k1 = ld8f(c + 64 + c0), k2 = ld8f(c + 128 + c0), k3 = ld8f(c + 192 + c0), k4 = ld8f(c + 256 + c0);
-  const F8 mean = ld8f(A.w.mean + c0), rstd = ld8f(A.w.rstd + c0);
-  const int y0 = 2 * hp;
-  const int npix = (y0 + 1 < g.H ? 2 : 1) * g.W;
-  const bool row_pooled = hp < g.HP;
-  bf16* out = A.base ? A.w.ay : A.w.aty;
-  for (int p = warp * 4 + sub; p < npix; p += 32) {
-    const int dy = p >= g.W ? 1 : 0, x = p - dy * g.W;
-    const int64_t off = ((((int64_t)n * (g.H + 2) + y0 + dy + 1) * (g.W + 2)) + x + 1) * 64 + c0;
-    const F8 yv = ld8(A.w.yb + off);
-    F8 t, aq, at;
-    if (!A.base) t = ld8(A.w.ty + off);
-    const int wp = x >> 1;
-    const bool pooled = row_pooled && wp < g.WP;
-    unsigned code[8];
-    if (pooled) {
-      const int64_t pi = ((((int64_t)n * g.HP + hp) * g.WP) + wp) * 64 + c0;
-      ld_codes(A.w.sel + pi, code);
-      aq = ld8(A.w.aqm + pi);
-      if (!A.base) at = load_atq8(A, n, hp, wp, c0);
-    }
-    const unsigned here = (unsigned)(dy * 2 + (x & 1));
-    F8 v;
+  // r = k0 + k1 xhat + k2 t  with xhat = (y - mean) rstd  ->  e0 + e1 y + k2 t
+  F8 e0 = ld8f(c + c0), e1 = ld8f(c + 64 + c0);
+  const F8 k2 = ld8f(c + 128 + c0), k3 = ld8f(c + 192 + c0), k4 = ld8f(c + 256 + c0);
+  {
+    const F8 mean = ld8f(A.w.mean + c0), rstd = ld8f(A.w.rstd + c0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float xh = (yv.v[e] - mean.v[e]) * rstd.v[e];
-      float r = fmaf(xh, k1.v[e], k0.v[e]);
-      if (!A.base) r = fmaf(t.v[e], k2.v[e], r);
-      if (pooled && (code[e] & 3u) == here) {
-        r = fmaf(k4.v[e], aq.v[e], r);
-        if (!A.base && (code[e] & 4u)) r = fmaf(k3.v[e], at.v[e], r);
-      }
-      v.v[e] = r;
+      e1.v[e] *= rstd.v[e];
+      e0.v[e] -= e1.v[e] * mean.v[e];
     }
-    st8(out + off, v);
+  }
+  const int HC = (g.H + 1) >> 1, WC = (g.W + 1) >> 1;
+  const int64_t total = (int64_t)g.N * HC * WC;
+  const bf16* __restrict__ yb = A.w.yb;
+  const bf16* __restrict__ ty = A.w.ty;
+  const bf16* __restrict__ aqm = A.w.aqm;
+  const unsigned char* __restrict__ sel = A.w.sel;
+  bf16* __restrict__ out = BASE ? A.w.ay : A.w.aty;
+  const int64_t step = (int64_t)gridDim.x * 8 * DU;
+  for (int64_t w0 = ((int64_t)blockIdx.x * 8 + warp) * DU; w0 < total; w0 += step) {
+    int n = (int)(w0 / (HC * WC));
+    int rem = (int)(w0 - (int64_t)n * HC * WC);
+    int hp = rem / WC, wp = rem - hp * WC;
+    uint4 yq[DU], tq[DU], aq[DU], at[DU];
+    F8 atf[ATQF32 ? DU : 1];
+    uint2 cd[DU];
+    int64_t off[DU];
+    bool inb[DU], pooled[DU];
+#pragma unroll
+    for (int u = 0; u < DU; ++u) {
+      const int y = 2 * hp + dy, x = 2 * wp + dx;
+      inb[u] = w0 + u < total && y < g.H && x < g.W;
+      pooled[u] = inb[u] && hp < g.HP && wp < g.WP;
+      off[u] = ((((int64_t)n * (g.H + 2) + y + 1) * (g.W + 2)) + x + 1) * 64 + c0;
+      if (inb[u]) {
+        yq[u] = *reinterpret_cast<const uint4*>(yb + off[u]);
+        if (!BASE) tq[u] = *reinterpret_cast<const uint4*>(ty + off[u]);
+      }
+      if (pooled[u]) {
+        const int64_t pi = ((((int64_t)n * g.HP + hp) * g.WP) + wp) * 64 + c0;
+        cd[u] = *reinterpret_cast<const uint2*>(sel + pi);
+        aq[u] = *reinterpret_cast<const uint4*>(aqm + pi);
+        if (!BASE) {
+          if (ATQF32)
+            atf[ATQF32 ? u : 0] = load_atq8(A, n, hp, wp, c0);
+          else
+            at[u] = *reinterpret_cast<const uint4*>(A.atq_nhwc + ((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + c0);
+        }
+      }
+      if (++wp == WC) {
+        wp = 0;
+        if (++hp == HC) {
+          hp = 0;
+          ++n;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DU; ++u) {
+      if (!inb[u]) continue;
+      float yv[8], t[8], a[8], b[8];
+      unpack8(yq[u], yv);
+      if (!BASE) unpack8(tq[u], t);
+      if (pooled[u]) {
+        unpack8(aq[u], a);
+        if (!BASE && !ATQF32) unpack8(at[u], b);
+      }
+      F8 v;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float r = fmaf(yv[e], e1.v[e], e0.v[e]);
+        if (!BASE) r = fmaf(t[e], k2.v[e], r);
+        if (pooled[u]) {
+          const unsigned code = ((e < 4 ? cd[u].x : cd[u].y) >> (8 * (e & 3))) & 0xffu;
+          if ((code & 3u) == (unsigned)sub) {
+            r = fmaf(k4.v[e], a[e], r);
+            if (!BASE && (code & 4u)) r = fmaf(k3.v[e], ATQF32 ? atf[ATQF32 ? u : 0].v[e] : b[e], r);
+          }
+        }
+        v.v[e] = r;
+      }
+      st8(out + off[u], v);
+    }
   }
 }
 
@@ -526,7 +586,8 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
     if (b > 8 * BB_SM_COUNT) b = 8 * BB_SM_COUNT;
     return (int)(b < 1 ? 1 : b);
   };
-  const dim3 dense_grid(g.N, (g.H + 1) / 2);
+  const int64_t dense_windows = (int64_t)g.N * ((g.H + 1) / 2) * ((g.W + 1) / 2);
+  const int dense_grid = (int)std::min<int64_t>((dense_windows + 8 * DU - 1) / (8 * DU), (int64_t)16 * BB_SM_COUNT);
   const size_t pack_smem = 4 * (size_t)g.W * 65;
   int rc;
   if (pass == BB_PASS_BASE_BWD) {
@@ -538,7 +599,7 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
     cb2_pack_padded_kernel<<<dim3(g.N, g.H), 256, pack_smem, s>>>(nd.base[0], nd.dt[0], 64, g.H, g.W, A.w.xin);
     A.base = 1;
     cb2_coef_kernel<<<1, 64, 0, s>>>(A);
-    cb2_dense_kernel<<<dense_grid, 256, 0, s>>>(A);
+    cb2_dense_kernel<true, false><<<dense_grid, 256, 0, s>>>(A);
     bb_launch_tally += 8;
     BB_LAUNCH_CHECK();
     if ((rc = bb_pack_convw(nd.base[1], nd.dt[1], 64, 64, taps, 0, A.w.wf, 64, s))) return rc;
@@ -578,7 +639,10 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
   BB_CUDA_TRY(cudaMemsetAsync(A.w.dsum + 4 * 64, 0, sizeof(double) * 3 * 64, s));
   cb2_reduce_kernel<<<stream_grid(nwin), 256, 0, s>>>(A);
   cb2_coef_kernel<<<1, 64, 0, s>>>(A);
-  cb2_dense_kernel<<<dense_grid, 256, 0, s>>>(A);
+  if (A.atq_nhwc)
+    cb2_dense_kernel<false, false><<<dense_grid, 256, 0, s>>>(A);
+  else
+    cb2_dense_kernel<false, true><<<dense_grid, 256, 0, s>>>(A);
   bb_launch_tally += 4;
   BB_LAUNCH_CHECK();
   if ((rc = bb_pack_convw(nd.t[1], BB_F32, 64, 64, taps, 1, A.w.twd, 64, s))) return rc;
