@@ -19,6 +19,7 @@
 // So neither y-sized tangents nor y-sized adjoints exist: per iteration the block reads x and streams pooled-size
 // arrays (a quarter of y).  All arithmetic fp32 (x / y / q are read in the dtype the forward recorded).
 // Verified against the composition of the three member rules (oracle/plan_interp.py) and autograd's double backward.
+#include <algorithm>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -70,6 +71,8 @@ struct CbWs {
   void* xh;         // [N*HP*WP*O] NHWC xhat at the arg-max pixel          (fp32 or bf16, CbGeom::ps)
   void* dxh;        // [N*HP*WP*O] NHWC dxhat at the arg-max pixel (per iteration)
   void* aqm;        // [N*HP*WP*O] NHWC mask * a_q
+  void* pfrag;      // [ceil(N*HP*WP/16)][8][32] uint4: patch fragments of the tensor-core path (O == 64 only)
+  void* pfragT;     // same size: the transposed fragments (reduce kernel)
   size_t bytes;
 };
 
@@ -101,6 +104,11 @@ CbWs cb_layout(void* base, const CbGeom& g) {
   w.xh = take(ps * pooled);
   w.dxh = take(ps * pooled);
   w.aqm = take(ps * pooled);
+  if (g.O == 64) {
+    const size_t nmt = ((size_t)g.N * g.HP * g.WP + 15) / 16;
+    w.pfrag = take(nmt * 8 * 32 * 16);
+    w.pfragT = take(nmt * 8 * 32 * 16);
+  }
   w.bytes = at;
   return w;
 }
@@ -668,6 +676,369 @@ __global__ void __launch_bounds__(64) cb_finish_kernel(const CbArgs A, int CKK) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core path of the K-loop kernels (O == 64, bf16 pooled arrays, NHWC neighbours on both sides).
+//
+// x is data, so the 3x3xC patch of each of the four candidate pixels of a window never changes during a call: the base
+// pass writes them once as bf16 mma.sync fragments (`pfrag`: rows = 16 consecutive windows, columns = the C*9 taps
+// padded to 32; `pfragT`: the transpose).  The tangent-forward kernel is then, per 16 windows, 64 m16n8k16 products
+// [windows x taps] x [taps x channels] for the four candidates plus a register select by the arg-max code; the
+// reduce kernel is 64 products [taps x windows] x [windows x channels] of the code-masked adjoint tangent.  The SIMT
+// kernels above spent ~105 instructions per (window, channel) on 27 multiply-adds; column C*9 of the patch matrix
+// holds 1, so the plain channel sum of the masked adjoint falls out of the same product.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MT = 16;            // windows per m-tile
+constexpr int STG_V = 144;        // bytes per staged row of 64 bf16 (128 + 16: conflict-free for ldmatrix and pair reads)
+constexpr int STG_C = 80;         // bytes per staged row of 64 code bytes
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// value of the patch matrix: window w (flat over N*HP*WP), candidate d = dy*2+dx, column k = (c*3+i)*3+j
+template <int C>
+__device__ __forceinline__ float patch_value(const CbArgs& A, int64_t w, int64_t total, int d, int k) {
+  const CbGeom& g = A.g;
+  if (w >= total || k > C * 9) return 0.f;
+  if (k == C * 9) return 1.f;
+  const int wp = (int)(w % g.WP);
+  const int64_t r = w / g.WP;
+  const int hp = (int)(r % g.HP), n = (int)(r / g.HP);
+  const int c = k / 9, i = (k % 9) / 3, j = k % 3;
+  const int iy = 2 * hp + (d >> 1) + i - g.ph, ix = 2 * wp + (d & 1) + j - g.pw;
+  if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
+  return bb::ldf(A.x, (((int64_t)n * C + c) * g.H + iy) * g.W + ix, A.dtx);
+}
+
+// one thread per (m-tile, fragment q, lane): q < 8 -> pfrag[d*2+ks], q >= 8 -> pfragT[d*2+mk]
+template <int C>
+__global__ void __launch_bounds__(256) cb_patch_frag_kernel(const CbArgs A, int64_t nmt) {
+  const int64_t total = (int64_t)A.g.N * A.g.HP * A.g.WP;
+  const int64_t nthreads = nmt * 16 * 32;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads; i += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = (int)(i & 31), q = (int)((i >> 5) & 15);
+    const int64_t mt = i >> 9;
+    const int gq = lane >> 2, t = lane & 3;
+    const int d = (q & 7) >> 1, hi = q & 1;
+    const int64_t w0 = mt * MT;
+    float v[8];
+    if (q < 8) {
+      // A operand of the forward product: rows = windows, columns = taps hi*16 ..
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int row = gq + ((e >> 1) & 1) * 8, k = hi * 16 + 2 * t + (e & 1) + (e >> 2) * 8;
+        v[e] = patch_value<C>(A, w0 + row, total, d, k);
+      }
+    } else {
+      // A operand of the reduce product: rows = taps hi*16 .., columns = windows
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = hi * 16 + gq + ((e >> 1) & 1) * 8, wl = 2 * t + (e & 1) + (e >> 2) * 8;
+        v[e] = patch_value<C>(A, w0 + wl, total, d, k);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    uint4* dst = reinterpret_cast<uint4*>(q < 8 ? A.w.pfrag : A.w.pfragT);
+    dst[(mt * 8 + (q & 7)) * 32 + lane] = o;
+  }
+}
+
+// padded-NHWC pixel index of window w (the fused neighbour's [N][HP+2][WP+2][64] layout)
+__device__ __forceinline__ int64_t padded_pixel(const CbGeom& g, int64_t w) {
+  const int wp = (int)(w % g.WP);
+  const int64_t r = w / g.WP;
+  const int hp = (int)(r % g.HP);
+  const int64_t n = r / g.HP;
+  return ((n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) cb_tf_mma_kernel(const CbArgs A, int64_t nmt) {
+  constexpr int CKK = C * 9;
+  __shared__ uint2 bfrag[8 * 2 * 32];
+  __shared__ __align__(16) float cst[6][64];                 // rstd, e_x, e_0, c_y, c_x, c_0
+  extern __shared__ __align__(16) uint8_t stage_raw[];         // [8 warps][MT * (STG_C + 2 * STG_V)]
+  const CbGeom& g = A.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int64_t total = (int64_t)g.N * g.HP * g.WP;
+  if (tid < 64) {
+    const int o = tid;
+    const double invP = 1.0 / ((double)g.N * g.HO * g.WO);
+    double d0 = 0, d1 = 0;
+    for (int k = 0; k < CKK; ++k) {
+      const double tw = A.t_W[o * CKK + k];
+      d0 += tw * A.w.s[k];
+      d1 += tw * A.w.G[o * KP + k];
+    }
+    const float tb = A.t_b ? A.t_b[o] : 0.f;
+    const double mt = d0 * invP + tb;
+    const double sx = A.w.sx[o];
+    const float mean_t = (float)mt;
+    const float sdot = (float)((d1 + tb * sx - mt * sx) * invP);
+    const float rstd = A.w.rstd[o];
+    const float gam = A.gamma ? A.gamma[o] : 1.f, tgam = A.t_gamma ? A.t_gamma[o] : 0.f;
+    const float tbeta = A.t_beta ? A.t_beta[o] : 0.f;
+    if (blockIdx.x == 0) {
+      A.w.mean_t[o] = mean_t;
+      A.w.sdot[o] = sdot;
+    }
+    cst[0][o] = rstd;
+    cst[1][o] = -sdot * rstd;
+    cst[2][o] = (tb - mean_t) * rstd;
+    cst[3][o] = gam * rstd;
+    cst[4][o] = tgam - gam * rstd * sdot;
+    cst[5][o] = tbeta + gam * rstd * (tb - mean_t);
+  }
+  for (int i = tid; i < 8 * 2 * 32; i += 256) {
+    const int ln = i & 31, ks = (i >> 5) & 1, j = i >> 6;
+    const int o = j * 8 + (ln >> 2), k0 = ks * 16 + 2 * (ln & 3);
+    auto tw = [&](int k) { return k < CKK ? A.t_W[o * CKK + k] : 0.f; };
+    bfrag[i] = make_uint2(pack_bf16(tw(k0), tw(k0 + 1)), pack_bf16(tw(k0 + 8), tw(k0 + 9)));
+  }
+  __syncthreads();
+  uint8_t* codes_s = stage_raw + warp * (MT * (STG_C + 2 * STG_V));
+  uint8_t* xh_s = codes_s + MT * STG_C;
+  uint8_t* tq_s = xh_s + MT * STG_V;
+  const uint4* pf = reinterpret_cast<const uint4*>(A.w.pfrag);
+  const uint8_t* xhg = reinterpret_cast<const uint8_t*>(A.w.xh);
+  uint8_t* dxg = reinterpret_cast<uint8_t*>(A.w.dxh);
+  const int srow = lane >> 1, shalf = lane & 1;               // staging role: (window row, 32-channel half)
+  for (int64_t mt = (int64_t)blockIdx.x * 8 + warp; mt < nmt; mt += (int64_t)gridDim.x * 8) {
+    const int64_t w0 = mt * MT;
+    uint4 af[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) af[q] = ldg_nc16(pf + (mt * 8 + q) * 32 + lane);
+    const int64_t ws = w0 + srow;
+    const bool live = ws < total;
+    {
+      uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, x0 = c0, x1 = c0, x2 = c0, x3 = c0;
+      if (live) {
+        const uint8_t* cs = A.w.sel + ws * 64 + shalf * 32;
+        c0 = ldg_nc16(cs); c1 = ldg_nc16(cs + 16);
+        const uint8_t* xs = xhg + (ws * 64 + shalf * 32) * 2;
+        x0 = ldg_nc16(xs); x1 = ldg_nc16(xs + 16); x2 = ldg_nc16(xs + 32); x3 = ldg_nc16(xs + 48);
+      }
+      uint4* cd = reinterpret_cast<uint4*>(codes_s + srow * STG_C + shalf * 32);
+      cd[0] = c0; cd[1] = c1;
+      uint4* xd = reinterpret_cast<uint4*>(xh_s + srow * STG_V + shalf * 64);
+      xd[0] = x0; xd[1] = x1; xd[2] = x2; xd[3] = x3;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float acc[4][4][4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[d][j][r] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint2 b = bfrag[((h * 4 + j) * 2 + ks) * 32 + lane];
+#pragma unroll
+          for (int d = 0; d < 4; ++d) mma16816(acc[d][j], af[d * 2 + ks], b.x, b.y);
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = (h * 4 + j) * 8 + 2 * t;
+        const float2 k_r = *reinterpret_cast<const float2*>(&cst[0][col]), k_ex = *reinterpret_cast<const float2*>(&cst[1][col]);
+        const float2 k_e0 = *reinterpret_cast<const float2*>(&cst[2][col]), k_cy = *reinterpret_cast<const float2*>(&cst[3][col]);
+        const float2 k_cx = *reinterpret_cast<const float2*>(&cst[4][col]), k_c0 = *reinterpret_cast<const float2*>(&cst[5][col]);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int row = gq + 8 * rr;
+          const unsigned cp = *reinterpret_cast<const unsigned short*>(codes_s + row * STG_C + col);
+          uint32_t* xp = reinterpret_cast<uint32_t*>(xh_s + row * STG_V + col * 2);
+          const uint32_t xr = *xp;
+          const float xa = __uint_as_float(xr << 16), xb = __uint_as_float(xr & 0xffff0000u);
+          const unsigned ca = cp & 0xffu, cb = cp >> 8;
+          const unsigned sa = ca & 3u, sb = cb & 3u;
+          const float ta = sa == 0 ? acc[0][j][2 * rr] : sa == 1 ? acc[1][j][2 * rr] : sa == 2 ? acc[2][j][2 * rr] : acc[3][j][2 * rr];
+          const float tb2 = sb == 0 ? acc[0][j][2 * rr + 1] : sb == 1 ? acc[1][j][2 * rr + 1] : sb == 2 ? acc[2][j][2 * rr + 1]
+                                                                                                    : acc[3][j][2 * rr + 1];
+          const float da = fmaf(k_r.x, ta, fmaf(k_ex.x, xa, k_e0.x)), db = fmaf(k_r.y, tb2, fmaf(k_ex.y, xb, k_e0.y));
+          const float qa = (ca & 4u) ? fmaf(k_cy.x, ta, fmaf(k_cx.x, xa, k_c0.x)) : 0.f;
+          const float qb = (cb & 4u) ? fmaf(k_cy.y, tb2, fmaf(k_cx.y, xb, k_c0.y)) : 0.f;
+          *xp = pack_bf16(da, db);                                            // dxhat* over xhat* (same owner thread)
+          *reinterpret_cast<uint32_t*>(tq_s + row * STG_V + col * 2) = pack_bf16(qa, qb);
+        }
+      }
+    }
+    __syncwarp();
+    if (live) {
+      const uint4* xd = reinterpret_cast<const uint4*>(xh_s + srow * STG_V + shalf * 64);
+      uint4* dd = reinterpret_cast<uint4*>(dxg + (ws * 64 + shalf * 32) * 2);
+      dd[0] = xd[0]; dd[1] = xd[1]; dd[2] = xd[2]; dd[3] = xd[3];
+      const uint4* td = reinterpret_cast<const uint4*>(tq_s + srow * STG_V + shalf * 64);
+      uint4* qd = reinterpret_cast<uint4*>(A.tq_nhwc + padded_pixel(g, ws) * 64 + shalf * 32);
+      qd[0] = td[0]; qd[1] = td[1]; qd[2] = td[2]; qd[3] = td[3];
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+// GW[o][k] = sum_w v[w][o] patch_{code(w,o)}[w][k]  (+ the channel sums s0 = sum v, s1 = sum v xhat*, s2 = sum a_q dxhat*)
+// v = mask a_q (BASE) or the masked adjoint tangent at_q.  Per 16 windows: the [w][o] tile of v and of the codes (as
+// 16-bit) are staged in shared memory, ldmatrix.trans turns them into B fragments (pairs along w), the per-candidate
+// mask is two SIMD-in-word compares per register.
+template <int C, bool BASE>
+__global__ void __launch_bounds__(256) cb_reduce_mma_kernel(const CbArgs A, int64_t nmt) {
+  constexpr int CKK = C * 9;
+  __shared__ __align__(16) uint8_t stage[8][2 * MT * STG_V];
+  __shared__ float red[64][KP + NSUM];
+  const CbGeom& g = A.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int64_t total = (int64_t)g.N * g.HP * g.WP;
+  for (int i = tid; i < 64 * (KP + NSUM); i += 256) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  uint8_t* v_s = stage[warp];
+  uint8_t* c_s = v_s + MT * STG_V;
+  const uint4* pf = reinterpret_cast<const uint4*>(A.w.pfragT);
+  const uint8_t* xhg = reinterpret_cast<const uint8_t*>(A.w.xh);
+  const uint8_t* dxg = reinterpret_cast<const uint8_t*>(A.w.dxh);
+  const uint8_t* aqg = reinterpret_cast<const uint8_t*>(A.w.aqm);
+  const int srow = lane >> 1, shalf = lane & 1;
+  float gw[2][8][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) gw[m][j][r] = 0.f;
+  float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;     // channels 2*lane, 2*lane+1
+  // ldmatrix row address of this lane: matrix mi = lane>>3 -> (window block mi&1, channel block + (mi>>1))
+  const int lm_row = ((lane >> 3) & 1) * 8 + (lane & 7), lm_jo = lane >> 4;
+  for (int64_t mt = (int64_t)blockIdx.x * 8 + warp; mt < nmt; mt += (int64_t)gridDim.x * 8) {
+    const int64_t w0 = mt * MT;
+    uint4 af[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) af[q] = ldg_nc16(pf + (mt * 8 + q) * 32 + lane);
+    const int64_t ws = w0 + srow;
+    const bool live = ws < total;
+    {
+      uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+      uint32_t v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = 0u;
+      if (live) {
+        const uint8_t* cs = A.w.sel + ws * 64 + shalf * 32;
+        c0 = ldg_nc16(cs); c1 = ldg_nc16(cs + 16);
+        const uint8_t* vs = BASE ? aqg + (ws * 64 + shalf * 32) * 2
+                                 : reinterpret_cast<const uint8_t*>(A.atq_nhwc) + (padded_pixel(g, ws) * 64 + shalf * 32) * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint4 r = BASE ? ldg_nc16(vs + 16 * e) : *reinterpret_cast<const uint4*>(vs + 16 * e);
+          v[4 * e] = r.x; v[4 * e + 1] = r.y; v[4 * e + 2] = r.z; v[4 * e + 3] = r.w;
+        }
+      }
+      const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      uint32_t c16[16];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        c16[2 * e] = __byte_perm(cw[e], 0u, 0x4140);          // codes 0,1 of the word as two 16-bit lanes
+        c16[2 * e + 1] = __byte_perm(cw[e], 0u, 0x4342);      // codes 2,3
+      }
+      if (!BASE) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] &= __vcmpne2(c16[e] & 0x00040004u, 0u);      // relu mask (a_q m is pre-masked)
+      }
+      uint4* vd = reinterpret_cast<uint4*>(v_s + srow * STG_V + shalf * 64);
+      uint4* cd = reinterpret_cast<uint4*>(c_s + srow * STG_V + shalf * 64);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        vd[e] = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        cd[e] = make_uint4(c16[4 * e], c16[4 * e + 1], c16[4 * e + 2], c16[4 * e + 3]);
+      }
+    }
+    __syncwarp();
+    // channel sums: lane <-> channels 2*lane, 2*lane+1, loop over the tile's windows
+    {
+      const int nlive = (int)((total - w0) < MT ? (total - w0) : MT);
+#pragma unroll 4
+      for (int r = 0; r < MT; ++r) {
+        if (r >= nlive) break;
+        const int64_t gi = ((w0 + r) * 64 + 2 * lane) * 2;
+        const uint32_t vv = *reinterpret_cast<const uint32_t*>(v_s + r * STG_V + lane * 4);
+        const uint32_t xx = *reinterpret_cast<const uint32_t*>(xhg + gi);
+        const float va = __uint_as_float(vv << 16), vb = __uint_as_float(vv & 0xffff0000u);
+        s1a = fmaf(va, __uint_as_float(xx << 16), s1a);
+        s1b = fmaf(vb, __uint_as_float(xx & 0xffff0000u), s1b);
+        if (!BASE) {
+          const uint32_t aa = *reinterpret_cast<const uint32_t*>(aqg + gi), dd = *reinterpret_cast<const uint32_t*>(dxg + gi);
+          s2a = fmaf(__uint_as_float(aa << 16), __uint_as_float(dd << 16), s2a);
+          s2b = fmaf(__uint_as_float(aa & 0xffff0000u), __uint_as_float(dd & 0xffff0000u), s2b);
+        }
+      }
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      uint32_t bv[4], bc[4];
+      ldmatrix_x4_trans(bv, v_s + lm_row * STG_V + (2 * jp + lm_jo) * 16);
+      ldmatrix_x4_trans(bc, c_s + lm_row * STG_V + (2 * jp + lm_jo) * 16);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bc[e] &= 0x00030003u;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const uint32_t want = (uint32_t)d * 0x00010001u;
+        uint32_t m[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m[e] = bv[e] & __vcmpeq2(bc[e], want);
+#pragma unroll
+        for (int mk = 0; mk < 2; ++mk) {
+          mma16816(gw[mk][2 * jp], af[d * 2 + mk], m[0], m[1]);
+          mma16816(gw[mk][2 * jp + 1], af[d * 2 + mk], m[2], m[3]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // per-CTA partial row: taps k < CKK -> GW columns, k == CKK -> s0
+#pragma unroll
+  for (int mk = 0; mk < 2; ++mk)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = mk * 16 + gq + (r >> 1) * 8, o = j * 8 + 2 * t + (r & 1);
+        if (k < CKK)
+          atomicAdd(&red[o][k], gw[mk][j][r]);
+        else if (k == CKK)
+          atomicAdd(&red[o][KP + 0], gw[mk][j][r]);
+      }
+  atomicAdd(&red[2 * lane][KP + 1], s1a);
+  atomicAdd(&red[2 * lane + 1][KP + 1], s1b);
+  if (!BASE) {
+    atomicAdd(&red[2 * lane][KP + 2], s2a);
+    atomicAdd(&red[2 * lane + 1][KP + 2], s2b);
+  }
+  __syncthreads();
+  for (int i = tid; i < 64 * (KP + NSUM); i += 256) A.w.part[(size_t)blockIdx.x * 64 * (KP + NSUM) + i] = (&red[0][0])[i];
+}
+
 template <int C, typename PT>
 int run(const CbArgs& A0, int pass, cudaStream_t s) {
   CbArgs A = A0;
@@ -691,6 +1062,19 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_gram_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   if (smem_red > 200 * 1024) return BB_ERR_UNSUPPORTED;
+  // tensor-core path of the K-loop kernels: bf16 pooled arrays, 64 channels, NHWC neighbour on the pooled side
+  static const bool no_mma = getenv("BB200_NO_CBMMA") != nullptr;
+  const bool mma = !no_mma && g.O == 64 && sizeof(PT) == 2 && A.tq_nhwc && A.atq_nhwc && A.w.pfrag;
+  const int64_t nmt = ((int64_t)g.N * g.HP * g.WP + MT - 1) / MT;
+  auto mma_blocks = [&](const void* fn, size_t smem) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return (int)std::min<int64_t>((nmt + 7) / 8, (int64_t)std::min(per_sm * BB_SM_COUNT, GRID_MAX));
+  };
+  const size_t smem_tf_mma = 8 * MT * (STG_C + 2 * STG_V);
+  static BbOncePerDevice once_mma;
+  if (mma && once_mma.need())
+    BB_CUDA_TRY(cudaFuncSetAttribute(cb_tf_mma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tf_mma));
   // persistent grids: exactly the CTAs that are resident at once (a partial second wave would run at a fraction of
   // the occupancy for as long as a full one)
   auto resident = [&](const void* fn, size_t smem) {
@@ -714,24 +1098,44 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     int ggrid = g.N * bands < GRID_MAX ? g.N * bands : GRID_MAX;
     cb_gram_kernel<C><<<ggrid, NT, tile, s>>>(A);
     cb_gram_finish_kernel<<<8, 256, 0, s>>>(A);
-    const int grid = resident((const void*)cb_reduce_kernel<C, true, PT>, smem_red);
-    A.nparts = grid;
-    cb_reduce_kernel<C, true, PT><<<grid, NT, smem_red, s>>>(A);
+    if (mma) {
+      cb_patch_frag_kernel<C><<<8 * BB_SM_COUNT, 256, 0, s>>>(A, nmt);
+      const int mma_grid = mma_blocks((const void*)cb_reduce_mma_kernel<C, true>, 0);
+      A.nparts = mma_grid;
+      cb_reduce_mma_kernel<C, true><<<mma_grid, 256, 0, s>>>(A, nmt);
+      bb_launch_tally += 1;
+    } else {
+      const int grid = resident((const void*)cb_reduce_kernel<C, true, PT>, smem_red);
+      A.nparts = grid;
+      cb_reduce_kernel<C, true, PT><<<grid, NT, smem_red, s>>>(A);
+    }
     cb_finish_kernel<true><<<g.O, 64, 0, s>>>(A, C * 9);
     bb_launch_tally += 9;
     BB_LAUNCH_CHECK();
     return BB_OK;
   }
   if (pass == BB_PASS_TAN_FWD) {
+    if (mma) {
+      cb_tf_mma_kernel<C><<<mma_blocks((const void*)cb_tf_mma_kernel<C>, smem_tf_mma), 256, smem_tf_mma, s>>>(A, nmt);
+      bb_launch_tally += 1;
+      BB_LAUNCH_CHECK();
+      return BB_OK;
+    }
     const int grid = resident((const void*)cb_tf_kernel<C, PT>, smem_tf);
     cb_tf_kernel<C, PT><<<grid, NT, smem_tf, s>>>(A);
     bb_launch_tally += 1;
     BB_LAUNCH_CHECK();
     return BB_OK;
   }
-  const int grid = resident((const void*)cb_reduce_kernel<C, false, PT>, smem_red);
-  A.nparts = grid;
-  cb_reduce_kernel<C, false, PT><<<grid, NT, smem_red, s>>>(A);
+  if (mma) {
+    const int mma_grid = mma_blocks((const void*)cb_reduce_mma_kernel<C, false>, 0);
+    A.nparts = mma_grid;
+    cb_reduce_mma_kernel<C, false><<<mma_grid, 256, 0, s>>>(A, nmt);
+  } else {
+    const int grid = resident((const void*)cb_reduce_kernel<C, false, PT>, smem_red);
+    A.nparts = grid;
+    cb_reduce_kernel<C, false, PT><<<grid, NT, smem_red, s>>>(A);
+  }
   cb_finish_kernel<false><<<g.O, 64, 0, s>>>(A, C * 9);
   bb_launch_tally += 2;
   BB_LAUNCH_CHECK();

@@ -447,23 +447,25 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&o)[8]) {
   o[6] = __uint_as_float(r.w << 16); o[7] = __uint_as_float(r.w & 0xffff0000u);
 }
 template <bool BASE, bool ATQF32>
-__global__ void __launch_bounds__(256) cb2_dense_kernel(const A2 A) {
+__global__ void __launch_bounds__(256, 2) cb2_dense_kernel(const A2 A) {
   const G2& g = A.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, c0 = (lane & 7) * 8;
   const int dy = sub >> 1, dx = sub & 1;
-  const float* c = A.w.coef;
-  // r = k0 + k1 xhat + k2 t  with xhat = (y - mean) rstd  ->  e0 + e1 y + k2 t
-  F8 e0 = ld8f(c + c0), e1 = ld8f(c + 64 + c0);
-  const F8 k2 = ld8f(c + 128 + c0), k3 = ld8f(c + 192 + c0), k4 = ld8f(c + 256 + c0);
-  {
-    const F8 mean = ld8f(A.w.mean + c0), rstd = ld8f(A.w.rstd + c0);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      e1.v[e] *= rstd.v[e];
-      e0.v[e] -= e1.v[e] * mean.v[e];
-    }
+  // r = k0 + k1 xhat + k2 t  with xhat = (y - mean) rstd  ->  e0 + e1 y + k2 t; the five coefficient rows live in shared
+  // memory (40 registers less per thread: two CTAs per SM)
+  __shared__ __align__(16) float cf[5][64];
+  if (threadIdx.x < 64) {
+    const int o = threadIdx.x;
+    const float* c = A.w.coef;
+    const float e1 = c[64 + o] * A.w.rstd[o];
+    cf[0][o] = c[o] - e1 * A.w.mean[o];
+    cf[1][o] = e1;
+    cf[2][o] = c[128 + o];
+    cf[3][o] = c[192 + o];
+    cf[4][o] = c[256 + o];
   }
+  __syncthreads();
   const int HC = (g.H + 1) >> 1, WC = (g.W + 1) >> 1;
   const int64_t total = (int64_t)g.N * HC * WC;
   const bf16* __restrict__ yb = A.w.yb;
@@ -521,18 +523,24 @@ __global__ void __launch_bounds__(256) cb2_dense_kernel(const A2 A) {
         if (!BASE && !ATQF32) unpack8(at[u], b);
       }
       F8 v;
+      const F8 e0 = ld8f(&cf[0][c0]), e1 = ld8f(&cf[1][c0]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float r = fmaf(yv[e], e1.v[e], e0.v[e]);
-        if (!BASE) r = fmaf(t[e], k2.v[e], r);
-        if (pooled[u]) {
+      for (int e = 0; e < 8; ++e) v.v[e] = fmaf(yv[e], e1.v[e], e0.v[e]);
+      if (!BASE) {
+        const F8 k2 = ld8f(&cf[2][c0]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = fmaf(t[e], k2.v[e], v.v[e]);
+      }
+      if (pooled[u]) {
+        const F8 k3 = ld8f(&cf[3][c0]), k4 = ld8f(&cf[4][c0]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
           const unsigned code = ((e < 4 ? cd[u].x : cd[u].y) >> (8 * (e & 3))) & 0xffu;
           if ((code & 3u) == (unsigned)sub) {
-            r = fmaf(k4.v[e], a[e], r);
-            if (!BASE && (code & 4u)) r = fmaf(k3.v[e], ATQF32 ? atf[ATQF32 ? u : 0].v[e] : b[e], r);
+            v.v[e] = fmaf(k4.v[e], a[e], v.v[e]);
+            if (!BASE && (code & 4u)) v.v[e] = fmaf(k3.v[e], ATQF32 ? atf[ATQF32 ? u : 0].v[e] : b[e], v.v[e]);
           }
         }
-        v.v[e] = r;
       }
       st8(out + off[u], v);
     }
