@@ -177,6 +177,39 @@ __global__ void __launch_bounds__(256) cb_stats_kernel(const CbArgs A) {
   }
 }
 
+// bf16 y with HO*WO % 8 == 0: a warp per (image, channel) plane, 16-byte loads (the generic kernel above pays a 64-bit
+// division per element: 1.08 ms for 722 MB; this one streams)
+__global__ void __launch_bounds__(256) cb_stats_bf16_kernel(const CbArgs A) {
+  const int HW = A.g.HO * A.g.WO, lane = threadIdx.x & 31;
+  const int64_t planes = (int64_t)A.g.N * A.g.O;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(A.y);
+  for (int64_t pl = warp0; pl < planes; pl += nwarps) {
+    const uint4* src = reinterpret_cast<const uint4*>(y + pl * HW);
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = lane; i < HW / 8; i += 32) {
+      const uint4 r = src[i];
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xffff0000u);
+        s0 += a + b;
+        s1 = fmaf(a, a, fmaf(b, b, s1));
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if (lane == 0) {
+      const int o = (int)(pl % A.g.O);
+      atomicAdd(&A.w.dsum[o], (double)s0);
+      atomicAdd(&A.w.dsum[A.g.O + o], (double)s1);
+    }
+  }
+}
+
 __global__ void cb_stats_finish_kernel(const CbArgs A) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= A.g.O) return;
@@ -253,29 +286,45 @@ __device__ __forceinline__ float patch_dot(const float* xs, int base, int plane,
 // ---------------------------------------------------------------------------------------------------------------
 // base-backward preparation: arg-max codes, ReLU mask, xhat at the arg-max pixel, masked base adjoint (NHWC)
 // ---------------------------------------------------------------------------------------------------------------
+// One block per (image, pooled row): phase 1 walks the NCHW pooled tensors (idx / q / a_q: runs of WP contiguous
+// elements per channel) and fills a [WP][O] shared tile, phase 2 writes the channels-last rows in full 128-byte lines
+// (the element-per-thread version scattered three 1-2 byte stores per element: 2.45 ms at N=800).
 template <typename PT>
 __global__ void __launch_bounds__(256) cb_prep_kernel(const CbArgs A) {
+  extern __shared__ float prep_sm[];
   const CbGeom& g = A.g;
-  const int64_t total = (int64_t)g.N * g.HP * g.WP * g.O;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // i walks the NCHW pooled tensor (coalesced reads of idx / q / a_q); the NHWC writes are scattered, once per call
-    const int wp = (int)(i % g.WP);
-    int64_t r = i / g.WP;
-    const int hp = (int)(r % g.HP);
-    r /= g.HP;
-    const int o = (int)(r % g.O);
-    const int n = (int)(r / g.O);
+  const int n = blockIdx.x / g.HP, hp = blockIdx.x - n * g.HP;
+  const int cnt = g.WP * g.O;
+  float* xh_t = prep_sm;                       // [WP][O]
+  float* aq_t = prep_sm + cnt;                 // [WP][O]   (NCHW a_q only)
+  unsigned char* sel_t = reinterpret_cast<unsigned char*>(prep_sm + 2 * cnt);
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+    const int o = e / g.WP, wp = e - o * g.WP;
+    const int64_t i = (((int64_t)n * g.O + o) * g.HP + hp) * g.WP + wp;
     const int64_t id = A.idx[i];
     const int iy = (int)(id / g.WO), ix = (int)(id - (int64_t)iy * g.WO);
     const int dy = iy - 2 * hp, dx = ix - 2 * wp;
     const bool m = g.relu ? (bb::ldf(A.q, i, A.dtq) > 0.f) : true;
     const float yv = bb::ldf(A.y, ((int64_t)n * g.O + o) * g.HO * g.WO + id, A.dty);
-    const int64_t pi = (((int64_t)n * g.HP + hp) * g.WP + wp) * g.O + o;
-    A.w.sel[pi] = (unsigned char)((dy & 1) * 2 + (dx & 1) + (m ? 4 : 0));
-    stp<PT>(reinterpret_cast<PT*>(A.w.xh), pi, (yv - A.w.mean[o]) * A.w.rstd[o]);
-    const float aq = A.aq_nhwc ? __bfloat162float(A.aq_nhwc[((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + o])
-                               : A.a_q[i];
-    stp<PT>(reinterpret_cast<PT*>(A.w.aqm), pi, m ? aq : 0.f);
+    const int t = wp * g.O + o;
+    sel_t[t] = (unsigned char)((dy & 1) * 2 + (dx & 1) + (m ? 4 : 0));
+    xh_t[t] = (yv - A.w.mean[o]) * A.w.rstd[o];
+    if (!A.aq_nhwc) aq_t[t] = A.a_q[i];
+  }
+  __syncthreads();
+  const int64_t p0 = ((int64_t)n * g.HP + hp) * g.WP * g.O;
+  for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+    const unsigned char code = sel_t[t];
+    float aq;
+    if (A.aq_nhwc) {
+      const int wp = t / g.O, o = t - wp * g.O;
+      aq = __bfloat162float(A.aq_nhwc[((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + o]);
+    } else {
+      aq = aq_t[t];
+    }
+    A.w.sel[p0 + t] = code;
+    stp<PT>(reinterpret_cast<PT*>(A.w.xh), p0 + t, xh_t[t]);
+    stp<PT>(reinterpret_cast<PT*>(A.w.aqm), p0 + t, (code & 4) ? aq : 0.f);
   }
 }
 
@@ -707,52 +756,71 @@ __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
   return r;
 }
 
-// value of the patch matrix: window w (flat over N*HP*WP), candidate d = dy*2+dx, column k = (c*3+i)*3+j
-template <int C>
-__device__ __forceinline__ float patch_value(const CbArgs& A, int64_t w, int64_t total, int d, int k) {
-  const CbGeom& g = A.g;
-  if (w >= total || k > C * 9) return 0.f;
-  if (k == C * 9) return 1.f;
-  const int wp = (int)(w % g.WP);
-  const int64_t r = w / g.WP;
+// patch matrix: window w (flat over N*HP*WP), candidate d = dy*2+dx, column k = (c*3+i)*3+j; column C*9 holds 1
+struct WinPos {
+  int64_t base;     // index of x[n][0][2hp + dy - ph][2wp + dx - pw]
+  int iy0, ix0;
+  bool live;
+};
+__device__ __forceinline__ WinPos win_pos(const CbGeom& g, int C, int64_t w, int64_t total, int d) {
+  WinPos p;
+  p.live = w < total;
+  const int64_t ww = p.live ? w : 0;
+  const int wp = (int)(ww % g.WP);
+  const int64_t r = ww / g.WP;
   const int hp = (int)(r % g.HP), n = (int)(r / g.HP);
+  p.iy0 = 2 * hp + (d >> 1) - g.ph;
+  p.ix0 = 2 * wp + (d & 1) - g.pw;
+  p.base = (((int64_t)n * C) * g.H + p.iy0) * g.W + p.ix0;
+  return p;
+}
+template <int C>
+__device__ __forceinline__ float patch_value(const CbArgs& A, const WinPos& p, int k) {
+  if (!p.live || k > C * 9) return 0.f;
+  if (k == C * 9) return 1.f;
   const int c = k / 9, i = (k % 9) / 3, j = k % 3;
-  const int iy = 2 * hp + (d >> 1) + i - g.ph, ix = 2 * wp + (d & 1) + j - g.pw;
-  if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
-  return bb::ldf(A.x, (((int64_t)n * C + c) * g.H + iy) * g.W + ix, A.dtx);
+  const int iy = p.iy0 + i, ix = p.ix0 + j;
+  if (iy < 0 || iy >= A.g.H || ix < 0 || ix >= A.g.W) return 0.f;
+  return bb::ldf(A.x, p.base + ((int64_t)c * A.g.H + i) * A.g.W + j, A.dtx);
 }
 
-// one thread per (m-tile, fragment q, lane): q < 8 -> pfrag[d*2+ks], q >= 8 -> pfragT[d*2+mk]
+// one thread per (m-tile, candidate d, lane): the four fragments pfrag[d*2+ks] (rows = windows, columns = taps) and
+// pfragT[d*2+mk] (rows = taps, columns = windows) of its candidate
 template <int C>
 __global__ void __launch_bounds__(256) cb_patch_frag_kernel(const CbArgs A, int64_t nmt) {
   const int64_t total = (int64_t)A.g.N * A.g.HP * A.g.WP;
-  const int64_t nthreads = nmt * 16 * 32;
+  const int64_t nthreads = nmt * 4 * 32;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads; i += (int64_t)gridDim.x * blockDim.x) {
-    const int lane = (int)(i & 31), q = (int)((i >> 5) & 15);
-    const int64_t mt = i >> 9;
+    const int lane = (int)(i & 31), d = (int)((i >> 5) & 3);
+    const int64_t mt = i >> 7;
     const int gq = lane >> 2, t = lane & 3;
-    const int d = (q & 7) >> 1, hi = q & 1;
     const int64_t w0 = mt * MT;
-    float v[8];
-    if (q < 8) {
-      // A operand of the forward product: rows = windows, columns = taps hi*16 ..
+    uint4* pf = reinterpret_cast<uint4*>(A.w.pfrag) + (mt * 8 + d * 2) * 32 + lane;
+    uint4* pt = reinterpret_cast<uint4*>(A.w.pfragT) + (mt * 8 + d * 2) * 32 + lane;
+    {
+      const WinPos r0 = win_pos(A.g, C, w0 + gq, total, d), r1 = win_pos(A.g, C, w0 + gq + 8, total, d);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int row = gq + ((e >> 1) & 1) * 8, k = hi * 16 + 2 * t + (e & 1) + (e >> 2) * 8;
-        v[e] = patch_value<C>(A, w0 + row, total, d, k);
-      }
-    } else {
-      // A operand of the reduce product: rows = taps hi*16 .., columns = windows
+      for (int ks = 0; ks < 2; ++ks) {
+        float v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = hi * 16 + gq + ((e >> 1) & 1) * 8, wl = 2 * t + (e & 1) + (e >> 2) * 8;
-        v[e] = patch_value<C>(A, w0 + wl, total, d, k);
+        for (int e = 0; e < 8; ++e) v[e] = patch_value<C>(A, ((e >> 1) & 1) ? r1 : r0, ks * 16 + 2 * t + (e & 1) + (e >> 2) * 8);
+        pf[ks * 32] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
       }
     }
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    uint4* dst = reinterpret_cast<uint4*>(q < 8 ? A.w.pfrag : A.w.pfragT);
-    dst[(mt * 8 + (q & 7)) * 32 + lane] = o;
+    {
+      const WinPos c0 = win_pos(A.g, C, w0 + 2 * t, total, d), c1 = win_pos(A.g, C, w0 + 2 * t + 1, total, d);
+      const WinPos c2 = win_pos(A.g, C, w0 + 2 * t + 8, total, d), c3 = win_pos(A.g, C, w0 + 2 * t + 9, total, d);
+#pragma unroll
+      for (int mk = 0; mk < 2; ++mk) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = mk * 16 + gq + ((e >> 1) & 1) * 8;
+          v[e] = patch_value<C>(A, (e >> 2) ? ((e & 1) ? c3 : c2) : ((e & 1) ? c1 : c0), k);
+        }
+        pt[mk * 32] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      }
+    }
   }
 }
 
@@ -1060,8 +1128,9 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_reduce_kernel<C, false, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_reduce_kernel<C, true, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BB_CUDA_TRY(cudaFuncSetAttribute(cb_gram_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BB_CUDA_TRY(cudaFuncSetAttribute(cb_prep_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  if (smem_red > 200 * 1024) return BB_ERR_UNSUPPORTED;
+  if (smem_red > 200 * 1024 || (size_t)g.WP * g.O * 9 > 200 * 1024) return BB_ERR_UNSUPPORTED;
   // tensor-core path of the K-loop kernels: bf16 pooled arrays, 64 channels, NHWC neighbour on the pooled side
   static const bool no_mma = getenv("BB200_NO_CBMMA") != nullptr;
   const bool mma = !no_mma && g.O == 64 && sizeof(PT) == 2 && A.tq_nhwc && A.atq_nhwc && A.w.pfrag;
@@ -1091,9 +1160,12 @@ int run(const CbArgs& A0, int pass, cudaStream_t s) {
     int chunks = (int)((per + 256 * 64 - 1) / (256 * 64));
     if (chunks > 64) chunks = 64;
     if (chunks < 1) chunks = 1;
-    cb_stats_kernel<<<dim3(g.O, chunks), 256, 0, s>>>(A);
+    if (A.dty == BB_BF16 && (g.HO * g.WO) % 8 == 0)
+      cb_stats_bf16_kernel<<<8 * BB_SM_COUNT, 256, 0, s>>>(A);
+    else
+      cb_stats_kernel<<<dim3(g.O, chunks), 256, 0, s>>>(A);
     cb_stats_finish_kernel<<<1, 64, 0, s>>>(A);
-    cb_prep_kernel<PT><<<4 * BB_SM_COUNT, 256, 0, s>>>(A);
+    cb_prep_kernel<PT><<<g.N * g.HP, 256, (size_t)g.WP * g.O * 9, s>>>(A);
     const int bands = (g.HO + 2 * g.R - 1) / (2 * g.R);
     int ggrid = g.N * bands < GRID_MAX ? g.N * bands : GRID_MAX;
     cb_gram_kernel<C><<<ggrid, NT, tile, s>>>(A);

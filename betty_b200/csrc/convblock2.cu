@@ -143,46 +143,65 @@ __global__ void cb2_ystats_finish_kernel(const A2 A) {
   const double cnt = (double)A.g.N * A.g.H * A.g.W;
   const double mean = A.w.dsum[o] / cnt;
   const double var = A.w.dsum[64 + o] / cnt - mean * mean;
-  A.w.mean[o] = (float)mean;
-  A.w.rstd[o] = (float)rsqrt((var > 0 ? var : 0) + (double)A.eps);
+  const float mean_f = (float)mean, rstd_f = (float)rsqrt((var > 0 ? var : 0) + (double)A.eps);
+  A.w.mean[o] = mean_f;
+  A.w.rstd[o] = rstd_f;
+  // sum of xhat over y with the ROUNDED mean (what every kernel uses): (sum y - cnt mean_f) rstd_f, no second pass over y
+  A.w.dsum[9 * 64 + o] = (A.w.dsum[o] - cnt * (double)mean_f) * (double)rstd_f;
 }
 
 // pooled arrays (channels last) from the NCHW arg-max indices; per-channel Sa, Saxh; per-channel sum of xhat over y
+// One block per image, one pooled row per step: phase 1 walks the NCHW tensors (runs of WP contiguous elements per
+// channel) into a [WP][64] shared tile, phase 2 writes the channels-last rows in full lines and accumulates the channel
+// sums (thread t always owns channel t & 63).
 __global__ void __launch_bounds__(256) cb2_prep_kernel(const A2 A) {
-  __shared__ double red[32];
+  extern __shared__ float prep_sm[];
+  __shared__ double red[2][4][64];
   const G2& g = A.g;
-  const int o = blockIdx.x, PW = g.HP * g.WP, HW = g.H * g.W;
-  const float mean = A.w.mean[o], rstd = A.w.rstd[o];
-  double sa = 0, saxh = 0, sxh = 0;
-  for (int n = blockIdx.y; n < g.N; n += gridDim.y) {
-    const int64_t pbase = ((int64_t)n * 64 + o) * PW, ybase = ((int64_t)n * 64 + o) * HW;
-    for (int i = threadIdx.x; i < PW; i += blockDim.x) {
-      const int hp = i / g.WP, wp = i - hp * g.WP;
-      const int64_t id = A.idx[pbase + i];
+  const int n = blockIdx.x, PW = g.HP * g.WP, HW = g.H * g.W, cnt = g.WP * 64;
+  float* xh_t = prep_sm;
+  float* aq_t = prep_sm + cnt;
+  unsigned char* sel_t = reinterpret_cast<unsigned char*>(prep_sm + 2 * cnt);
+  const int o2 = threadIdx.x & 63;
+  double sa = 0, saxh = 0;
+  for (int hp = 0; hp < g.HP; ++hp) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+      const int o = e / g.WP, wp = e - o * g.WP;
+      const int64_t pi = ((int64_t)n * 64 + o) * PW + hp * g.WP + wp;
+      const int64_t id = A.idx[pi];
       const int iy = (int)(id / g.W), ix = (int)(id - (int64_t)iy * g.W);
-      const bool m = g.relu ? (bb::ldf(A.q, pbase + i, A.dtq) > 0.f) : true;
-      const float xh = (bb::ldf(A.y, ybase + id, A.dty) - mean) * rstd;
-      float aq = A.aq_nhwc ? __bfloat162float(A.aq_nhwc[((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + o])
-                           : A.aq_f32[pbase + i];
-      aq = m ? aq : 0.f;
-      const int64_t pi = (((int64_t)n * g.HP + hp) * g.WP + wp) * 64 + o;
-      A.w.sel[pi] = (unsigned char)(((iy - 2 * hp) & 1) * 2 + ((ix - 2 * wp) & 1) + (m ? 4 : 0));
-      A.w.xh[pi] = __float2bfloat16(xh);
-      A.w.aqm[pi] = __float2bfloat16(aq);
+      const bool m = g.relu ? (bb::ldf(A.q, pi, A.dtq) > 0.f) : true;
+      const int t = wp * 64 + o;
+      sel_t[t] = (unsigned char)(((iy - 2 * hp) & 1) * 2 + ((ix - 2 * wp) & 1) + (m ? 4 : 0));
+      xh_t[t] = (bb::ldf(A.y, ((int64_t)n * 64 + o) * HW + id, A.dty) - A.w.mean[o]) * A.w.rstd[o];
+      if (!A.aq_nhwc) aq_t[t] = A.aq_f32[pi];
+    }
+    __syncthreads();
+    const int64_t p0 = ((int64_t)n * g.HP + hp) * g.WP * 64;
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+      const unsigned char code = sel_t[t];
+      const int wp = t >> 6;
+      float aq = A.aq_nhwc ? __bfloat162float(A.aq_nhwc[((((int64_t)n * (g.HP + 2) + hp + 1) * (g.WP + 2)) + wp + 1) * 64 + o2])
+                           : aq_t[t];
+      aq = (code & 4) ? aq : 0.f;
+      const bf16 xb = __float2bfloat16(xh_t[t]), ab = __float2bfloat16(aq);
+      A.w.sel[p0 + t] = code;
+      A.w.xh[p0 + t] = xb;
+      A.w.aqm[p0 + t] = ab;
       // the sums use the values as the K-loop kernels will read them back (bf16)
-      const float aqr = __bfloat162float(__float2bfloat16(aq)), xhr = __bfloat162float(__float2bfloat16(xh));
+      const float aqr = __bfloat162float(ab), xhr = __bfloat162float(xb);
       sa += aqr;
       saxh += (double)aqr * xhr;
     }
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) sxh += (bb::ldf(A.y, ybase + i, A.dty) - mean) * rstd;
   }
-  sa = bb::block_sum<double>(sa, red);
-  saxh = bb::block_sum<double>(saxh, red);
-  sxh = bb::block_sum<double>(sxh, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&A.w.dsum[7 * 64 + o], sa);
-    atomicAdd(&A.w.dsum[8 * 64 + o], saxh);
-    atomicAdd(&A.w.dsum[9 * 64 + o], sxh);
+  red[0][threadIdx.x >> 6][o2] = sa;
+  red[1][threadIdx.x >> 6][o2] = saxh;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6;
+    const double v = red[which][0][o2] + red[which][1][o2] + red[which][2][o2] + red[which][3][o2];
+    atomicAdd(&A.w.dsum[(7 + which) * 64 + o2], v);
   }
 }
 
@@ -602,7 +621,7 @@ int bb_launch_convblock2(const bb_node& nd, int pass, cudaStream_t s) {
     BB_CUDA_TRY(cudaMemsetAsync(A.w.dsum, 0, sizeof(double) * 10 * 64, s));
     cb2_ystats_kernel<<<per_channel, 256, 0, s>>>(A);
     cb2_ystats_finish_kernel<<<1, 64, 0, s>>>(A);
-    cb2_prep_kernel<<<per_channel, 256, 0, s>>>(A);
+    cb2_prep_kernel<<<g.N, 256, (size_t)g.WP * 64 * 9, s>>>(A);
     cb2_pack_padded_kernel<<<dim3(g.N, g.H), 256, pack_smem, s>>>(A.y, A.dty, 64, g.H, g.W, A.w.yb);
     cb2_pack_padded_kernel<<<dim3(g.N, g.H), 256, pack_smem, s>>>(nd.base[0], nd.dt[0], 64, g.H, g.W, A.w.xin);
     A.base = 1;

@@ -80,7 +80,13 @@ def test_engine_matches_oracle_same_device(case, hvp_mode):
     want = ref_port.METHODS[rec["method"]](wl.vector, wl.lower, wl.upper, False)
     w_before = [p.detach().clone() for p in wl.lower.parameters()]
     got = H.jvp_fn_mapping[rec["method"]](wl.vector, wl.lower, wl.upper, False)
-    assert_close(got, want, _tolerance(rec, case), f"{case}[{hvp_mode}]")
+    tol = _tolerance(rec, case)
+    if hvp_mode == "autograd":
+        # test-only hybrid (products by torch autograd): BOTH sides are then fp32 runs with atomics in cuDNN / index_add,
+        # each `floor` away from fp64 and not run-to-run reproducible, so their distance can reach 2 x floor
+        # (lenet_cg: floor 6.1e-5, one 1.0e-4 miss in ~10 runs).  The native path is deterministic and keeps the hard bar.
+        tol = max(tol, 2 * _reference_floor(rec, case))
+    assert_close(got, want, tol, f"{case}[{hvp_mode}]")
     # inputs are borrowed: parameters restored / untouched (SURVEY §8b ownership)
     for a, b in zip(wl.lower.parameters(), w_before):
         assert torch.allclose(a, b, rtol=0, atol=1e-6)
