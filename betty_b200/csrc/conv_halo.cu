@@ -62,16 +62,6 @@ struct alignas(64) HaloArgs {
   int bo_mode;               // 1: descriptor base offset = (start >> 7) & 7 (PTX ISA), 0: always 0
 };
 
-__device__ __forceinline__ uint64_t desc_k_bo(uint32_t saddr, uint32_t bo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(bo & 7) << 49;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // Shared memory: [npairs x 9 x 8 KB] weights (resident for the whole kernel) | [NB x band_alloc] activation bands |
 // barriers.  The MMA issue loop must stay free of waits: a variant that streamed the second pair's weights through a
@@ -111,7 +101,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
 
   if (warp == 0) {
     // ---------------- TMA producer: activation bands (+ the resident weights once) ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       for (int p = 0; p < G.npairs; ++p) {
         tma_prefetch_desc(&G.a[p]);
         tma_prefetch_desc(&G.b[p]);
@@ -132,8 +122,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // One elected thread; everything the 36 instructions of a (tile, pair) need is a 32-bit add away: the descriptors'
+    // constant upper half, the nine tap offsets (in 16-byte units) and the weight tiles' addresses are set up once.
+    // With N = 64 an instruction is only ~34 clocks of tensor work, so every scalar instruction between two issues counts
+    // (the first version rebuilt both 64-bit descriptors per instruction and ran at ~108 clocks per instruction).
+    if (elect_one()) {
       const uint32_t idesc = idesc_bf16(BM, BN, false, false);
+      const uint64_t dhi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      uint32_t tap16[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int i = t / 3, j = t - 3 * i;
+        const int dy = G.flip ? 1 - i : i - 1, dx = G.flip ? 1 - j : j - 1;
+        tap16[t] = (uint32_t)((G.Wp + 1 + dy * G.Wp + dx) * 8);
+      }
+      const uint32_t w16 = (smem_u32(wsm) & 0x3FFFF) >> 4, band16_0 = (smem_u32(bands) & 0x3FFFF) >> 4;
+      const uint32_t band16_step = (uint32_t)G.band_alloc >> 4;
       mbar_wait(wfull, 0);
       tc_fence_after();
       int git = 0, lt = 0;
@@ -148,17 +152,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_halo_kernel(const __grid_con
           const int b = git % NB;
           mbar_wait(bfull0 + 8 * b, (git / NB) & 1);
           tc_fence_after();
-          const uint32_t band = smem_u32(bands + (size_t)b * G.band_alloc);
-#pragma unroll 1
+          const uint32_t band16 = band16_0 + (uint32_t)b * band16_step;
+          const uint32_t wp16 = w16 + (uint32_t)p * (9 * W_TILE >> 4);
+#pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const int i = t / 3, j = t - 3 * i;
-            const int dy = G.flip ? 1 - i : i - 1, dx = G.flip ? 1 - j : j - 1;
-            const uint32_t a0 = band + (uint32_t)((G.Wp + 1 + dy * G.Wp + dx) * 128);
-            const uint32_t bo = G.bo_mode ? ((a0 >> 7) & 7u) : 0u;
-            const uint32_t b0 = smem_u32(wsm + (p * 9 + t) * W_TILE);
+            const uint32_t alo = band16 + tap16[t], blo = wp16 + (uint32_t)t * (W_TILE >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tacc, desc_k_bo(a0 + k * 32, bo), desc_k(b0 + k * 32), idesc, (p > 0 || t > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tacc, dhi | (uint64_t)(alo + 2 * k), dhi | (uint64_t)(blo + 2 * k), idesc, (p > 0 || t > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(bempty0 + 8 * b);
         }
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo_kernel(const __grid_co
   const uint32_t bytes = (uint32_t)G.band_rows * 128u + (uint32_t)WH_G_BYTES;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int p = 0; p < G.npairs; ++p) {
         tma_prefetch_desc(&G.x[p]);
         tma_prefetch_desc(&G.g[p]);
@@ -314,22 +315,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_halo_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = idesc_bf16(128, 64, true, true);
+      // descriptor halves set up once (see conv_halo_kernel): per instruction only the 32-bit start addresses change
+      const uint64_t dhi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint64_t ghi = dhi | ((uint64_t)(8192 >> 4) << 16);
+      uint64_t xhi[5];
+      uint32_t x16[5];
+#pragma unroll
+      for (int tp = 0; tp < 5; ++tp) {
+        const int t1 = 2 * tp, t2 = (2 * tp + 1 < 9) ? 2 * tp + 1 : 2 * tp;
+        const int d1 = (t1 / 3 - 1) * G.Wp + (t1 % 3 - 1), d2 = (t2 / 3 - 1) * G.Wp + (t2 % 3 - 1);
+        const uint32_t lbo = t2 == t1 ? 128u : (uint32_t)((d2 - d1) * 128);   // (tap 8 alone: the upper half is ignored)
+        xhi[tp] = dhi | ((uint64_t)(lbo >> 4) << 16);
+        x16[tp] = (uint32_t)((G.Wp + 1 + d1) * 8);
+      }
       for (int it = 0; it < total; ++it) {
         const int s = it % G.stages;
         mbar_wait(full0 + 8 * s, (it / G.stages) & 1);
         tc_fence_after();
-        const uint32_t band = smem_u32(smem + s * WH_STAGE), g_addr = band + BAND_BYTES;
-#pragma unroll 1
+        const uint32_t band16 = (smem_u32(smem + s * WH_STAGE) & 0x3FFFF) >> 4, g16 = band16 + (BAND_BYTES >> 4);
+#pragma unroll
         for (int tp = 0; tp < 5; ++tp) {
-          const int t1 = 2 * tp, t2 = (2 * tp + 1 < 9) ? 2 * tp + 1 : 2 * tp;
-          const int d1 = (t1 / 3 - 1) * G.Wp + (t1 % 3 - 1), d2 = (t2 / 3 - 1) * G.Wp + (t2 % 3 - 1);
-          const uint32_t x_addr = band + (uint32_t)((G.Wp + 1 + d1) * 128);
-          const uint32_t lbo = t2 == t1 ? 128u : (uint32_t)((d2 - d1) * 128);   // (tap 8 alone: the upper half is ignored)
+          const uint32_t xa = band16 + x16[tp];
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_bf16(tmem_base + (uint32_t)(tp * 64), desc_mn(x_addr + ks * 2048, lbo), desc_mn(g_addr + ks * 2048, 8192),
+            umma_bf16(tmem_base + (uint32_t)(tp * 64), xhi[tp] | (uint64_t)(xa + ks * 128), ghi | (uint64_t)(g16 + ks * 128),
                       idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);

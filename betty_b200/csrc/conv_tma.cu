@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_c
   const int total = my_tiles * G.npairs;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int p = 0; p < G.npairs; ++p) {
         tma_prefetch_desc(&G.x[p]);
         tma_prefetch_desc(&G.g[p]);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = idesc_bf16(128, 64, true, true);
       const int ksteps = G.RK / 16;
       for (int it = 0; it < total; ++it) {

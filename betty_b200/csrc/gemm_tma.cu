@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       for (int p = 0; p < G.npairs; ++p) {
         tma_prefetch_desc(&G.a[p]);
         tma_prefetch_desc(&G.b[p]);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < total_kb; ++it) {
         const int s = it % STAGES;
         const int pair = it / nkb;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_persist_kernel(const __g
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       for (int p = 0; p < G.npairs; ++p) {
         tma_prefetch_desc(&G.a[p]);
         tma_prefetch_desc(&G.b[p]);
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tma_persist_kernel(const __g
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       int git = 0, lt = 0;   // lt = this CTA's tile counter
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;

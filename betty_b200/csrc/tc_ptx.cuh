@@ -75,6 +75,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// one thread of a converged warp; unlike `lane == 0` the compiler treats the guarded region as warp-uniform, so the
+// tcgen05.mma operands stay in uniform registers (no R2UR + ELECT/BRA.U.ANY loop around every instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
