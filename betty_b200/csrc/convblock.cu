@@ -915,10 +915,11 @@ __global__ void __launch_bounds__(256) cb_tf_mma_kernel(const CbArgs A, int64_t 
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int r = 0; r < 4; ++r) acc[d][j][r] = 0.f;
+      // ks outermost: 16 independent products between two that touch the same accumulator
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+        for (int j = 0; j < 4; ++j) {
           const uint2 b = bfrag[((h * 4 + j) * 2 + ks) * 32 + lane];
 #pragma unroll
           for (int d = 0; d < 4; ++d) mma16816(acc[d][j], af[d * 2 + ks], b.x, b.y);
@@ -973,7 +974,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 // 16-bit) are staged in shared memory, ldmatrix.trans turns them into B fragments (pairs along w), the per-candidate
 // mask is two SIMD-in-word compares per register.
 template <int C, bool BASE>
-__global__ void __launch_bounds__(256) cb_reduce_mma_kernel(const CbArgs A, int64_t nmt) {
+__global__ void __launch_bounds__(256, 2) cb_reduce_mma_kernel(const CbArgs A, int64_t nmt) {
   constexpr int CKK = C * 9;
   __shared__ __align__(16) uint8_t stage[8][2 * MT * STG_V];
   __shared__ float red[64][KP + NSUM];
