@@ -30,9 +30,17 @@ def get_grads(loss, path, retain_graph, do_sync):
     return jvp
 
 
-def install(reference_module=None):
-    """Rebind ``betty.hypergradient.jvp_fn_mapping`` entries to the B200 engine.  Returns the table."""
+def install(reference_module=None, callers: bool = False):
+    """Rebind ``betty.hypergradient.jvp_fn_mapping`` entries to the B200 engine.  Returns the table.
+    ``callers=True`` also rebinds the three caller-side methods of SURVEY.md §8 f4 (``betty_b200.callers``:
+    flat ``Problem.synchronize_params``, arena ``ImplicitProblem.cache_states`` / ``recover_states``)."""
     if reference_module is None:
         import betty.hypergradient as reference_module  # the user's installed reference
     reference_module.jvp_fn_mapping.update(jvp_fn_mapping)
+    if callers:
+        import importlib
+
+        from ..callers import install_callers
+
+        install_callers(importlib.import_module(reference_module.__name__.split(".")[0]))
     return reference_module.jvp_fn_mapping
