@@ -44,6 +44,9 @@ _SIGS = {
     "bb_fd_eps": ([C.c_void_p, C.c_double, C.c_void_p], 1),
     "bb_mt_fd_combine": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], 1),
     "bb_mt_adam_precondition": ([C.c_void_p, C.c_int, C.c_void_p], 1),
+    "bb_bn_forward_splits": ([C.c_int64, C.c_int], 0),
+    "bb_bn_forward": ([C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                       C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p], 3),
     "bb_gemm_bf16_tc": ([C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                          C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p], 1),
     "bb_gemm_bf16_tma": ([C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,

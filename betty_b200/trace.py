@@ -9,6 +9,7 @@ user code and the upper module); ``lower.py`` then turns the tape into the secon
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Any, Callable, List, Sequence, Tuple
 
@@ -41,6 +42,58 @@ class Tape:
     loss: torch.Tensor = None
 
 
+# ---- native prologue pieces ------------------------------------------------------------------------
+# Training-mode BatchNorm forward on a large channels-first CUDA activation: PyTorch launches one block per channel
+# (5.4 ms for 800 x 64 x 84 x 84 bf16, profiles/r02_launches_maml_final.csv); csrc/bn_fwd.cu does it in 0.4 ms.
+# The recorder executes those calls natively; everything else of the forward stays on PyTorch.
+_BN_FWD_OPS = {"aten.native_batch_norm.default": True, "aten._native_batch_norm_legit.default": True,
+               "aten._native_batch_norm_legit.no_stats": False}   # name -> has running statistics arguments
+native_bn_min_numel = int(os.environ.get("BB200_PROLOGUE_BN_MIN", str(1 << 20)))   # <= 0 disables
+native_bn_calls = 0
+
+
+def _native_bn_forward(name, args, kwargs):
+    """(out, save_mean, save_invstd) of a training-mode batch norm computed by bb_bn_forward, or None when this call
+    is left to PyTorch (small / CPU / eval mode / exotic layouts)."""
+    global native_bn_calls
+    if kwargs or native_bn_min_numel <= 0:
+        return None
+    if _BN_FWD_OPS[name]:
+        if len(args) != 8:
+            return None
+        x, w, b, rm, rv, training, momentum, eps = args
+    else:
+        if len(args) != 6:
+            return None
+        x, w, b, training, momentum, eps = args
+        rm = rv = None
+    if not (training and isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.is_contiguous()
+            and x.dtype in (torch.float32, torch.bfloat16) and x.numel() >= native_bn_min_numel
+            and x.shape[1] <= 65535 and x.numel() // x.shape[1] > 1):
+        return None
+    for t in (w, b, rm, rv):
+        if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            return None
+    from . import _native as N
+
+    n, c, hw = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        stats = torch.empty((3, c), dtype=torch.float32, device=x.device)
+        splits = N.lib().bb_bn_forward_splits(n, c)
+        ws = torch.empty(2 * c * splits, dtype=torch.float64, device=x.device)
+        N.call("bb_bn_forward", x.data_ptr(), 0 if x.dtype == torch.float32 else 1,
+               w.data_ptr() if w is not None else None, b.data_ptr() if b is not None else None, float(eps),
+               y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), ws.data_ptr(), n, c, hw,
+               torch.cuda.current_stream().cuda_stream)
+        if rm is not None:      # running statistics exactly as aten does: (1 - momentum) * running + momentum * batch
+            rm.mul_(1.0 - momentum).add_(stats[0], alpha=momentum)
+        if rv is not None:
+            rv.mul_(1.0 - momentum).add_(stats[2], alpha=momentum)
+    native_bn_calls += 1
+    return y, stats[0], stats[1]
+
+
 class _Recorder(TorchDispatchMode):
     def __init__(self, tape: Tape):
         super().__init__()
@@ -48,7 +101,14 @@ class _Recorder(TorchDispatchMode):
 
     def __torch_dispatch__(self, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
-        out = func(*args, **kwargs)
+        out = None
+        name = _NAMES.get(func)
+        if name is None:
+            name = _NAMES[func] = str(func)
+        if name in _BN_FWD_OPS:
+            out = _native_bn_forward(name, args, kwargs)
+        if out is None:
+            out = func(*args, **kwargs)
         # keeping args/out alive keeps id() stable and the base activations resident for the K-loop
         self.tape.ops.append(TapeOp(func, args, kwargs, out))
         return out

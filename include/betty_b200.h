@@ -82,6 +82,17 @@ typedef struct bb_mt_adam_chunk {
 } bb_mt_adam_chunk;
 int bb_mt_adam_precondition(const bb_mt_adam_chunk* table_dev, int nchunks, void* stream);
 
+/* ---- prologue: training-mode BatchNorm forward of the lower problem's own forward pass.
+ *      Replaces the aten.native_batch_norm(training=True) call PyTorch makes inside curr.training_step_exec
+ *      (reference neumann.py:31 / cg.py:27 run that forward once per call) for large channels-first CUDA
+ *      activations: x, y [N][C][HW] (dtype BB_F32 | BB_BF16), weight / bias fp32 [C] or NULL,
+ *      mean / invstd / var_unbiased fp32 [C] (var_unbiased may be NULL), ws >= 2 * C * bb_bn_forward_splits(N, C)
+ *      doubles.  out = weight * (x - mean) * invstd + bias, invstd = rsqrt(biased variance + eps); the statistics
+ *      are reduced in fp64 in a fixed order.  csrc/bn_fwd.cu                                                  */
+int bb_bn_forward_splits(int64_t N, int C);
+int bb_bn_forward(const void* x, int dtype, const float* weight, const float* bias, double eps, void* y, float* mean,
+                  float* invstd, float* var_unbiased, double* ws, int64_t N, int C, int64_t HW, void* stream);
+
 /* ---- K5-K9: second-order tape ("HVP plan").  Replaces reference neumann.py:62 / cg.py:39-41
  *      (torch.autograd.grad(in_grad, params, grad_outputs=v, retain_graph=True): reverse-over-reverse
  *      through the retained autograd graph) with forward-over-reverse over a recorded op list.
