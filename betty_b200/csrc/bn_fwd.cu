@@ -3,9 +3,10 @@
 // The prologue of every plugin call runs the user's lower forward once (reference neumann.py:31, cg.py:27).  On a
 // channels-first activation of 64 channels PyTorch's `batch_norm_collect_statistics_kernel` launches one block per
 // channel (64 blocks on 148 SMs, strided bf16 reads): 5.4 ms for 800 x 64 x 84 x 84 bf16 (profiles/
-// r02_launches_maml_final.csv, ids 9 / 21 / 33 / 45: 7.6 ms of the 13 ms forward).  The dispatch-mode recorder
-// (betty_b200/trace.py) therefore executes aten.native_batch_norm(training=True) on large CUDA inputs with these
-// three kernels instead -- same outputs (out, save_mean, save_invstd), same formula
+// r02_launches_maml_final.csv, ids 9 / 21 / 33 / 45: 7.6 ms of the 13 ms forward).  When asked to
+// (BB200_PROLOGUE_BN_MIN, opt-in: see profiles/r02_prologue_bn.md for why bit-identical base activations matter for the
+// bf16 parity bar) the dispatch-mode recorder (betty_b200/trace.py) executes aten.native_batch_norm(training=True) on
+// large CUDA inputs with these three kernels instead -- same outputs (out, save_mean, save_invstd), same formula
 //     out = gamma * (x - mean) * invstd + beta,   invstd = rsqrt(biased_var + eps)
 // with the statistics reduced in fp64 in a fixed order (bit-reproducible run to run):
 //

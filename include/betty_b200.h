@@ -85,7 +85,7 @@ int bb_mt_adam_precondition(const bb_mt_adam_chunk* table_dev, int nchunks, void
 /* ---- prologue: training-mode BatchNorm forward of the lower problem's own forward pass.
  *      Replaces the aten.native_batch_norm(training=True) call PyTorch makes inside curr.training_step_exec
  *      (reference neumann.py:31 / cg.py:27 run that forward once per call) for large channels-first CUDA
- *      activations: x, y [N][C][HW] (dtype BB_F32 | BB_BF16), weight / bias fp32 [C] or NULL,
+ *      activations -- opt-in, BB200_PROLOGUE_BN_MIN (profiles/r02_prologue_bn.md): x, y [N][C][HW] (dtype BB_F32 | BB_BF16), weight / bias fp32 [C] or NULL,
  *      mean / invstd / var_unbiased fp32 [C] (var_unbiased may be NULL), ws >= 2 * C * bb_bn_forward_splits(N, C)
  *      doubles.  out = weight * (x - mean) * invstd + bias, invstd = rsqrt(biased variance + eps); the statistics
  *      are reduced in fp64 in a fixed order.  csrc/bn_fwd.cu                                                  */
