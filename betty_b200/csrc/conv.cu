@@ -175,6 +175,22 @@ TcSrc wdgrad(const void* p, int dt, const Geom& g) {
   return s;
 }
 
+// second-generation small-channel kernels first (conv_small2.cu), the first generation when they decline
+int small_corr(const SmallConvArgs& A, cudaStream_t s) {
+  if (!getenv("BB200_CONV_SMALL_V1")) {
+    const int rc = bb_conv_small_corr2(A, s);
+    if (rc != BB_DECLINED) return rc;
+  }
+  return bb_conv_small_corr(A, s);
+}
+int small_wgrad(const SmallConvArgs& A, cudaStream_t s) {
+  if (!getenv("BB200_CONV_SMALL_V1")) {
+    const int rc = bb_conv_small_wgrad2(A, s);
+    if (rc != BB_DECLINED) return rc;
+  }
+  return bb_conv_small_wgrad(A, s);
+}
+
 }  // namespace
 
 int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
@@ -225,7 +241,7 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
     A.beta = 0;
     A.N = g.N; A.CI = g.C; A.H = g.H; A.W = g.W; A.CO = g.O; A.KH = g.KH; A.KW = g.KW; A.HO = g.HO; A.WO = g.WO;
     A.ph = g.ph; A.pw = g.pw; A.C_orig = g.C;
-    return bb_conv_small_corr(A, s);
+    return small_corr(A, s);
   }
   if (pass == BB_PASS_TAN_FWD) {
     WLoad la{};
@@ -265,7 +281,7 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
     A.beta = nd.beta[0];
     A.N = g.N; A.CI = g.O; A.H = g.HO; A.W = g.WO; A.CO = g.C; A.KH = g.KH; A.KW = g.KW; A.HO = g.H; A.WO = g.W;
     A.ph = g.KH - 1 - g.ph; A.pw = g.KW - 1 - g.pw; A.C_orig = g.C;
-    rc = bb_conv_small_corr(A, s);
+    rc = small_corr(A, s);
     if (rc) return rc;
   } else if (need & 1) {
     WLoadD la{};
@@ -309,7 +325,7 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
     A.out = out;
     A.N = g.N; A.CI = g.C; A.H = g.H; A.W = g.W; A.CO = g.O; A.KH = g.KH; A.KW = g.KW; A.HO = g.HO; A.WO = g.WO;
     A.ph = g.ph; A.pw = g.pw; A.C_orig = g.C;
-    rc = bb_conv_small_wgrad(A, s);
+    rc = small_wgrad(A, s);
     if (rc) return rc;
   } else if (need & 2) {
     GLoadW la{};

@@ -23,3 +23,8 @@ bool bb_conv_small_corr_ok(int CI, int CO, int KH, int KW, int npairs);
 int bb_conv_small_corr(const SmallConvArgs& A, cudaStream_t s);
 bool bb_conv_small_wgrad_ok(int O, int C, int H, int W, int HO, int WO, int KH, int KW);
 int bb_conv_small_wgrad(const SmallConvArgs& A, cudaStream_t s);
+
+// second generation (conv_small2.cu): shared-memory staged, warp-per-output-row correlation and channel-blocked weight
+// gradient; BB_DECLINED when the geometry does not fit (the callers then use the kernels above)
+int bb_conv_small_corr2(const SmallConvArgs& A, cudaStream_t s);
+int bb_conv_small_wgrad2(const SmallConvArgs& A, cudaStream_t s);
