@@ -39,7 +39,7 @@ WORKLOADS = {
     "neural_architecture_search_lite": ("neural_architecture_search", dict(batch=64, c=16, cells=4), "compact DARTS-style supernet c16 x 4 cells B=64, finite difference, fp32 (round-1 stand-in)"),
 }
 DEFAULT = "implicit_maml"      # the config BASELINE.json's ">=60 % HBM roofline on the Neumann K=20 path" is quoted on
-EXTRA = ("learning_to_reweight", "bert_data_reweighting")   # sub-records of the default run
+EXTRA = ("learning_to_reweight", "bert_data_reweighting", "neural_architecture_search")   # sub-records of the default run
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -441,7 +441,7 @@ def main():
     if "cpu_baseline" in main_rec:
         line["cpu_baseline"] = main_rec["cpu_baseline"]
     if extras:
-        # the other two headline configs of BASELINE.json (LeNet CG K=20 fp32; RoBERTa-base CG K=10 bf16) as
+        # the other headline configs of BASELINE.json (LeNet CG K=20 fp32; RoBERTa-base CG K=10 bf16; DARTS finite difference) as
         # sub-records of the same line: same timing rules, fewer steps
         line["extra"] = {}
         for name in extras:

@@ -24,22 +24,45 @@
 
 namespace {
 
+// ---- asynchronous staging (cp.async, 4-byte granules; src_size 0 = zero fill) -------------------------------------
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct Corr2Geom {
-  int XG, IMGS, RY, RS, CIC, pitch, S;   // x-groups per row, images per block, rows per block, staged rows, channel chunk,
-                                         // staged row pitch, image stride (floats)
+  int XG, IMGS, RY, RS, CIC, pitch, S, nbuf, VW, bands, groups;
+  // x-groups per row, images per unit, output rows per unit, staged rows (max over the bands), channel chunk, staged row
+  // pitch, image stride (floats), staging buffers, staging vector width (floats), row bands, image groups
 };
+
+template <int VW>
+__device__ __forceinline__ void cp_async_vec(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 * VW : 0;
+  if (VW == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+  else if (VW == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
 
 // accumulator-heavy instantiations (16 channels x 5 pixels) run with at most 12 warps so that ptxas may use 170 registers
 template <int CO_T, int PX>
 constexpr int corr2_max_threads() { return CO_T * PX > 64 ? 384 : 512; }
 
+// Persistent: a block walks work units u = blockIdx.x, +gridDim.x, ...; unit = (image group, row band).  The stages of
+// all its units -- (unit, operand pair, channel chunk) -- form one sequence that is double buffered: while stage k is
+// being computed the cp.asyncs of stage k+1 (possibly the next unit's images) are in flight.  The weights are staged once.
 template <int OP, int KW, int CO_T, int PX>
 __global__ void __launch_bounds__(corr2_max_threads<CO_T, PX>()) conv_small_corr2_kernel(const __grid_constant__ SmallConvArgs A,
                                                                 const __grid_constant__ Corr2Geom G) {
   extern __shared__ float sm2[];
   const int K = A.CI * A.KH * KW;
   float* wsm = sm2;                                  // [npairs][K][OP]
-  float* xs = sm2 + ((A.npairs * K * OP + 3) & ~3);  // [IMGS][CIC][RS][pitch] (image stride S)
+  float* xs = sm2 + ((A.npairs * K * OP + 3) & ~3);  // nbuf x [IMGS][CIC][RS][pitch] (image stride S)
   for (int e = threadIdx.x; e < A.npairs * K * OP; e += blockDim.x) {
     const int co = e % OP, k = (e / OP) % K, p = e / (OP * K);
     float v = 0.f;
@@ -52,90 +75,138 @@ __global__ void __launch_bounds__(corr2_max_threads<CO_T, PX>()) conv_small_corr
     }
     wsm[e] = v;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int y0 = blockIdx.y * G.RY;                  // first output row of this block
-  const int y = y0 + warp;
-  const int r0 = y0 - A.ph;                          // input row staged at index 0
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int img_l = lane / G.XG, xg = lane - img_l * G.XG;
   const int x0 = xg * PX;
-  const int64_t n = (int64_t)blockIdx.x * G.IMGS + img_l;
-  const bool active = img_l < G.IMGS && n < A.N && warp < G.RY && y < A.HO;
   constexpr int NV = PX + KW - 1;
+  const int nchunks = (A.CI + G.CIC - 1) / G.CIC;
+  const int nstages = A.npairs * nchunks;            // stages per unit
+  const int bufsz = G.IMGS * G.S;
+  const int units = G.groups * G.bands;
+  const int my_units = units > (int)blockIdx.x ? (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = my_units * nstages;
+  const int vpl = G.pitch / G.VW;                    // vectors per staged row
+
+  // geometry of unit k of this block
+  auto unit_geom = [&](int k, int& grp, int& y0, int& r0, int& rs) {
+    const int u = (int)blockIdx.x + k * (int)gridDim.x;
+    grp = u / G.bands;
+    y0 = (u - grp * G.bands) * G.RY;
+    r0 = max(y0 - A.ph, 0);     // input rows the band touches: [r0, r0 + rs), clipped to the image
+    rs = min(y0 + G.RY - 1 - A.ph + A.KH - 1, A.H - 1) - r0 + 1;
+  };
+
+  // issue the copies of global stage gst into buffer b; nothing waits here
+  auto stage = [&](int gst, int b) {
+    const int k = gst / nstages, st = gst - k * nstages;
+    int grp, y0, r0, rs;
+    unit_geom(k, grp, y0, r0, rs);
+    const int p = st / nchunks, c0 = (st - p * nchunks) * G.CIC;
+    const int cic = min(G.CIC, A.CI - c0);
+    const int imgs_here = (int)min((int64_t)G.IMGS, A.N - (int64_t)grp * G.IMGS);
+    float* buf = xs + b * bufsz;
+    const float* src0 = reinterpret_cast<const float*>(A.in[p]);
+    const bool f32 = A.dt_in[p] == BB_F32;
+    const int nvec = imgs_here * cic * rs * vpl;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const int ln = v / vpl, pc = (v - ln * vpl) * G.VW;
+      const int r = ln % rs, t = ln / rs, cl = t % cic, im = t / cic;
+      const int64_t base = ((((int64_t)grp * G.IMGS + im) * A.CI + c0 + cl) * A.H + (r0 + r)) * A.W;
+      float* dst = buf + im * G.S + (cl * G.RS + r) * G.pitch + pc;
+      const int col = pc - A.pw;
+      const bool ok = col >= 0 && col < A.W;          // a vector is entirely inside or outside (VW divides pw and W)
+      if (f32) {
+        const float* src = ok ? src0 + base + col : src0;
+        if (G.VW == 4) cp_async_vec<4>(dst, src, ok);
+        else if (G.VW == 2) cp_async_vec<2>(dst, src, ok);
+        else cp_async_vec<1>(dst, src, ok);
+      } else {
+        for (int q = 0; q < G.VW; ++q) dst[q] = ok ? bb::ldf(A.in[p], base + col + q, A.dt_in[p]) : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
 
   float acc[CO_T][PX];
+  if (total > 0) stage(0, 0);
+  for (int gst = 0; gst < total; ++gst) {
+    const int b = G.nbuf == 2 ? (gst & 1) : 0;
+    if (G.nbuf == 2 && gst + 1 < total) {
+      stage(gst + 1, b ^ 1);         // prefetch the next stage while this one is computed
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int k = gst / nstages, st = gst - k * nstages;
+    int grp, y0, r0, rs;
+    unit_geom(k, grp, y0, r0, rs);
+    const int y = y0 + warp;
+    const int64_t n = (int64_t)grp * G.IMGS + img_l;
+    const bool active = img_l < G.IMGS && n < A.N && warp < G.RY && y < A.HO;
+    if (st == 0) {
 #pragma unroll
-  for (int o = 0; o < CO_T; ++o)
+      for (int o = 0; o < CO_T; ++o)
 #pragma unroll
-    for (int q = 0; q < PX; ++q) acc[o][q] = 0.f;
-
-  const int imgs_here = (int)min((int64_t)G.IMGS, A.N - (int64_t)blockIdx.x * G.IMGS);
-  for (int p = 0; p < A.npairs; ++p) {
-    for (int c0 = 0; c0 < A.CI; c0 += G.CIC) {
+        for (int q = 0; q < PX; ++q) acc[o][q] = 0.f;
+    }
+    if (active) {
+      const int p = st / nchunks, c0 = (st - p * nchunks) * G.CIC;
       const int cic = min(G.CIC, A.CI - c0);
-      __syncthreads();
-      // stage: one (image, channel, row) line per warp step, lanes along the padded row
-      const int lines = imgs_here * cic * G.RS;
-      for (int ln = warp; ln < lines; ln += nwarps) {
-        const int r = ln % G.RS, t = ln / G.RS, cl = t % cic, im = t / cic;
-        const int hy = r0 + r;
-        float* dst = xs + im * G.S + (cl * G.RS + r) * G.pitch;
-        const bool rowok = hy >= 0 && hy < A.H;
-        const int64_t base = ((((int64_t)blockIdx.x * G.IMGS + im) * A.CI + c0 + cl) * A.H + hy) * A.W;
-        for (int pc = lane; pc < G.pitch; pc += 32) {
-          const int col = pc - A.pw;
-          dst[pc] = (rowok && col >= 0 && col < A.W) ? bb::ldf(A.in[p], base + col, A.dt_in[p]) : 0.f;
-        }
-      }
-      __syncthreads();
-      if (active) {
-        const float* wp = wsm + (int64_t)p * K * OP;
-        const float* img = xs + img_l * G.S + x0;
-        for (int cl = 0; cl < cic; ++cl) {
-          for (int i = 0; i < A.KH; ++i) {
-            const int hy = y - A.ph + i;
-            if (hy < 0 || hy >= A.H) continue;                  // warp-uniform: all lanes share y
-            const float* src = img + (cl * G.RS + (hy - r0)) * G.pitch;
-            float v[NV];
+      const float* wp = wsm + (int64_t)p * K * OP;
+      const float* img = xs + b * bufsz + img_l * G.S + x0;
+      for (int cl = 0; cl < cic; ++cl) {
+        for (int i = 0; i < A.KH; ++i) {
+          const int hy = y - A.ph + i;
+          if (hy < 0 || hy >= A.H) continue;                  // warp-uniform: all lanes share y
+          const float* src = img + (cl * G.RS + (hy - r0)) * G.pitch;
+          float v[NV];
 #pragma unroll
-            for (int q = 0; q < NV; ++q) v[q] = src[q];
-            const float* wr = wp + (((c0 + cl) * A.KH + i) * KW) * OP;
+          for (int q = 0; q < NV; ++q) v[q] = src[q];
+          const float* wr = wp + (((c0 + cl) * A.KH + i) * KW) * OP;
 #pragma unroll
-            for (int j = 0; j < KW; ++j) {
+          for (int j = 0; j < KW; ++j) {
 #pragma unroll
-              for (int o = 0; o < OP; o += 4) {
-                if (o >= CO_T) break;
-                float w4[4];
-                if (o + 4 <= CO_T) {
-                  const float4 t4 = *reinterpret_cast<const float4*>(wr + j * OP + o);
-                  w4[0] = t4.x; w4[1] = t4.y; w4[2] = t4.z; w4[3] = t4.w;
-                } else {
-                  const float2 t2 = *reinterpret_cast<const float2*>(wr + j * OP + o);
-                  w4[0] = t2.x; w4[1] = t2.y; w4[2] = 0.f; w4[3] = 0.f;
-                  if (o + 2 < CO_T) w4[2] = wr[j * OP + o + 2];
-                }
+            for (int o = 0; o < OP; o += 4) {
+              if (o >= CO_T) break;
+              float w4[4];
+              if (o + 4 <= CO_T) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wr + j * OP + o);
+                w4[0] = t4.x; w4[1] = t4.y; w4[2] = t4.z; w4[3] = t4.w;
+              } else {
+                const float2 t2 = *reinterpret_cast<const float2*>(wr + j * OP + o);
+                w4[0] = t2.x; w4[1] = t2.y; w4[2] = 0.f; w4[3] = 0.f;
+                if (o + 2 < CO_T) w4[2] = wr[j * OP + o + 2];
+              }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (o + u < CO_T) {
+              for (int u = 0; u < 4; ++u) {
+                if (o + u < CO_T) {
 #pragma unroll
-                    for (int q = 0; q < PX; ++q) acc[o + u][q] = fmaf(v[q + j], w4[u], acc[o + u][q]);
-                  }
+                  for (int q = 0; q < PX; ++q) acc[o + u][q] = fmaf(v[q + j], w4[u], acc[o + u][q]);
                 }
               }
             }
           }
         }
       }
+      if (st == nstages - 1) {
+#pragma unroll
+        for (int o = 0; o < CO_T; ++o) {
+          if (o >= A.CO) break;
+          const float bv = A.bias ? A.bias[o] : 0.f;
+          float* dst = A.out + ((n * A.CO + o) * A.HO + y) * A.WO + x0;
+#pragma unroll
+          for (int q = 0; q < PX; ++q) {
+            if (x0 + q < A.WO) dst[q] = A.beta ? dst[q] + acc[o][q] + bv : acc[o][q] + bv;
+          }
+        }
+      }
     }
-  }
-  if (!active) return;
-#pragma unroll
-  for (int o = 0; o < CO_T; ++o) {
-    if (o >= A.CO) break;
-    const float b = A.bias ? A.bias[o] : 0.f;
-    float* dst = A.out + ((n * A.CO + o) * A.HO + y) * A.WO + x0;
-#pragma unroll
-    for (int q = 0; q < PX; ++q) {
-      if (x0 + q < A.WO) dst[q] = A.beta ? dst[q] + acc[o][q] + b : acc[o][q] + b;
+    if (G.nbuf == 1 && gst + 1 < total) {
+      __syncthreads();
+      stage(gst + 1, 0);
+    } else if (gst + 2 < total) {
+      __syncthreads();               // buffer b is overwritten by the prefetch issued in the next iteration
     }
   }
 }
@@ -150,8 +221,8 @@ __global__ void __launch_bounds__(256) conv_small_wgrad2_kernel(const __grid_con
                                                                  const __grid_constant__ Wgrad2Geom G) {
   extern __shared__ float sm3[];
   const int O = A.CO, C = A.CI;
-  float* gs = sm3;                       // [HO][gp] with gp >= WO*OPs: pixel-major, channels last
-  float* is = sm3 + A.HO * G.gp;         // [C][iplane], rows of pitch ip
+  const int bufsz = (A.HO * G.gp + C * G.iplane + 3) & ~3;   // one staged (image, pair): gs [HO][gp] pixel-major, channels
+                                                             // last | is [C][iplane], rows of pitch ip
   const int t = threadIdx.x;
   const int task = t % G.tasks, slice = t / G.tasks;
   const bool live = slice < G.ns;
@@ -161,22 +232,65 @@ __global__ void __launch_bounds__(256) conv_small_wgrad2_kernel(const __grid_con
   for (int o = 0; o < OB; ++o)
 #pragma unroll
     for (int j = 0; j < KW; ++j) acc[o][j] = 0.f;
-  const int HWo = A.HO * A.WO, gsz = O * HWo, isz = C * A.H * A.W;
-  for (int n = blockIdx.x; n < A.N; n += gridDim.x) {
-    for (int p = 0; p < A.npairs; ++p) {
-      __syncthreads();
-      // g[n][o][y][x] -> gs[y][x][o]: lanes run over (pixel, o) with o fastest, so the shared-memory stores of a warp
-      // are consecutive words; the strided global reads stay in L1 across the loop (one image is a few KB)
-      for (int e = t; e < HWo * G.OPs; e += blockDim.x) {
-        const int o = e % G.OPs, px = e / G.OPs, yy = px / A.WO, xx = px - yy * A.WO;
-        gs[yy * G.gp + xx * G.OPs + o] = o < O ? bb::ldf(A.g[p], (int64_t)n * gsz + (int64_t)o * HWo + px, A.dt_g[p]) : 0.f;
+  const int HWo = A.HO * A.WO, gsz = O * HWo, HWi = A.H * A.W, isz = C * HWi;
+  // the padding channels (o >= O) of both buffers are never staged: zero them once
+  for (int e = t; e < 2 * bufsz; e += blockDim.x) sm3[e] = 0.f;
+  __syncthreads();
+
+  // stage image n, pair p into buffer b.  g[n][o][y][x] -> gs[y][x][o]: the threads run along the pixels of one channel
+  // plane (coalesced global reads), every element is one 4-byte cp.async; indices advance without divisions.
+  auto stage = [&](int64_t n, int p, int b) {
+    float* gs = sm3 + b * bufsz;
+    float* is = gs + A.HO * G.gp;
+    const bool gf32 = A.dt_g[p] == BB_F32, if32 = A.dt_in[p] == BB_F32;
+    const float* gsrc = reinterpret_cast<const float*>(A.g[p]) + n * gsz;
+    const float* isrc = reinterpret_cast<const float*>(A.in[p]) + n * isz;
+    {
+      int yy = t / A.WO, xx = t - yy * A.WO;
+      const int dy = (int)blockDim.x / A.WO, dx = (int)blockDim.x - dy * A.WO;
+      for (int px = t; px < HWo; px += blockDim.x) {
+        float* dst = gs + yy * G.gp + xx * G.OPs;
+        for (int o = 0; o < O; ++o) {
+          if (gf32) cp_async4(dst + o, gsrc + (int64_t)o * HWo + px, true);
+          else dst[o] = bb::ldf(A.g[p], n * gsz + (int64_t)o * HWo + px, A.dt_g[p]);
+        }
+        xx += dx; yy += dy;
+        if (xx >= A.WO) { xx -= A.WO; ++yy; }
       }
-      for (int e = t; e < isz; e += blockDim.x) {
-        const int pl = e / (A.H * A.W), r = e - pl * (A.H * A.W), yy = r / A.W, xx = r - yy * A.W;
-        is[pl * G.iplane + yy * G.ip + xx] = bb::ldf(A.in[p], (int64_t)n * isz + e, A.dt_in[p]);
+    }
+    {
+      int yy = t / A.W, xx = t - yy * A.W;
+      const int dy = (int)blockDim.x / A.W, dx = (int)blockDim.x - dy * A.W;
+      for (int px = t; px < HWi; px += blockDim.x) {
+        float* dst = is + yy * G.ip + xx;
+        for (int c = 0; c < C; ++c) {
+          if (if32) cp_async4(dst + c * G.iplane, isrc + (int64_t)c * HWi + px, true);
+          else dst[c * G.iplane] = bb::ldf(A.in[p], n * isz + (int64_t)c * HWi + px, A.dt_in[p]);
+        }
+        xx += dx; yy += dy;
+        if (xx >= A.W) { xx -= A.W; ++yy; }
       }
-      __syncthreads();
-      if (!live) continue;
+    }
+    cp_async_commit();
+  };
+
+  // work items of this block: (image, pair) pairs, double buffered
+  const int64_t nimg = A.N > blockIdx.x ? (A.N - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t items = nimg * A.npairs;
+  if (items > 0) stage(blockIdx.x, 0, 0);
+  for (int64_t it = 0; it < items; ++it) {
+    const int b = (int)(it & 1);
+    if (it + 1 < items) {
+      const int64_t nx = (it + 1) / A.npairs;
+      stage(blockIdx.x + nx * gridDim.x, (int)(it + 1 - nx * A.npairs), b ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* gs = sm3 + b * bufsz;
+    const float* is = gs + A.HO * G.gp;
+    if (live) {
       for (int y = slice; y < A.HO; y += G.ns) {
         const int hy = y - A.ph + ti;
         if (hy < 0 || hy >= A.H) continue;
@@ -235,6 +349,7 @@ __global__ void __launch_bounds__(256) conv_small_wgrad2_kernel(const __grid_con
         }
       }
     }
+    if (it + 2 < items) __syncthreads();   // buffer b is refilled by the prefetch of the next iteration
   }
   if (!live) return;
 #pragma unroll
@@ -248,7 +363,7 @@ __global__ void __launch_bounds__(256) conv_small_wgrad2_kernel(const __grid_con
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
-constexpr int kCorr2SmemCap = 100 * 1024;   // two blocks per SM
+constexpr int kCorr2SmemCap = 216 * 1024;   // one block per SM, double-buffered staging
 
 bool corr2_plan(const SmallConvArgs& A, int OP, int& PX, Corr2Geom& G, size_t& smem) {
   if (A.HO < 1 || A.WO < 1) return false;
@@ -274,8 +389,18 @@ bool corr2_plan(const SmallConvArgs& A, int OP, int& PX, Corr2Geom& G, size_t& s
   const int maxw = (OP * PX > 64 ? 384 : 512) / 32;    // == corr2_max_threads / 32 (CO_T * PX > 64 only for OP = 16)
   const int nb = (A.HO + maxw - 1) / maxw;
   G.RY = (A.HO + nb - 1) / nb;                         // equal bands of <= maxw rows
-  G.RS = G.RY + A.KH - 1;
+  G.RS = G.RY + A.KH - 1 < A.H ? G.RY + A.KH - 1 : A.H;   // a band never needs more rows than the image has
   G.pitch = G.XG * PX + A.KW - 1;
+  // staging vector width: columns [-pw, 0) and [W, ...) are zero fill, so a vector must not straddle those borders
+  G.VW = 1;
+  if (A.W % 2 == 0 && A.pw % 2 == 0) G.VW = 2;
+  if (A.W % 4 == 0 && A.pw % 4 == 0) G.VW = 4;
+  for (int p = 0; p < A.npairs; ++p)
+    if (reinterpret_cast<uintptr_t>(A.in[p]) % 16) G.VW = 1;
+  if (getenv("BB200_CORR2_VW1")) G.VW = 1;
+  G.pitch = (G.pitch + G.VW - 1) / G.VW * G.VW;
+  G.bands = (A.HO + G.RY - 1) / G.RY;
+  G.groups = (int)((A.N + G.IMGS - 1) / G.IMGS);
   const size_t wbytes = sizeof(float) * (((size_t)A.npairs * A.CI * A.KH * A.KW * OP + 3) & ~(size_t)3);
   for (int cic = A.CI; cic >= 1; --cic) {
     int S = cic * G.RS * G.pitch;
@@ -286,11 +411,15 @@ bool corr2_plan(const SmallConvArgs& A, int OP, int& PX, Corr2Geom& G, size_t& s
       for (int l = 0; l < G.IMGS * G.XG; ++l) conf += cnt[((l / G.XG) * s + (l % G.XG) * PX) & 31]++;
       if (conf < best_conf) { best_conf = conf; best_s = s; }
     }
+    // image stride: multiple of the staging vector width, residue (mod 32) as close to the conflict-free one as that allows
     S += ((best_s - S) % 32 + 32) % 32;
-    const size_t bytes = wbytes + sizeof(float) * (size_t)G.IMGS * S;
+    S = (S + G.VW - 1) / G.VW * G.VW;
+    const int nbuf = 2;
+    const size_t bytes = wbytes + sizeof(float) * (size_t)nbuf * G.IMGS * S;
     if (bytes <= (size_t)kCorr2SmemCap) {
       G.CIC = cic;
       G.S = S;
+      G.nbuf = nbuf;
       smem = bytes;
       return true;
     }
@@ -304,7 +433,8 @@ int launch_corr2(const SmallConvArgs& A, const Corr2Geom& G, size_t smem, cudaSt
   if (configured.need())
     BB_CUDA_TRY(cudaFuncSetAttribute(conv_small_corr2_kernel<OP, KW, CO_T, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kCorr2SmemCap));
-  const dim3 grid((unsigned)((A.N + G.IMGS - 1) / G.IMGS), (unsigned)((A.HO + G.RY - 1) / G.RY));
+  const int units = G.groups * G.bands;
+  const int grid = units < BB_SM_COUNT ? units : BB_SM_COUNT;     // one persistent block per SM
   conv_small_corr2_kernel<OP, KW, CO_T, PX><<<grid, G.RY * 32, smem, s>>>(A, G);
   bb_launch_tally += 1;
   BB_LAUNCH_CHECK();
@@ -321,25 +451,41 @@ int dispatch_px(const SmallConvArgs& A, int PX, const Corr2Geom& G, size_t smem,
   return BB_DECLINED;
 }
 
+constexpr int kWgrad2SmemCap = 100 * 1024;
+
 bool wgrad2_plan(const SmallConvArgs& A, int OB, Wgrad2Geom& G, size_t& smem) {
   const int O = A.CO, C = A.CI;
   G.OG = (O + OB - 1) / OB;
   G.OPs = (G.OG * OB + 3) & ~3;
   G.tasks = G.OG * C * A.KH;
   if (G.tasks > 256 || G.tasks < 1) return false;
+  // measured (profiles/r02_lenet_small_conv.md): with few tasks per image (LeNet conv1: 15) a block needs ~17 row slices
+  // and its per-image barriers dominate -- the first-generation kernel is faster there (0.32 vs 0.43 ms)
+  if (G.tasks < 64 && !getenv("BB200_WGRAD2_ALWAYS")) return false;
   G.ns = 256 / G.tasks;
   if (G.ns > A.HO) G.ns = A.HO;
+  {   // fewest slices with the same maximum of rows per slice: every slice gets (nearly) the same work between barriers
+    const int rows = (A.HO + G.ns - 1) / G.ns;
+    G.ns = (A.HO + rows - 1) / rows;
+  }
   const int row = A.WO * G.OPs;
   G.gp = row + (((G.OPs - row) % 32) + 32) % 32;      // gp mod 32 == OPs mod 32: the row slices of a warp hit distinct banks
   G.ip = A.W | 1;
   G.iplane = (A.H * G.ip) | 1;
-  smem = sizeof(float) * ((size_t)A.HO * G.gp + (size_t)C * G.iplane);
-  return smem <= 48 * 1024;
+  smem = sizeof(float) * 2 * (((size_t)A.HO * G.gp + (size_t)C * G.iplane + 3) & ~(size_t)3);   // double buffered
+  return smem <= (size_t)kWgrad2SmemCap;
 }
 
 template <int KW, int OB>
 int launch_wgrad2(const SmallConvArgs& A, const Wgrad2Geom& G, size_t smem, cudaStream_t s) {
-  int grid = BB_SM_COUNT * 4;
+  static BbOncePerDevice configured;
+  if (configured.need())
+    BB_CUDA_TRY(cudaFuncSetAttribute(conv_small_wgrad2_kernel<KW, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kWgrad2SmemCap));
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm > 6) per_sm = 6;
+  if (per_sm < 1) per_sm = 1;
+  int grid = BB_SM_COUNT * per_sm;
   if (grid > A.N) grid = A.N;
   conv_small_wgrad2_kernel<KW, OB><<<grid, 256, smem, s>>>(A, G);
   bb_launch_tally += 1;
