@@ -136,11 +136,40 @@ int launch(const LA& la, const LB& lb, const SC& sc, int64_t M, int64_t N, int64
 }
 
 // out[ch] += sum_{img, q} g[(img*CH + ch)*HW + q]
-__global__ void __launch_bounds__(256) chansum_kernel(const float* __restrict__ g, float* out, int NIMG, int CH, int HW) {
+__global__ void __launch_bounds__(256) chansum_kernel(const float* __restrict__ g, float* out, int NIMG, int CH, int HW,
+                                                      int small_max) {
   __shared__ float red[32];
   const int ch = blockIdx.x;
   float acc = 0.f;
   const bool vec = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  if (HW <= small_max) {
+    // small planes (LeNet conv2: 100 elements): a block per plane would keep 25 of 256 threads busy.  A warp per
+    // plane instead, four planes in flight per warp.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int wstride = gridDim.y * nw;
+    for (int img0 = blockIdx.y * nw + warp; img0 < NIMG; img0 += 4 * wstride) {
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int img = img0 + u * wstride;
+        if (img < NIMG) {
+          const float* src = g + ((int64_t)img * CH + ch) * HW;
+          if (vec) {
+            for (int q = lane * 4; q < HW; q += 128) {
+              const float4 v = bb::ld4_stream(src + q);
+              part[u] += (v.x + v.y) + (v.z + v.w);
+            }
+          } else {
+            for (int q = lane; q < HW; q += 32) part[u] += src[q];
+          }
+        }
+      }
+      acc += (part[0] + part[1]) + (part[2] + part[3]);
+    }
+    acc = bb::block_sum<float>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out + ch, acc);
+    return;
+  }
   for (int img = blockIdx.y; img < NIMG; img += gridDim.y) {
     const float* src = g + ((int64_t)img * CH + ch) * HW;
     if (vec) {
@@ -356,7 +385,8 @@ int bb_launch_conv2d(const bb_node& nd, int pass, cudaStream_t s) {
       bb_launch_tally += 1;
     }
     int gy_blocks = g.N < 64 ? g.N : 64;
-    chansum_kernel<<<dim3(g.O, gy_blocks), 256, 0, s>>>(reinterpret_cast<const float*>(gy), out, g.N, g.O, g.HO * g.WO);
+    static const int small_max = getenv("BB200_CHANSUM_V1") ? 0 : 512;
+    chansum_kernel<<<dim3(g.O, gy_blocks), 256, 0, s>>>(reinterpret_cast<const float*>(gy), out, g.N, g.O, g.HO * g.WO, small_max);
     bb_launch_tally += 1;
     BB_LAUNCH_CHECK();
   }

@@ -124,7 +124,10 @@ int run_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int npairs, const M
   const bool small_m = M <= 16, small_n = N <= 16 && !small_m;
   // 64x64 tiles unless that leaves most SMs idle: then 32x32 tiles (4x the CTAs)
   const int64_t tiles64 = ((M + 63) / 64) * ((N + 63) / 64) * batch;
-  const bool mid = !small_m && !small_n && tiles64 < 2 * BB_SM_COUNT;
+  // measured on LeNet B=4096 (profiles/r02_lenet_small_conv.md): 128 tiles of 64x64 (4x4 per thread) beat 512 tiles of
+  // 32x32 (2x2 per thread, one shared-memory load per FMA) -- only below ~64 big tiles do the small ones pay
+  static const int mid_below = getenv("BB200_GEMM_MID") ? atoi(getenv("BB200_GEMM_MID")) : 64;
+  const bool mid = !small_m && !small_n && tiles64 < mid_below;
   const int BM = small_m ? 16 : (mid ? 32 : 64), BN = small_n ? 16 : (mid ? 32 : 64);
   const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
   int ksplit = 1;
