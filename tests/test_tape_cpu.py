@@ -305,3 +305,23 @@ def test_side_computations_without_a_rule_do_not_abort():
 
     g = _hvp_against_autograd(wl, step)
     assert all(n.op != "poison" for n in g.nodes)
+
+
+def test_native_prologue_batchnorm_is_opt_in_and_never_touches_cpu_tensors(monkeypatch):
+    """The recorder substitutes aten.native_batch_norm only when asked to (BB200_PROLOGUE_BN_MIN) and only for CUDA
+    inputs (betty_b200/trace.py, profiles/r02_prologue_bn.md): by default the lower forward is PyTorch's, bit for bit."""
+    import torch
+
+    from betty_b200 import trace as T
+
+    assert T.native_bn_min_numel <= 0 or "BB200_PROLOGUE_BN_MIN" in __import__("os").environ
+    net = torch.nn.Sequential(torch.nn.Conv2d(2, 4, 3, padding=1), torch.nn.BatchNorm2d(4))
+    x = torch.randn(3, 2, 6, 6)
+    want = net(x).sum()
+    for thr in (0, 1):
+        monkeypatch.setattr(T, "native_bn_min_numel", thr)
+        before = T.native_bn_calls
+        loss, tape = T.record_tape(lambda: net(x).sum(), list(net.parameters()))
+        assert T.native_bn_calls == before                       # CPU input: left to PyTorch even when switched on
+        assert any(op.name in T._BN_FWD_OPS or "batch_norm" in op.name for op in tape.ops)
+        assert torch.equal(loss.detach(), want.detach())
