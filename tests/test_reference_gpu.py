@@ -69,15 +69,22 @@ def test_install_is_a_drop_in_for_the_real_engine(case, reference_table):
     engine, upper, lower = R.real_problems(wl, upper_step, strategy="gpu")
     assert next(lower.module.parameters()).is_cuda and lower.cur_batch[0].is_cuda
     want = R.hypergradient_through_reference(upper, lower)          # the reference's own plugin, same GPU
+    # the reference's fp32 result on a GPU is not bit-reproducible (atomics in cuDNN / index_add backward); where two
+    # runs of the REFERENCE differ by more than 2e-5 the 1e-4 bar is widened by exactly that measured self-distance
+    # (profiles/r02_parity_noise.md) -- on every case seen so far it is not
+    again = R.hypergradient_through_reference(upper, lower)
+    self_dist = rel_l2(again, want)
+    tol = 1e-4 if self_dist <= 2e-5 else 1e-4 + self_dist
+    print(f"[reference parity] {case}: reference-vs-reference {self_dist:.3e}, tolerance {tol:.2e}")
     table = betty_b200.install()
     assert table is reference_table.jvp_fn_mapping and table["cg"].__module__.startswith("betty_b200")
     got = R.hypergradient_through_reference(upper, lower)
-    assert_close(got, want, 1e-4, case)
+    assert_close(got, want, tol, case)
     # sync=True: accumulate into .grad (through autograd.backward, so a DDP reducer would fire) and return None
     for p in upper.trainable_parameters():
         p.grad = None
     assert R.hypergradient_through_reference(upper, lower, do_sync=True) is None
-    assert_close([p.grad for p in upper.trainable_parameters()], want, 1e-4, case + " sync")
+    assert_close([p.grad for p in upper.trainable_parameters()], want, tol, case + " sync")
 
 
 def test_reference_regression_suite_on_the_rebound_table(reference_table):
