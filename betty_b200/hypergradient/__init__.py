@@ -5,13 +5,16 @@ named by BASELINE.json; the reference calls the same algorithm ``darts``, SURVEY
 the ``Config(type=...)`` selector are used unchanged (reference betty/hypergradient/__init__.py:13-19).
 """
 from .cg import cg
+from .cg_global import cg_global
 from .darts import darts
 from .neumann import neumann
 from .sama import sama
 
 finite_diff = darts
 
-jvp_fn_mapping = {"darts": darts, "finite_diff": darts, "sama": sama, "neumann": neumann, "cg": cg}
+# "cg_global" is an ADDITION to the reference's table (global-batch CG with rank-sharded vectors, SURVEY.md 8e optional
+# variant); the other keys replace the reference's entries one for one
+jvp_fn_mapping = {"darts": darts, "finite_diff": darts, "sama": sama, "neumann": neumann, "cg": cg, "cg_global": cg_global}
 
 
 def get_grads(loss, path, retain_graph, do_sync):
