@@ -454,7 +454,11 @@ def main():
         # sub-records of the same line: same timing rules, fewer steps
         line["extra"] = {}
         for name in extras:
-            r = measure(name, args, dev, dist, world, rank, local, max(3, args.steps // 2), 3, with_cpu)
+            try:
+                r = measure(name, args, dev, dist, world, rank, local, max(3, args.steps // 2), 3, with_cpu)
+            except Exception as exc:      # a sub-record must never cost the headline line
+                line["extra"][name] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+                continue
             line["extra"][name] = r
             line["gpu_launches"] += r["gpu_launches"] + r["e2e"]["gpu_launches"]
     if rank == 0:
